@@ -1,0 +1,343 @@
+// Exact-fp32 convolution kernels (FFMA pipe): the parity path for every nn.Conv2d on the
+// flow path and the GEMMs that are expressed as per-sample 1x1 convolutions.
+//
+// Implicit GEMM, NHWC:  M = out pixels of one image, N = cout, K = taps x concatenated cin.
+// CTA tile 128(M) x 64(N) x 16(K), 256 threads, 8x4 register tile, double-buffered shared
+// memory with register prefetch.  grid = (M tiles, N tiles, batch).
+#include "common.cuh"
+
+namespace accflow {
+
+constexpr int BM = 128, BN = 64, BK = 16, NTHREADS = 256, APAD = 4;
+
+struct ConvK {
+  accflow_conv_desc d;
+  int out_h, out_w, cin_total;
+  int src_off[ACCFLOW_MAX_SRC];
+  int src_vec[ACCFLOW_MAX_SRC];
+  int out_vec;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 2) conv_f32_kernel(const ConvK p) {
+  __shared__ __align__(16) float As[2][BK][BM + APAD];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const accflow_conv_desc& d = p.d;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int npix = p.out_h * p.out_w;
+
+  // A-load slots: two (pixel, 4-channel group) pairs per thread, fixed over the K loop
+  int a_iy0[2], a_ix0[2];
+  bool a_ok[2];
+  const int a_c4 = tid & 3;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    int pl = (tid + j * NTHREADS) >> 2;
+    int pm = m0 + pl;
+    a_ok[j] = pm < npix;
+    int oy = pm / p.out_w, ox = pm - oy * p.out_w;
+    a_iy0[j] = oy * d.stride - d.pad_h;
+    a_ix0[j] = ox * d.stride - d.pad_w;
+  }
+  const int b_row = tid >> 4;
+  const int b_n = n0 + (tid & 15) * 4;
+  const float* wbase = d.weight + (long long)b * d.weight_batch_stride;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int taps = d.kh * d.kw;
+  int tap = 0, s = 0, c0 = 0;  // chunk iterator
+  float4 ra[2], rb;
+
+  auto load_chunk = [&]() {
+    const int ky = tap / d.kw, kx = tap - ky * d.kw;
+    const int C = d.src_c[s];
+    const float* sp = d.src[s];
+    const int ld = d.src_ld[s];
+    const int c = c0 + a_c4 * 4;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      int iy = a_iy0[j] + ky, ix = a_ix0[j] + kx;
+      if (a_ok[j] && iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w && c < C) {
+        const float* ptr = sp + ((long long)(b * d.in_h + iy) * d.in_w + ix) * ld + c;
+        if (p.src_vec[s] && c + 3 < C) {
+          v = __ldg(reinterpret_cast<const float4*>(ptr));
+        } else {
+          v.x = __ldg(ptr);
+          if (c + 1 < C) v.y = __ldg(ptr + 1);
+          if (c + 2 < C) v.z = __ldg(ptr + 2);
+          if (c + 3 < C) v.w = __ldg(ptr + 3);
+        }
+      }
+      ra[j] = v;
+    }
+    rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int krow = c0 + b_row;
+    if (krow < C && b_n < d.cout_pad) {
+      const long long kg = (long long)tap * p.cin_total + p.src_off[s] + krow;
+      rb = __ldg(reinterpret_cast<const float4*>(wbase + kg * d.cout_pad + b_n));
+    }
+  };
+  auto store_chunk = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      int pl = (tid + j * NTHREADS) >> 2;
+      As[buf][a_c4 * 4 + 0][pl] = ra[j].x;
+      As[buf][a_c4 * 4 + 1][pl] = ra[j].y;
+      As[buf][a_c4 * 4 + 2][pl] = ra[j].z;
+      As[buf][a_c4 * 4 + 3][pl] = ra[j].w;
+    }
+    *reinterpret_cast<float4*>(&Bs[buf][b_row][(tid & 15) * 4]) = rb;
+  };
+  auto advance = [&]() -> bool {  // next chunk; false when exhausted
+    c0 += BK;
+    if (c0 >= d.src_c[s]) {
+      c0 = 0;
+      if (++s >= d.nsrc) {
+        s = 0;
+        if (++tap >= taps) return false;
+      }
+    }
+    return true;
+  };
+
+  load_chunk();
+  store_chunk(0);
+  __syncthreads();
+  int cur = 0;
+  bool more = advance();
+  while (true) {
+    if (more) load_chunk();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[cur][kk][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[cur][kk][ty * 8 + 4]);
+      float4 bv = *reinterpret_cast<const float4*>(&Bs[cur][kk][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bw[j], acc[i][j]);
+    }
+    if (!more) break;
+    store_chunk(cur ^ 1);
+    __syncthreads();
+    cur ^= 1;
+    more = advance();
+  }
+
+  // ---- epilogue ---------------------------------------------------------------------------
+  const int nb = n0 + tx * 4;
+  if (nb >= d.cout) return;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int n = nb + j;
+    bool ok = n < d.cout;
+    sc[j] = d.alpha * ((d.scale && ok) ? __ldg(d.scale + n) : 1.f);
+    sh[j] = (d.shift && ok) ? __ldg(d.shift + n) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int pm = m0 + ty * 8 + i;
+    if (pm >= npix) continue;
+    const long long pix = (long long)b * npix + pm;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaf(acc[i][j], sc[j], sh[j]);
+    if (d.epilogue == ACCFLOW_EPI_STORE) {
+      if (p.out_vec && nb + 3 < d.cout) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = act_apply(v[j], d.act);
+        if (d.residual) {
+          float4 r = *reinterpret_cast<const float4*>(d.residual + pix * d.res_ld + nb);
+          v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+        }
+        if (d.post_relu) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        *reinterpret_cast<float4*>(d.out + pix * d.out_ld + nb) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int n = nb + j;
+          if (n >= d.cout) break;
+          bool second = d.act_split > 0 && n >= d.act_split;
+          float y = act_apply(v[j], second ? d.act2 : d.act);
+          if (d.residual) y += d.residual[pix * d.res_ld + n];
+          if (d.post_relu) y = fmaxf(y, 0.f);
+          if (second && d.out2) d.out2[pix * d.out2_ld + (n - d.act_split)] = y;
+          else d.out[pix * d.out_ld + n] = y;
+        }
+      }
+    } else if (d.epilogue == ACCFLOW_EPI_GRU_ZR) {
+      const int hd = d.cout >> 1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int n = nb + j;
+        if (n >= d.cout) break;
+        float g = 1.f / (1.f + expf(-v[j]));
+        if (n < hd) d.z[pix * d.z_ld + n] = g;
+        else d.out2[pix * d.out2_ld + (n - hd)] = g * d.h[pix * d.h_ld + (n - hd)];
+      }
+    } else {  // ACCFLOW_EPI_GRU_Q
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int n = nb + j;
+        if (n >= d.cout) break;
+        float q = tanhf(v[j]);
+        float zz = d.z[pix * d.z_ld + n];
+        float hh = d.h[pix * d.h_ld + n];
+        d.h[pix * d.h_ld + n] = (1.f - zz) * hh + zz * q;
+      }
+    }
+  }
+}
+
+// ---- small-cin KSxKS convolution ------------------------------------------------------------
+template <int CIN, int KS, int STRIDE, int COUT, bool NCHW>
+__global__ void __launch_bounds__(256) conv_smallc_kernel(const float* __restrict__ in, int in_h, int in_w,
+                                                          const float* __restrict__ w,
+                                                          const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, int act,
+                                                          float* __restrict__ out, int out_ld, int out_h,
+                                                          int out_w) {
+  constexpr int TILE = 8, PATCH = (TILE - 1) * STRIDE + KS, K = CIN * KS * KS, CG = COUT / 4, PAD = KS / 2;
+  extern __shared__ __align__(16) float sm[];
+  float* Ws = sm;                   // [K][COUT]
+  float* patch = sm + K * COUT;     // [CIN][PATCH][PATCH+1]
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * TILE, ox0 = blockIdx.x * TILE;
+  for (int i = tid; i < K * COUT / 4; i += 256)
+    reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+  const int iy0 = oy0 * STRIDE - PAD, ix0 = ox0 * STRIDE - PAD;
+  for (int i = tid; i < CIN * PATCH * PATCH; i += 256) {
+    int c = i / (PATCH * PATCH), r = i - c * PATCH * PATCH;
+    int py = r / PATCH, px = r - py * PATCH;
+    int iy = iy0 + py, ix = ix0 + px;
+    float v = 0.f;
+    if (iy >= 0 && iy < in_h && ix >= 0 && ix < in_w)
+      v = NCHW ? __ldg(in + ((long long)(b * CIN + c) * in_h + iy) * in_w + ix)
+               : __ldg(in + ((long long)(b * in_h + iy) * in_w + ix) * CIN + c);
+    patch[(c * PATCH + py) * (PATCH + 1) + px] = v;
+  }
+  __syncthreads();
+  const int pixel = tid & 63, g = tid >> 6;
+  const int ly = pixel >> 3, lx = pixel & 7;
+  float acc[CG];
+#pragma unroll
+  for (int j = 0; j < CG; ++j) acc[j] = 0.f;
+  for (int ky = 0; ky < KS; ++ky)
+    for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        float v = patch[(c * PATCH + ly * STRIDE + ky) * (PATCH + 1) + lx * STRIDE + kx];
+        const float4* wr = reinterpret_cast<const float4*>(Ws + ((ky * KS + kx) * CIN + c) * COUT + g * CG);
+#pragma unroll
+        for (int j = 0; j < CG / 4; ++j) {
+          float4 ww = wr[j];
+          acc[4 * j + 0] = fmaf(v, ww.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(v, ww.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(v, ww.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(v, ww.w, acc[4 * j + 3]);
+        }
+      }
+  const int oy = oy0 + ly, ox = ox0 + lx;
+  if (oy >= out_h || ox >= out_w) return;
+  float* op = out + ((long long)(b * out_h + oy) * out_w + ox) * out_ld + g * CG;
+#pragma unroll
+  for (int j = 0; j < CG; ++j) {
+    int n = g * CG + j;
+    float v = acc[j];
+    v = fmaf(v, scale ? __ldg(scale + n) : 1.f, shift ? __ldg(shift + n) : 0.f);
+    op[j] = act_apply(v, act);
+  }
+}
+
+template <int CIN, int KS, int STRIDE, int COUT, bool NCHW>
+static int launch_smallc(const float* in, int batch, int in_h, int in_w, const float* w, const float* scale,
+                         const float* shift, int act, float* out, int out_ld, cudaStream_t st) {
+  constexpr int TILE = 8, PATCH = (TILE - 1) * STRIDE + KS, K = CIN * KS * KS, PAD = KS / 2;
+  const int out_h = (in_h + 2 * PAD - KS) / STRIDE + 1, out_w = (in_w + 2 * PAD - KS) / STRIDE + 1;
+  const size_t smem = (size_t)(K * COUT + CIN * PATCH * (PATCH + 1)) * sizeof(float);
+  auto kern = conv_smallc_kernel<CIN, KS, STRIDE, COUT, NCHW>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "conv_smallc: smem attribute: %s", cudaGetErrorString(e));
+    configured_dev = dev;
+  }
+  dim3 grid(cdiv(out_w, TILE), cdiv(out_h, TILE), batch);
+  kern<<<grid, 256, smem, st>>>(in, in_h, in_w, w, scale, shift, act, out, out_ld, out_h, out_w);
+  return launched("conv_smallc");
+}
+
+}  // namespace accflow
+
+using namespace accflow;
+
+extern "C" int accflow_conv2d_f32(const accflow_conv_desc* dp, void* stream) {
+  ACCFLOW_REQUIRE(dp != nullptr, "conv2d: null descriptor");
+  ConvK k;
+  k.d = *dp;
+  const accflow_conv_desc& d = k.d;
+  ACCFLOW_REQUIRE(d.nsrc >= 1 && d.nsrc <= ACCFLOW_MAX_SRC, "conv2d: nsrc=%d out of range", d.nsrc);
+  ACCFLOW_REQUIRE(d.batch > 0 && d.in_h > 0 && d.in_w > 0, "conv2d: bad input shape %dx%dx%d", d.batch, d.in_h, d.in_w);
+  ACCFLOW_REQUIRE(d.kh > 0 && d.kw > 0 && d.stride > 0, "conv2d: bad filter geometry");
+  ACCFLOW_REQUIRE(d.cout > 0 && d.cout_pad >= d.cout && d.cout_pad % 4 == 0, "conv2d: cout=%d cout_pad=%d", d.cout, d.cout_pad);
+  ACCFLOW_REQUIRE(d.weight && aligned16(d.weight) && d.weight_batch_stride % 4 == 0, "conv2d: weight must be 16B aligned");
+  k.cin_total = 0;
+  for (int s = 0; s < ACCFLOW_MAX_SRC; ++s) {
+    k.src_off[s] = k.cin_total;
+    k.src_vec[s] = 0;
+    if (s < d.nsrc) {
+      ACCFLOW_REQUIRE(d.src[s] && d.src_c[s] > 0 && d.src_ld[s] >= d.src_c[s], "conv2d: bad source %d", s);
+      k.src_vec[s] = aligned16(d.src[s]) && d.src_ld[s] % 4 == 0;
+      k.cin_total += d.src_c[s];
+    }
+  }
+  k.out_h = (d.in_h + 2 * d.pad_h - d.kh) / d.stride + 1;
+  k.out_w = (d.in_w + 2 * d.pad_w - d.kw) / d.stride + 1;
+  ACCFLOW_REQUIRE(k.out_h > 0 && k.out_w > 0, "conv2d: empty output");
+  if (d.epilogue == ACCFLOW_EPI_STORE) {
+    ACCFLOW_REQUIRE(d.out != nullptr, "conv2d: null output");
+    ACCFLOW_REQUIRE(d.act_split == 0 || (d.act_split % 4 == 0), "conv2d: act_split must be a multiple of 4");
+  } else if (d.epilogue == ACCFLOW_EPI_GRU_ZR) {
+    ACCFLOW_REQUIRE(d.z && d.h && d.out2 && d.cout % 2 == 0, "conv2d: GRU_ZR needs z, h, out2");
+  } else if (d.epilogue == ACCFLOW_EPI_GRU_Q) {
+    ACCFLOW_REQUIRE(d.z && d.h, "conv2d: GRU_Q needs z, h");
+  } else {
+    return fail(-1, "conv2d: unknown epilogue %d", d.epilogue);
+  }
+  k.out_vec = d.epilogue == ACCFLOW_EPI_STORE && d.act_split == 0 && aligned16(d.out) && d.out_ld % 4 == 0 &&
+              (!d.residual || (aligned16(d.residual) && d.res_ld % 4 == 0));
+  dim3 grid(cdiv((long long)k.out_h * k.out_w, BM), cdiv(d.cout, BN), d.batch);
+  conv_f32_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(k);
+  return launched("conv2d_f32");
+}
+
+extern "C" int accflow_conv_smallc_f32(const float* in, int in_is_nchw, int batch, int cin, int in_h, int in_w,
+                                       const float* weight, const float* scale, const float* shift, int ks,
+                                       int stride, int cout, int act, float* out, int out_ld, void* stream) {
+  ACCFLOW_REQUIRE(in && weight && out && aligned16(weight), "conv_smallc: null/unaligned pointer");
+  ACCFLOW_REQUIRE(batch > 0 && in_h > 0 && in_w > 0 && out_ld >= cout, "conv_smallc: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cin == 3 && ks == 7 && stride == 2 && cout == 64 && in_is_nchw)
+    return launch_smallc<3, 7, 2, 64, true>(in, batch, in_h, in_w, weight, scale, shift, act, out, out_ld, st);
+  if (cin == 2 && ks == 7 && stride == 1 && cout == 128 && !in_is_nchw)
+    return launch_smallc<2, 7, 1, 128, false>(in, batch, in_h, in_w, weight, scale, shift, act, out, out_ld, st);
+  return fail(-1, "conv_smallc: unsupported configuration cin=%d ks=%d stride=%d cout=%d nchw=%d", cin, ks, stride,
+              cout, in_is_nchw);
+}

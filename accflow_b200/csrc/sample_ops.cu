@@ -1,0 +1,573 @@
+// Gather / resample / normalisation kernels of the flow path (all HBM- or latency-bound).
+#include "common.cuh"
+
+namespace accflow {
+
+// =============================== InstanceNorm (NHWC) =======================================
+constexpr int IN_CHUNK = 1024;  // pixels per partial-reduction block
+
+__global__ void __launch_bounds__(256) instnorm_partial_kernel(const float* __restrict__ x, int hw, int c,
+                                                               float* __restrict__ partial, int chunks) {
+  __shared__ float red[2][256];
+  const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int groups = 256 / c;  // c <= 256
+  const int ch = tid % c, g = tid / c;
+  const float* xb = x + (long long)b * hw * c;
+  float s = 0.f, q = 0.f;
+  if (g < groups) {
+    const float ref = __ldg(xb + ch);  // shift by the first pixel: avoids E[x^2]-E[x]^2 cancellation
+    const int p1 = min(hw, (chunk + 1) * IN_CHUNK);
+    for (int p = chunk * IN_CHUNK + g; p < p1; p += groups) {
+      float v = __ldg(xb + (long long)p * c + ch) - ref;
+      s += v;
+      q = fmaf(v, v, q);
+    }
+  }
+  red[0][tid] = s;
+  red[1][tid] = q;
+  __syncthreads();
+  if (tid < c) {
+    for (int k = 1; k < groups; ++k) {
+      s += red[0][tid + k * c];
+      q += red[1][tid + k * c];
+    }
+    float* o = partial + (((long long)b * chunks + chunk) * c + tid) * 2;
+    o[0] = s;
+    o[1] = q;
+  }
+}
+
+__global__ void instnorm_finalize_kernel(const float* __restrict__ x, const float* __restrict__ partial, int hw,
+                                         int c, int chunks, float eps, float* __restrict__ stats) {
+  const int b = blockIdx.x, ch = threadIdx.x;
+  if (ch >= c) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    const float* pp = partial + (((long long)b * chunks + k) * c + ch) * 2;
+    s += (double)pp[0];
+    q += (double)pp[1];
+  }
+  const double ref = (double)x[(long long)b * hw * c + ch];
+  const double ms = s / hw;
+  double var = q / hw - ms * ms;
+  if (var < 0.0) var = 0.0;
+  stats[((long long)b * c + ch) * 2 + 0] = (float)(ms + ref);
+  stats[((long long)b * c + ch) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// x and out may alias (in-place normalisation): no __restrict__ / read-only loads on them.
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* x, const float* __restrict__ stats,
+                                                             long long n4, int hw, int c, int relu,
+                                                             const float* residual, int post_relu, float* out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const int c4n = c >> 2;
+  const int c4 = (int)(i % c4n);
+  const int b = (int)(i / ((long long)hw * c4n));
+  float4 v = reinterpret_cast<const float4*>(x)[i];
+  const float4* st = reinterpret_cast<const float4*>(stats + ((long long)b * c + c4 * 4) * 2);
+  float4 s0 = __ldg(st), s1 = __ldg(st + 1);  // (mean0,rstd0,mean1,rstd1), (mean2,rstd2,mean3,rstd3)
+  float r[4] = {(v.x - s0.x) * s0.y, (v.y - s0.z) * s0.w, (v.z - s1.x) * s1.y, (v.w - s1.z) * s1.w};
+  if (relu) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = fmaxf(r[k], 0.f);
+  }
+  if (residual) {
+    float4 q = reinterpret_cast<const float4*>(residual)[i];
+    r[0] += q.x; r[1] += q.y; r[2] += q.z; r[3] += q.w;
+  }
+  if (post_relu) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = fmaxf(r[k], 0.f);
+  }
+  reinterpret_cast<float4*>(out)[i] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+// =============================== transpose [B,HW,C] -> [B,C,HW] ============================
+__global__ void transpose_kernel(const float* __restrict__ in, int hw, int c, int in_ld, float* __restrict__ out, int out_ld) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    int p = p0 + k, cc = c0 + tx;
+    tile[k][tx] = (p < hw && cc < c) ? __ldg(in + ((long long)b * hw + p) * in_ld + cc) : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    int cc = c0 + k, p = p0 + tx;
+    if (cc < c && p < hw) out[((long long)b * c + cc) * out_ld + p] = tile[tx][k];
+  }
+}
+
+// =============================== correlation pyramid pooling ===============================
+// One block per volume row (source pixel): the row's h x w target map is staged in shared
+// memory and the three successive 2x2 means are taken from it (raft/corr.py:20-22).
+__global__ void __launch_bounds__(256) corr_pool_kernel(const float* __restrict__ lvl0, int h, int w,
+                                                        float* __restrict__ l1, float* __restrict__ l2,
+                                                        float* __restrict__ l3) {
+  extern __shared__ float sm[];
+  const int h1 = h >> 1, w1 = w >> 1, h2 = h1 >> 1, w2 = w1 >> 1, h3 = h2 >> 1, w3 = w2 >> 1;
+  float* s0 = sm;
+  float* s1 = s0 + h * w;
+  float* s2 = s1 + h1 * w1;
+  const long long row = blockIdx.x;
+  const float* src = lvl0 + row * h * w;
+  for (int i = threadIdx.x; i < h * w; i += 256) s0[i] = __ldg(src + i);
+  __syncthreads();
+  for (int i = threadIdx.x; i < h1 * w1; i += 256) {
+    int y = i / w1, x = i - y * w1;
+    const float* q = s0 + (2 * y) * w + 2 * x;
+    float v = (((q[0] + q[1]) + q[w]) + q[w + 1]) * 0.25f;
+    s1[i] = v;
+    l1[row * h1 * w1 + i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < h2 * w2; i += 256) {
+    int y = i / w2, x = i - y * w2;
+    const float* q = s1 + (2 * y) * w1 + 2 * x;
+    float v = (((q[0] + q[1]) + q[w1]) + q[w1 + 1]) * 0.25f;
+    s2[i] = v;
+    l2[row * h2 * w2 + i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < h3 * w3; i += 256) {
+    int y = i / w3, x = i - y * w3;
+    const float* q = s2 + (2 * y) * w2 + 2 * x;
+    l3[row * h3 * w3 + i] = (((q[0] + q[1]) + q[w2]) + q[w2 + 1]) * 0.25f;
+  }
+}
+
+// =============================== correlation lookup ========================================
+struct LookupP {
+  const float* lvl[4];
+  int lh[4], lw[4];
+  int batch, h, w, radius;
+  const float* coords;
+  float* out; int out_ld;
+  float* flow_out; float* mf_tail; int mf_ld;
+};
+
+__device__ __forceinline__ float bilinear_zeros(const float* __restrict__ img, int H, int W, float x, float y) {
+  // ATen grid_sampler_2d (bilinear, zeros padding, align_corners=True) on un-normalised coords
+  if (!(x > -2.f && x < (float)W + 1.f && y > -2.f && y < (float)H + 1.f)) return 0.f;
+  const float xf = floorf(x), yf = floorf(y);
+  const int x0 = (int)xf, y0 = (int)yf;
+  const float wx1 = x - xf, wy1 = y - yf;
+  const float wx0 = (xf + 1.f) - x, wy0 = (yf + 1.f) - y;
+  const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
+  const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
+  float r = 0.f;
+  if (yin0 && xin0) r += __ldg(img + y0 * W + x0) * (wx0 * wy0);
+  if (yin0 && xin1) r += __ldg(img + y0 * W + x0 + 1) * (wx1 * wy0);
+  if (yin1 && xin0) r += __ldg(img + (y0 + 1) * W + x0) * (wx0 * wy1);
+  if (yin1 && xin1) r += __ldg(img + (y0 + 1) * W + x0 + 1) * (wx1 * wy1);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupP p) {
+  const int k1 = 2 * p.radius + 1, k2 = k1 * k1, nch = 4 * k2;
+  const long long total = (long long)p.batch * p.h * p.w * nch;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const long long pix = idx / nch;
+  const int ch = (int)(idx - pix * nch);
+  const int lvl = ch / k2, t = ch - lvl * k2;
+  const int a = t / k1, bb = t - a * k1;
+  const float cx = __ldg(p.coords + pix * 2), cy = __ldg(p.coords + pix * 2 + 1);
+  const float inv = 1.f / (float)(1 << lvl);  // exact power of two
+  const float x = __fadd_rn(cx * inv, (float)(a - p.radius));
+  const float y = __fadd_rn(cy * inv, (float)(bb - p.radius));
+  const int H = p.lh[lvl], W = p.lw[lvl];
+  const float* img = p.lvl[lvl] + pix * (long long)(H * W);
+  p.out[pix * p.out_ld + ch] = bilinear_zeros(img, H, W, grid_roundtrip(x, W), grid_roundtrip(y, H));
+  if (ch == 0) {
+    const int pl = (int)(pix % ((long long)p.h * p.w));
+    const float fx = cx - (float)(pl % p.w), fy = cy - (float)(pl / p.w);
+    if (p.flow_out) { p.flow_out[pix * 2] = fx; p.flow_out[pix * 2 + 1] = fy; }
+    if (p.mf_tail) { p.mf_tail[pix * p.mf_ld] = fx; p.mf_tail[pix * p.mf_ld + 1] = fy; }
+  }
+}
+
+__global__ void coords_init_kernel(const float* __restrict__ finit, int batch, int h, int w, float* __restrict__ coords) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int hw = h * w;
+  if (i >= batch * hw) return;
+  const int b = i / hw, pl = i - b * hw;
+  float fx = 0.f, fy = 0.f;
+  if (finit) { fx = finit[((long long)b * 2) * hw + pl]; fy = finit[((long long)b * 2 + 1) * hw + pl]; }
+  coords[(long long)i * 2] = (float)(pl % w) + fx;
+  coords[(long long)i * 2 + 1] = (float)(pl / w) + fy;
+}
+
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long long n) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) y[i] = y[i] + a * x[i];
+}
+
+// =============================== convex upsample ===========================================
+__global__ void __launch_bounds__(256) convex_upsample_kernel(const float* __restrict__ flow, int flow_ld,
+                                                              int coords_mode, const float* __restrict__ mask,
+                                                              int mask_ld, int h, int w, float* __restrict__ out) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x = blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int sub = threadIdx.x & 63;
+  if (x >= w) return;
+  const long long pix = ((long long)b * h + y) * w + x;
+  const float* mp = mask + pix * mask_ld + sub;
+  float m[9], mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { m[k] = __ldg(mp + k * 64); mx = fmaxf(mx, m[k]); }
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { m[k] = expf(m[k] - mx); sum += m[k]; }
+  float ox = 0.f, oy = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+    float fx = 0.f, fy = 0.f;
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+      const float* fp = flow + (((long long)b * h + yy) * w + xx) * flow_ld;
+      fx = __ldg(fp); fy = __ldg(fp + 1);
+      if (coords_mode) { fx -= (float)xx; fy -= (float)yy; }
+    }
+    const float pk = m[k] / sum;
+    ox += pk * (8.f * fx);
+    oy += pk * (8.f * fy);
+  }
+  const int i = sub >> 3, j = sub & 7;
+  const long long H8 = 8LL * h, W8 = 8LL * w;
+  float* o = out + ((long long)b * 2 * H8 + (8 * y + i)) * W8 + 8 * x + j;
+  o[0] = ox;
+  o[H8 * W8] = oy;
+}
+
+// =============================== downflow8 ==================================================
+__global__ void downflow8_kernel(const float* __restrict__ in, int batch, int H, int W, float* __restrict__ out) {
+  const int h = H / 8, w = W / 8;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= batch * h * w) return;
+  const int b = i / (h * w), r = i - b * h * w, oy = r / w, ox = r - oy * w;
+  // ATen upsample_bilinear2d, align_corners=True: scale = (in-1)/(out-1); src = scale*dst
+  const float sy = h > 1 ? (float)(H - 1) / (float)(h - 1) : 0.f;
+  const float sx = w > 1 ? (float)(W - 1) / (float)(w - 1) : 0.f;
+  const float fy = __fmul_rn(sy, (float)oy), fx = __fmul_rn(sx, (float)ox);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const float* pl = in + ((long long)b * 2 + c) * H * W;
+    float v = hy * (hx * __ldg(pl + (long long)y0 * W + x0) + lx * __ldg(pl + (long long)y0 * W + x1)) +
+              ly * (hx * __ldg(pl + (long long)y1 * W + x0) + lx * __ldg(pl + (long long)y1 * W + x1));
+    out[(long long)i * 2 + c] = v / 8.f;
+  }
+}
+
+// =============================== warp + occlusion ==========================================
+// One warp per pixel; lanes stride over 4-channel groups.
+__global__ void __launch_bounds__(256) warp_occ_kernel(const float* __restrict__ c1, int c1_ld,
+                                                       const float* __restrict__ c2, int c2_ld,
+                                                       const float* __restrict__ flow, int batch, int h, int w,
+                                                       int c, float* __restrict__ occ, int occ_ld,
+                                                       float* __restrict__ emap, int emap_ld) {
+  const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= (long long)batch * h * w) return;
+  const int hw = h * w;
+  const int b = (int)(pix / hw), pl = (int)(pix - (long long)b * hw);
+  const int py = pl / w, px = pl - py * w;
+  const float x = grid_roundtrip(__fadd_rn((float)px, __ldg(flow + pix * 2)), w);
+  const float y = grid_roundtrip(__fadd_rn((float)py, __ldg(flow + pix * 2 + 1)), h);
+  float wgt[4] = {0.f, 0.f, 0.f, 0.f};
+  long long off[4] = {0, 0, 0, 0};
+  if (x > -2.f && x < (float)w + 1.f && y > -2.f && y < (float)h + 1.f) {
+    const float xf = floorf(x), yf = floorf(y);
+    const int x0 = (int)xf, y0 = (int)yf;
+    const float wx1 = x - xf, wy1 = y - yf, wx0 = (xf + 1.f) - x, wy0 = (yf + 1.f) - y;
+    const float ww[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
+      if (xx >= 0 && xx < w && yy >= 0 && yy < h) {
+        wgt[k] = ww[k];
+        off[k] = ((long long)b * hw + (long long)yy * w + xx) * c2_ld;
+      }
+    }
+  }
+  float esum = 0.f;
+  for (int c4 = lane; c4 < (c >> 2); c4 += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (wgt[k] != 0.f) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(c2 + off[k]) + c4);
+        acc.x += v.x * wgt[k]; acc.y += v.y * wgt[k]; acc.z += v.z * wgt[k]; acc.w += v.w * wgt[k];
+      }
+    }
+    float4 a = __ldg(reinterpret_cast<const float4*>(c1 + pix * c1_ld) + c4);
+    float4 e = make_float4(fabsf(a.x - acc.x), fabsf(a.y - acc.y), fabsf(a.z - acc.z), fabsf(a.w - acc.w));
+    esum += (e.x + e.y) + (e.z + e.w);
+    if (emap) reinterpret_cast<float4*>(emap + pix * emap_ld)[c4] = e;
+  }
+  if (occ) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+    if (lane == 0) occ[pix * occ_ld] = (esum / (float)c <= 1.0f) ? 1.f : 0.f;
+  }
+}
+
+__global__ void backwarp_nchw_kernel(const float* __restrict__ img, const float* __restrict__ flow, int batch,
+                                     int c, int h, int w, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int hw = h * w;
+  if (i >= (long long)batch * hw) return;
+  const int b = (int)(i / hw), pl = (int)(i - (long long)b * hw);
+  const int py = pl / w, px = pl - py * w;
+  const float x = grid_roundtrip(__fadd_rn((float)px, __ldg(flow + ((long long)b * 2) * hw + pl)), w);
+  const float y = grid_roundtrip(__fadd_rn((float)py, __ldg(flow + ((long long)b * 2 + 1) * hw + pl)), h);
+  for (int ch = 0; ch < c; ++ch)
+    out[((long long)b * c + ch) * hw + pl] = bilinear_zeros(img + ((long long)b * c + ch) * hw, h, w, x, y);
+}
+
+// =============================== deformable gather ==========================================
+// One warp per pixel; 9 modulated bilinear taps -> col[pix][tap*c + ch].
+__global__ void __launch_bounds__(256) deform_gather_kernel(const float* __restrict__ x, int x_ld,
+                                                            const float* __restrict__ om, int om_ld, int batch,
+                                                            int h, int w, int c, float* __restrict__ col) {
+  const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int hw = h * w;
+  if (pix >= (long long)batch * hw) return;
+  const int b = (int)(pix / hw), pl = (int)(pix - (long long)b * hw);
+  const int py = pl / w, px = pl - py * w;
+  const float* omp = om + pix * om_ld;
+  const int c4n = c >> 2;
+  for (int k = 0; k < 9; ++k) {
+    const float sy = (float)(py - 1 + k / 3) + __ldg(omp + 2 * k);
+    const float sx = (float)(px - 1 + k % 3) + __ldg(omp + 2 * k + 1);
+    const float mk = 1.f / (1.f + expf(-__ldg(omp + 18 + k)));
+    float wgt[4] = {0.f, 0.f, 0.f, 0.f};
+    long long off[4] = {0, 0, 0, 0};
+    if (sy > -1.f && sy < (float)h && sx > -1.f && sx < (float)w) {
+      const float yf = floorf(sy), xf = floorf(sx);
+      const int y0 = (int)yf, x0 = (int)xf;
+      const float ly = sy - yf, lx = sx - xf, hy = 1.f - ly, hx = 1.f - lx;
+      const float ww[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int yy = y0 + (q >> 1), xx = x0 + (q & 1);
+        if (yy >= 0 && yy <= h - 1 && xx >= 0 && xx <= w - 1) {
+          wgt[q] = ww[q];
+          off[q] = ((long long)b * hw + (long long)yy * w + xx) * x_ld;
+        }
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(col + (pix * 9 + k) * c);
+    for (int c4 = lane; c4 < c4n; c4 += 32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (wgt[q] != 0.f) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(x + off[q]) + c4);
+          acc.x += wgt[q] * v.x; acc.y += wgt[q] * v.y; acc.z += wgt[q] * v.z; acc.w += wgt[q] * v.w;
+        }
+      }
+      dst[c4] = make_float4(acc.x * mk, acc.y * mk, acc.z * mk, acc.w * mk);
+    }
+  }
+}
+
+__global__ void blend_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
+                             const float* __restrict__ m, int m_ld, long long n4, int c4n,
+                             float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const float mm = __ldg(m + (i / c4n) * m_ld);
+  float4 a = __ldg(reinterpret_cast<const float4*>(f1) + i), b = __ldg(reinterpret_cast<const float4*>(f2) + i);
+  const float om = 1.f - mm;
+  reinterpret_cast<float4*>(out)[i] =
+      make_float4(a.x * mm + om * b.x, a.y * mm + om * b.y, a.z * mm + om * b.z, a.w * mm + om * b.w);
+}
+
+// =============================== row softmax ================================================
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, int n) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  float* row = x + (long long)blockIdx.x * n;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float mx = -INFINITY;
+  for (int i = tid; i < n; i += 256) mx = fmaxf(mx, row[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[wid] = mx;
+  __syncthreads();
+  if (tid == 0) { float m = red[0]; for (int k = 1; k < 8; ++k) m = fmaxf(m, red[k]); bc = m; }
+  __syncthreads();
+  mx = bc;
+  float s = 0.f;
+  for (int i = tid; i < n; i += 256) { float e = expf(row[i] - mx); row[i] = e; s += e; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __syncthreads();
+  if (lane == 0) red[wid] = s;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int k = 0; k < 8; ++k) t += red[k]; bc = t; }
+  __syncthreads();
+  const float tot = bc;
+  for (int i = tid; i < n; i += 256) row[i] = row[i] / tot;
+}
+
+}  // namespace accflow
+
+using namespace accflow;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int accflow_abi_version(void) { return ACCFLOW_ABI_VERSION; }
+
+extern "C" int accflow_last_error(char* buf, size_t len) {
+  if (!buf || len == 0) return -1;
+  strncpy(buf, err_buf(), len - 1);
+  buf[len - 1] = 0;
+  return 0;
+}
+
+extern "C" long long accflow_launch_count(int reset) {
+  long long v = launch_counter().load();
+  if (reset) launch_counter().store(0);
+  return v;
+}
+
+extern "C" int accflow_instnorm_chunks(int hw) { return cdiv(hw, IN_CHUNK); }
+
+extern "C" int accflow_instnorm_f32(const float* x, int batch, int hw, int c, float eps, int relu,
+                                    const float* residual, int post_relu, float* out, float* partial,
+                                    float* stats, void* stream) {
+  ACCFLOW_REQUIRE(x && out && partial && stats, "instnorm: null pointer");
+  ACCFLOW_REQUIRE(batch > 0 && hw > 0 && c > 0 && c <= 256 && c % 4 == 0, "instnorm: bad shape b=%d hw=%d c=%d", batch, hw, c);
+  ACCFLOW_REQUIRE(aligned16(x) && aligned16(out) && aligned16(stats) && (!residual || aligned16(residual)), "instnorm: 16B alignment");
+  const int chunks = cdiv(hw, IN_CHUNK);
+  instnorm_partial_kernel<<<dim3(chunks, batch), 256, 0, ST>>>(x, hw, c, partial, chunks);
+  if (int e = launched("instnorm_partial")) return e;
+  instnorm_finalize_kernel<<<batch, 256, 0, ST>>>(x, partial, hw, c, chunks, eps, stats);
+  if (int e = launched("instnorm_finalize")) return e;
+  const long long n4 = (long long)batch * hw * c / 4;
+  instnorm_apply_kernel<<<cdiv(n4, 256), 256, 0, ST>>>(x, stats, n4, hw, c, relu, residual, post_relu, out);
+  return launched("instnorm_apply");
+}
+
+extern "C" int accflow_nhwc_transpose_f32(const float* in, int batch, int hw, int c, int in_ld, float* out_nchw,
+                                          int out_ld, void* stream) {
+  ACCFLOW_REQUIRE(in && out_nchw && batch > 0 && hw > 0 && c > 0 && in_ld >= c && out_ld >= hw, "transpose: bad arguments");
+  transpose_kernel<<<dim3(cdiv(hw, 32), cdiv(c, 32), batch), dim3(32, 8), 0, ST>>>(in, hw, c, in_ld, out_nchw, out_ld);
+  return launched("nhwc_transpose");
+}
+
+extern "C" int accflow_corr_pool_f32(const float* lvl0, long long n_rows, int h, int w, float* lvl1, float* lvl2,
+                                     float* lvl3, void* stream) {
+  ACCFLOW_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && n_rows > 0, "corr_pool: null pointer");
+  ACCFLOW_REQUIRE(h >= 8 && w >= 8, "corr_pool: map %dx%d too small for 4 levels", h, w);
+  const size_t smem = (size_t)(h * w + (h / 2) * (w / 2) + (h / 4) * (w / 4)) * sizeof(float);
+  ACCFLOW_REQUIRE(smem <= 200 * 1024, "corr_pool: map %dx%d exceeds shared memory", h, w);
+  static thread_local int cfg_dev = -1;
+  static thread_local size_t cfg_smem = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > 48 * 1024 && (cfg_dev != dev || cfg_smem < smem)) {
+    cudaError_t e = cudaFuncSetAttribute(corr_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "corr_pool: smem attribute: %s", cudaGetErrorString(e));
+    cfg_dev = dev;
+    cfg_smem = smem;
+  }
+  corr_pool_kernel<<<(unsigned)n_rows, 256, smem, ST>>>(lvl0, h, w, lvl1, lvl2, lvl3);
+  return launched("corr_pool");
+}
+
+extern "C" int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                                       int batch, int h, int w, int radius, const float* coords, float* out,
+                                       int out_ld, float* flow_out, float* mf_tail, int mf_ld, void* stream) {
+  ACCFLOW_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && coords && out, "corr_lookup: null pointer");
+  ACCFLOW_REQUIRE(batch > 0 && h >= 8 && w >= 8 && radius >= 0 && radius <= 8, "corr_lookup: bad shape");
+  const int nch = 4 * (2 * radius + 1) * (2 * radius + 1);
+  ACCFLOW_REQUIRE(out_ld >= nch, "corr_lookup: out_ld %d < %d channels", out_ld, nch);
+  LookupP p;
+  p.lvl[0] = lvl0; p.lvl[1] = lvl1; p.lvl[2] = lvl2; p.lvl[3] = lvl3;
+  int hh = h, ww = w;
+  for (int l = 0; l < 4; ++l) { p.lh[l] = hh; p.lw[l] = ww; hh >>= 1; ww >>= 1; }
+  p.batch = batch; p.h = h; p.w = w; p.radius = radius; p.coords = coords;
+  p.out = out; p.out_ld = out_ld; p.flow_out = flow_out; p.mf_tail = mf_tail; p.mf_ld = mf_ld;
+  const long long total = (long long)batch * h * w * nch;
+  corr_lookup_kernel<<<cdiv(total, 256), 256, 0, ST>>>(p);
+  return launched("corr_lookup");
+}
+
+extern "C" int accflow_coords_init_f32(const float* flow_init_nchw, int batch, int h, int w, float* coords, void* stream) {
+  ACCFLOW_REQUIRE(coords && batch > 0 && h > 0 && w > 0, "coords_init: bad arguments");
+  coords_init_kernel<<<cdiv((long long)batch * h * w, 256), 256, 0, ST>>>(flow_init_nchw, batch, h, w, coords);
+  return launched("coords_init");
+}
+
+extern "C" int accflow_axpy_f32(float* y, const float* x, float a, long long n, void* stream) {
+  ACCFLOW_REQUIRE(y && x && n > 0, "axpy: bad arguments");
+  axpy_kernel<<<cdiv(n, 256), 256, 0, ST>>>(y, x, a, n);
+  return launched("axpy");
+}
+
+extern "C" int accflow_convex_upsample_f32(const float* flow, int flow_ld, int coords_mode, const float* mask,
+                                           int mask_ld, int batch, int h, int w, float* out_nchw, void* stream) {
+  ACCFLOW_REQUIRE(flow && mask && out_nchw, "convex_upsample: null pointer");
+  ACCFLOW_REQUIRE(batch > 0 && h > 0 && w > 0 && flow_ld >= 2 && mask_ld >= 576, "convex_upsample: bad shape");
+  convex_upsample_kernel<<<dim3(cdiv(w, 4), h, batch), 256, 0, ST>>>(flow, flow_ld, coords_mode, mask, mask_ld, h, w, out_nchw);
+  return launched("convex_upsample");
+}
+
+extern "C" int accflow_downflow8_f32(const float* flow_nchw, int batch, int H, int W, float* out_nhwc, void* stream) {
+  ACCFLOW_REQUIRE(flow_nchw && out_nhwc && batch > 0, "downflow8: null pointer");
+  ACCFLOW_REQUIRE(H % 8 == 0 && W % 8 == 0 && H >= 8 && W >= 8, "downflow8: H,W must be multiples of 8 (AccFlow_.py:140)");
+  downflow8_kernel<<<cdiv((long long)batch * (H / 8) * (W / 8), 256), 256, 0, ST>>>(flow_nchw, batch, H, W, out_nhwc);
+  return launched("downflow8");
+}
+
+extern "C" int accflow_warp_occ_f32(const float* c1, int c1_ld, const float* c2, int c2_ld, const float* flow,
+                                    int batch, int h, int w, int c, float* occ_out, int occ_ld, float* emap_out,
+                                    int emap_ld, void* stream) {
+  ACCFLOW_REQUIRE(c1 && c2 && flow && (occ_out || emap_out), "warp_occ: null pointer");
+  ACCFLOW_REQUIRE(batch > 0 && h > 1 && w > 1 && c > 0 && c % 4 == 0 && c1_ld % 4 == 0 && c2_ld % 4 == 0 &&
+                      (!emap_out || emap_ld % 4 == 0), "warp_occ: bad shape / channel alignment");
+  ACCFLOW_REQUIRE(aligned16(c1) && aligned16(c2) && (!emap_out || aligned16(emap_out)), "warp_occ: 16B alignment");
+  warp_occ_kernel<<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(c1, c1_ld, c2, c2_ld, flow, batch, h, w, c, occ_out,
+                                                                    occ_ld, emap_out, emap_ld);
+  return launched("warp_occ");
+}
+
+extern "C" int accflow_backwarp_nchw_f32(const float* img, const float* flow, int batch, int c, int h, int w,
+                                         float* out, void* stream) {
+  ACCFLOW_REQUIRE(img && flow && out && batch > 0 && c > 0 && h > 1 && w > 1, "backwarp: bad arguments");
+  backwarp_nchw_kernel<<<cdiv((long long)batch * h * w, 256), 256, 0, ST>>>(img, flow, batch, c, h, w, out);
+  return launched("backwarp_nchw");
+}
+
+extern "C" int accflow_deform_gather_f32(const float* x, int x_ld, const float* offmask, int om_ld, int batch,
+                                         int h, int w, int c, float* col, void* stream) {
+  ACCFLOW_REQUIRE(x && offmask && col, "deform_gather: null pointer");
+  ACCFLOW_REQUIRE(batch > 0 && h > 0 && w > 0 && c % 4 == 0 && x_ld % 4 == 0 && om_ld >= 27, "deform_gather: bad shape");
+  ACCFLOW_REQUIRE(aligned16(x) && aligned16(col), "deform_gather: 16B alignment");
+  deform_gather_kernel<<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(x, x_ld, offmask, om_ld, batch, h, w, c, col);
+  return launched("deform_gather");
+}
+
+extern "C" int accflow_blend_f32(const float* f1, const float* f2, const float* m, int m_ld, long long npix, int c,
+                                 float* out, void* stream) {
+  ACCFLOW_REQUIRE(f1 && f2 && m && out && npix > 0 && c % 4 == 0, "blend: bad arguments");
+  ACCFLOW_REQUIRE(aligned16(f1) && aligned16(f2) && aligned16(out), "blend: 16B alignment");
+  const long long n4 = npix * c / 4;
+  blend_kernel<<<cdiv(n4, 256), 256, 0, ST>>>(f1, f2, m, m_ld, n4, c / 4, out);
+  return launched("blend");
+}
+
+extern "C" int accflow_softmax_rows_f32(float* x, long long rows, int n, void* stream) {
+  ACCFLOW_REQUIRE(x && rows > 0 && n > 0, "softmax_rows: bad arguments");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, ST>>>(x, n);
+  return launched("softmax_rows");
+}

@@ -1,0 +1,542 @@
+"""Host-side orchestration of the sm_100a kernels (through the C ABI in _lib.py).
+
+Nothing here computes on the CPU and there is no torch-op fallback for a kernel: torch is
+used for device memory (workspaces, packed weights), stream handles and tiny D2D copies.
+
+Data layout in HBM: every activation is NHWC fp32, ``[B, h, w, C]`` with an
+explicit leading dimension so that the reference's ``torch.cat([...], dim=1)`` becomes
+"several producers write channel slices of one buffer" or "one conv reads several slices".
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+F32 = torch.float32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class View:
+    """A channel slice of an NHWC fp32 tensor: (ptr, batch, h, w, channels, ld)."""
+    __slots__ = ("t", "ptr", "b", "h", "w", "c", "ld")
+
+    def __init__(self, t: torch.Tensor, ptr=None, b=None, c=None):
+        assert t.dtype == F32 and t.is_contiguous() and t.dim() == 4
+        self.t = t
+        self.b, self.h, self.w, self.ld = (t.shape[0] if b is None else b), t.shape[1], t.shape[2], t.shape[3]
+        self.c = self.ld if c is None else c
+        self.ptr = t.data_ptr() if ptr is None else ptr
+
+    def ch(self, c0: int, c1: int) -> "View":
+        assert 0 <= c0 < c1 <= self.c
+        return View(self.t, self.ptr + 4 * c0, self.b, c1 - c0)
+
+    def rows(self, b0: int, b1: int) -> "View":
+        assert 0 <= b0 < b1 <= self.b
+        return View(self.t, self.ptr + 4 * b0 * self.h * self.w * self.ld, b1 - b0, self.c)
+
+    @property
+    def npix(self):
+        return self.b * self.h * self.w
+
+
+class PackedConv:
+    """Weights of one conv in the kernel layout [kh*kw][cin][cout_pad] + epilogue vectors."""
+
+    def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]], stride=1,
+                 pad=(0, 0), bn=None, out_scale: Optional[torch.Tensor] = None, mult: float = 1.0):
+        w = torch.cat([x.detach().to(F32) for x in weights], 0)           # concat along cout
+        dev = w.device
+        self.cout, self.cin, self.kh, self.kw = w.shape
+        self.stride, self.pad_h, self.pad_w = stride, pad[0], pad[1]
+        self.cout_pad = (self.cout + 3) // 4 * 4
+        packed = torch.zeros(self.kh * self.kw, self.cin, self.cout_pad, device=dev, dtype=F32)
+        packed[:, :, : self.cout] = w.permute(2, 3, 1, 0).reshape(self.kh * self.kw, self.cin, self.cout)
+        self.w = packed.contiguous()
+        bias = torch.cat([(torch.zeros(x.shape[0], device=dev) if b is None else b.detach().to(F32))
+                          for x, b in zip(weights, biases)])
+        scale = None
+        shift = bias
+        if bn is not None:                      # eval BatchNorm folded into the epilogue affine
+            g, beta, rm, rv, eps = bn
+            inv = (g / torch.sqrt(rv + eps)).to(F32)
+            scale = inv
+            shift = (bias - rm) * inv + beta
+        if out_scale is not None:               # ZeroConv2d: (conv + b) * exp(3*scale)
+            scale = out_scale if scale is None else scale * out_scale
+            shift = shift * out_scale
+        if mult != 1.0:                         # mask head: 0.25 * (conv + b)
+            scale = torch.full_like(shift, mult) if scale is None else scale * mult
+            shift = shift * mult
+        self.scale = None if scale is None else scale.contiguous()
+        self.shift = shift.contiguous()
+        self.has_bias = any(b is not None for b in biases) or bn is not None
+
+
+class Kernels:
+    """Thin typed wrappers over the C ABI.  One instance per device."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        L.load()
+        self._ws: Dict[tuple, torch.Tensor] = {}
+
+    # ---- workspace -----------------------------------------------------------------------
+    def buf(self, name: str, *shape, zero: bool = False) -> torch.Tensor:
+        key = (name,) + tuple(shape)
+        t = self._ws.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(*shape, device=self.device, dtype=F32)
+            self._ws[key] = t
+        return t
+
+    def view(self, name: str, b: int, h: int, w: int, c: int) -> View:
+        return View(self.buf(name, b, h, w, c))
+
+    # ---- convolution ---------------------------------------------------------------------
+    def conv(self, pc: PackedConv, srcs: Sequence[View], out: Optional[View] = None, act=L.ACT_NONE, alpha=1.0,
+             act_split=0, act2=L.ACT_NONE, out2: Optional[View] = None, residual: Optional[View] = None,
+             post_relu=False, epilogue=L.EPI_STORE, h: Optional[View] = None, z: Optional[View] = None,
+             weight_ptr: Optional[int] = None, weight_batch_stride=0, cout=None, cout_pad=None,
+             use_affine=True):
+        d = L.ConvDesc()
+        cin = 0
+        for k, s in enumerate(srcs):
+            d.src[k], d.src_c[k], d.src_ld[k] = s.ptr, s.c, s.ld
+            cin += s.c
+        assert cin == pc.cin, f"conv expects {pc.cin} input channels, got {cin}"
+        s0 = srcs[0]
+        d.nsrc, d.batch, d.in_h, d.in_w = len(srcs), s0.b, s0.h, s0.w
+        d.weight = pc.w.data_ptr() if weight_ptr is None else weight_ptr
+        d.weight_batch_stride = weight_batch_stride
+        d.kh, d.kw, d.stride, d.pad_h, d.pad_w = pc.kh, pc.kw, pc.stride, pc.pad_h, pc.pad_w
+        d.cout = pc.cout if cout is None else cout
+        d.cout_pad = pc.cout_pad if cout_pad is None else cout_pad
+        d.alpha = alpha
+        if use_affine:
+            d.scale = None if pc.scale is None else pc.scale.data_ptr()
+            d.shift = pc.shift.data_ptr() if pc.has_bias else None
+        d.act, d.act_split, d.act2 = act, act_split, act2
+        if residual is not None:
+            d.residual, d.res_ld = residual.ptr, residual.ld
+        d.post_relu, d.epilogue = int(post_relu), epilogue
+        if out is not None:
+            d.out, d.out_ld = out.ptr, out.ld
+        if out2 is not None:
+            d.out2, d.out2_ld = out2.ptr, out2.ld
+        if h is not None:
+            d.h, d.h_ld = h.ptr, h.ld
+        if z is not None:
+            d.z, d.z_ld = z.ptr, z.ld
+        L.call("accflow_conv2d_f32", C.byref(d), _stream())
+
+    def conv_smallc(self, x_ptr: int, nchw: bool, batch, cin, h, w, pc: PackedConv, act, out: View):
+        L.call("accflow_conv_smallc_f32", x_ptr, int(nchw), batch, cin, h, w, pc.w.data_ptr(),
+               None if pc.scale is None else pc.scale.data_ptr(), pc.shift.data_ptr(), pc.kh, pc.stride, pc.cout,
+               act, out.ptr, out.ld, _stream())
+
+    def instnorm(self, x: View, relu: bool, residual: Optional[View], post_relu: bool, out: View, eps=1e-5):
+        assert x.c == x.ld and out.c == out.ld
+        hw = x.h * x.w
+        chunks = L.call("accflow_instnorm_chunks", hw)
+        partial = self.buf("in_partial", x.b * chunks * x.c * 2)
+        stats = self.buf("in_stats", x.b * x.c * 2)
+        L.call("accflow_instnorm_f32", x.ptr, x.b, hw, x.c, eps, int(relu),
+               None if residual is None else residual.ptr, int(post_relu), out.ptr, partial.data_ptr(),
+               stats.data_ptr(), _stream())
+
+    def transpose(self, x: View, out: torch.Tensor, out_ld: int):
+        L.call("accflow_nhwc_transpose_f32", x.ptr, x.b, x.h * x.w, x.c, x.ld, out.data_ptr(), out_ld, _stream())
+
+    def softmax_rows(self, t: torch.Tensor, rows: int, n: int):
+        L.call("accflow_softmax_rows_f32", t.data_ptr(), rows, n, _stream())
+
+
+def _p4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+# ================================================================================ encoders
+class EncoderPlan:
+    """BasicEncoder (raft/extractor.py:137-225) with norm in {'instance','batch','none'}."""
+
+    def __init__(self, sd, pfx: str, norm: str, out_dim: int):
+        self.norm, self.out_dim, self.pfx = norm, out_dim, pfx
+
+        def bn(name):
+            if norm != "batch":
+                return None
+            return (sd[name + ".weight"], sd[name + ".bias"], sd[name + ".running_mean"], sd[name + ".running_var"], 1e-5)
+
+        def pc(name, stride, pad, bnname=None):
+            return PackedConv([sd[name + ".weight"]], [sd[name + ".bias"]], stride, (pad, pad),
+                              bn(bnname) if bnname else None)
+
+        w = sd[pfx + "conv1.weight"]                       # (64,3,7,7) -> [(ky*7+kx)*3 + c][64]
+        self.stem = pc(pfx + "conv1", 2, 3, pfx + "norm1")
+        self.stem.w = w.detach().to(F32).permute(2, 3, 1, 0).reshape(147, 64).contiguous()
+        self.blocks = []
+        for stage, stride in ((1, 1), (2, 2), (3, 2)):
+            for blk in (0, 1):
+                p = f"{pfx}layer{stage}.{blk}."
+                s = stride if blk == 0 else 1
+                self.blocks.append(dict(
+                    conv1=pc(p + "conv1", s, 1, p + "norm1"), conv2=pc(p + "conv2", 1, 1, p + "norm2"),
+                    down=pc(p + "downsample.0", s, 0, p + "norm3") if s != 1 else None))
+        self.head = pc(pfx + "conv2", 1, 0)
+
+    def run(self, k: Kernels, images: Sequence[torch.Tensor], tag: str, head_kwargs=None, head_out: Optional[View] = None) -> Optional[View]:
+        n = sum(int(im.shape[0]) for im in images)
+        H, W = int(images[0].shape[-2]), int(images[0].shape[-1])
+        inst = self.norm == "instance"
+        relu = L.ACT_NONE if inst else L.ACT_RELU
+        h2, w2 = (H + 1) // 2, (W + 1) // 2
+        x = k.view(tag + ".stem", n, h2, w2, 64)
+        b0 = 0
+        for im in images:
+            assert im.dtype == F32 and im.is_contiguous() and im.shape[1] == 3
+            nb = int(im.shape[0])
+            k.conv_smallc(im.data_ptr(), True, nb, 3, H, W, self.stem, relu, x.rows(b0, b0 + nb))
+            b0 += nb
+        if inst:
+            k.instnorm(x, True, None, False, x)
+        for bi, blk in enumerate(self.blocks):
+            c1, c2, dn = blk["conv1"], blk["conv2"], blk["down"]
+            oh = (x.h + 2 - 3) // c1.stride + 1
+            ow = (x.w + 2 - 3) // c1.stride + 1
+            y1 = k.view(f"{tag}.b{bi}.y1", n, oh, ow, c1.cout)
+            y2 = k.view(f"{tag}.b{bi}.y2", n, oh, ow, c2.cout)
+            if inst:
+                k.conv(c1, [x], y1)
+                k.instnorm(y1, True, None, False, y1)
+                k.conv(c2, [y1], y2)
+                res = x
+                if dn is not None:
+                    res = k.view(f"{tag}.b{bi}.dn", n, oh, ow, dn.cout)
+                    k.conv(dn, [x], res)
+                    k.instnorm(res, False, None, False, res)
+                k.instnorm(y2, True, res, True, y2)
+            else:
+                k.conv(c1, [x], y1, act=L.ACT_RELU)
+                res = x
+                if dn is not None:
+                    res = k.view(f"{tag}.b{bi}.dn", n, oh, ow, dn.cout)
+                    k.conv(dn, [x], res)
+                k.conv(c2, [y1], y2, act=L.ACT_RELU, residual=res, post_relu=True)
+            x = y2
+        if head_kwargs is not None:
+            k.conv(self.head, [x], **head_kwargs)
+            return None
+        out = head_out if head_out is not None else k.view(tag + ".out", n, x.h, x.w, self.out_dim)
+        k.conv(self.head, [x], out)
+        return out
+
+
+# ================================================================================ RAFT / GMA
+class FlowEstimatorEngine:
+    """RAFT.forward / RAFTGMA.forward (raft/raft.py:94-146, gma/gma.py:70-125) on the kernels."""
+
+    RADIUS = 4
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device, pfx: str = "", gma: bool = False):
+        self.k = Kernels(device)
+        self.device, self.gma, self.pfx = device, gma, pfx
+        self.repack(sd)
+
+    def repack(self, sd):
+        p, gma = self.pfx, self.gma
+        sd = {n: t.detach().to(self.device) for n, t in sd.items() if n.startswith(p)}
+        self.fnet = EncoderPlan(sd, p + "fnet.", "instance", 256)
+        self.cnet = EncoderPlan(sd, p + "cnet.", "batch", 256)
+        u = p + "update_block."
+
+        def pc(name, pad, **kw):
+            return PackedConv([sd[name + ".weight"]], [sd.get(name + ".bias")], 1, pad, **kw)
+
+        self.convc1 = pc(u + "encoder.convc1", (0, 0))
+        self.convc2 = pc(u + "encoder.convc2", (1, 1))
+        self.convf1 = pc(u + "encoder.convf1", (3, 3))
+        self.convf1.w = sd[u + "encoder.convf1.weight"].to(F32).permute(2, 3, 1, 0).reshape(98, 128).contiguous()
+        self.convf2 = pc(u + "encoder.convf2", (1, 1))
+        self.convm = pc(u + "encoder.conv", (1, 1))
+        g = u + "gru."
+        self.gru = []
+        for tag, pad in (("1", (0, 2)), ("2", (2, 0))):
+            zr = PackedConv([sd[f"{g}convz{tag}.weight"], sd[f"{g}convr{tag}.weight"]],
+                            [sd[f"{g}convz{tag}.bias"], sd[f"{g}convr{tag}.bias"]], 1, pad)
+            q = pc(f"{g}convq{tag}", pad)
+            self.gru.append((zr, q))
+        self.fh1 = pc(u + "flow_head.conv1", (1, 1))
+        self.fh2 = pc(u + "flow_head.conv2", (1, 1))
+        self.mk1 = pc(u + "mask.0", (1, 1))
+        self.mk2 = pc(u + "mask.2", (0, 0), mult=0.25)
+        if gma:
+            self.to_qk = pc(p + "att.to_qk", (0, 0))
+            self.to_v = pc(u + "aggregator.to_v", (0, 0))
+            self.gamma = float(sd[u + "aggregator.gamma"].item())
+            self.qk_scale = 128 ** -0.5
+
+    # ------------------------------------------------------------------------------------
+    def features(self, image1: torch.Tensor, image2: torch.Tensor, tag="fe"):
+        """fnet on both images + correlation pyramid + cnet (+ GMA attention)."""
+        k = self.k
+        B, _, H, W = image1.shape
+        assert H % 8 == 0 and W % 8 == 0 and H >= 128 and W >= 128, "H, W must be multiples of 8 and >= 128"
+        h, w = H // 8, W // 8
+        P = h * w
+        fm = self.fnet.run(k, [image1, image2], tag + ".fnet")
+        st = dict(B=B, h=h, w=w, P=P, H=H, W=W)
+        st["pyr"] = self.corr_pyramid(fm.rows(0, B), fm.rows(B, 2 * B), tag)
+        hid = k.view(tag + ".h", B, h, w, 128)
+        inp = k.view(tag + ".inp", B, h, w, 128)
+        self.cnet.run(k, [image1], tag + ".cnet", head_kwargs=dict(out=hid, out2=inp, act=L.ACT_TANH, act_split=128,
+                                                                   act2=L.ACT_RELU))
+        st["h"], st["inp"] = hid, inp
+        if self.gma:
+            st["attn"] = self.attention(inp, tag)
+        return st
+
+    def corr_pyramid(self, f1: View, f2: View, tag: str):
+        """CorrBlock.__init__ (raft/corr.py:8-22)."""
+        k = self.k
+        B, h, w, D = f1.b, f1.h, f1.w, f1.c
+        P = h * w
+        Pp = _p4(P)
+        f2t = k.buf(tag + ".f2t", B, D, Pp, zero=True)
+        k.transpose(f2, f2t, Pp)
+        lv = [k.buf(tag + ".pyr0", B * P, P)]
+        hh, ww = h, w
+        for l in range(1, 4):
+            hh, ww = hh // 2, ww // 2
+            lv.append(k.buf(f"{tag}.pyr{l}", B * P, hh * ww))
+        gemm = _Gemm(D, P, Pp)
+        k.conv(gemm, [f1], View(lv[0].view(B, h, w, P)), alpha=1.0 / math.sqrt(D), weight_ptr=f2t.data_ptr(),
+               weight_batch_stride=D * Pp, use_affine=False)
+        L.call("accflow_corr_pool_f32", lv[0].data_ptr(), B * P, h, w, lv[1].data_ptr(), lv[2].data_ptr(),
+               lv[3].data_ptr(), _stream())
+        return lv
+
+    def attention(self, inp: View, tag: str):
+        """Attention.forward (gma/modules.py:54-76), heads=1, content only."""
+        k = self.k
+        B, h, w = inp.b, inp.h, inp.w
+        P, Pp = h * w, _p4(h * w)
+        qk = k.view(tag + ".qk", B, h, w, 256)
+        k.conv(self.to_qk, [inp], qk)
+        kt = k.buf(tag + ".kt", B, 128, Pp, zero=True)
+        k.transpose(qk.ch(128, 256), kt, Pp)
+        attn = k.buf(tag + ".attn", B, P, P)
+        k.conv(_Gemm(128, P, Pp), [qk.ch(0, 128)], View(attn.view(B, h, w, P)), alpha=self.qk_scale,
+               weight_ptr=kt.data_ptr(), weight_batch_stride=128 * Pp, use_affine=False)
+        k.softmax_rows(attn, B * P, P)
+        return attn
+
+    def iterate(self, st, iters: int, flow_init: Optional[torch.Tensor], tag="fe") -> torch.Tensor:
+        """The GRU refinement loop + final convex upsample (raft/raft.py:121-146)."""
+        k = self.k
+        B, h, w, P, H, W = st["B"], st["h"], st["w"], st["P"], st["H"], st["W"]
+        s = _stream
+        lv = st["pyr"]
+        hid, inp = st["h"], st["inp"]
+        coords = k.buf(tag + ".coords", B, P, 2)
+        flow = k.buf(tag + ".flow", B, P, 2)
+        corr = k.view(tag + ".corr", B, h, w, 324)
+        cor1 = k.view(tag + ".cor1", B, h, w, 256)
+        cf = k.view(tag + ".corflo", B, h, w, 256)
+        flo1 = k.view(tag + ".flo1", B, h, w, 128)
+        mf = k.view(tag + ".mf", B, h, w, 128)
+        rh = k.view(tag + ".rh", B, h, w, 128)
+        z = k.view(tag + ".z", B, h, w, 128)
+        fh = k.view(tag + ".fh", B, h, w, 256)
+        delta = k.view(tag + ".delta", B, h, w, 2)
+        x_srcs = [inp, mf]
+        if self.gma:
+            vbuf = k.view(tag + ".v", B, h, w, 128)
+            mfg = k.view(tag + ".mfg", B, h, w, 128)
+            x_srcs = [inp, mf, mfg]
+            agg = _Gemm(P, 128, 128)
+        if flow_init is not None:
+            flow_init = flow_init.to(device=self.device, dtype=F32).contiguous()
+            assert tuple(flow_init.shape) == (B, 2, h, w)
+        L.call("accflow_coords_init_f32", None if flow_init is None else flow_init.data_ptr(), B, h, w,
+               coords.data_ptr(), s())
+        for _ in range(iters):
+            L.call("accflow_corr_lookup_f32", lv[0].data_ptr(), lv[1].data_ptr(), lv[2].data_ptr(), lv[3].data_ptr(),
+                   B, h, w, self.RADIUS, coords.data_ptr(), corr.ptr, corr.ld, flow.data_ptr(), mf.ch(126, 128).ptr,
+                   mf.ld, s())
+            k.conv(self.convc1, [corr], cor1, act=L.ACT_RELU)
+            k.conv(self.convc2, [cor1], cf.ch(0, 192), act=L.ACT_RELU)
+            k.conv_smallc(flow.data_ptr(), False, B, 2, h, w, self.convf1, L.ACT_RELU, flo1)
+            k.conv(self.convf2, [flo1], cf.ch(192, 256), act=L.ACT_RELU)
+            k.conv(self.convm, [cf], mf.ch(0, 126), act=L.ACT_RELU)
+            if self.gma:
+                # Aggregate.forward (gma/modules.py:102-115): mf + gamma * (attn @ to_v(mf))
+                k.conv(self.to_v, [mf], vbuf)
+                k.conv(agg, [View(st["attn"].view(B, h, w, P))], mfg, alpha=self.gamma, weight_ptr=vbuf.ptr,
+                       weight_batch_stride=P * 128, residual=mf, use_affine=False)
+            for zr, q in self.gru:
+                k.conv(zr, [hid] + x_srcs, epilogue=L.EPI_GRU_ZR, h=hid, z=z, out2=rh)
+                k.conv(q, [rh] + x_srcs, epilogue=L.EPI_GRU_Q, h=hid, z=z)
+            k.conv(self.fh1, [hid], fh, act=L.ACT_RELU)
+            k.conv(self.fh2, [fh], delta)
+            L.call("accflow_axpy_f32", coords.data_ptr(), delta.ptr, 1.0, B * P * 2, s())
+        # mask head + convex upsample: only the last iteration's is observable (raft.py:139-146)
+        k.conv(self.mk1, [hid], fh, act=L.ACT_RELU)
+        mask = k.view(tag + ".mask", B, h, w, 576)
+        k.conv(self.mk2, [fh], mask)
+        out = torch.empty(B, 2, H, W, device=self.device, dtype=F32)
+        L.call("accflow_convex_upsample_f32", coords.data_ptr(), 2, 1, mask.ptr, mask.ld, B, h, w, out.data_ptr(), s())
+        return out
+
+    def forward(self, image1, image2, iters=12, flow_init=None, tag="fe"):
+        image1 = image1.to(device=self.device, dtype=F32).contiguous()
+        image2 = image2.to(device=self.device, dtype=F32).contiguous()
+        with torch.cuda.device(self.device):
+            st = self.features(image1, image2, tag)
+            return self.iterate(st, iters, flow_init, tag)
+
+
+class _Gemm:
+    """Shape carrier for per-sample GEMMs run through the conv kernel (1x1, weights given at call)."""
+
+    def __init__(self, cin, cout, cout_pad):
+        self.cin, self.cout, self.cout_pad = cin, cout, cout_pad
+        self.kh = self.kw = self.stride = 1
+        self.pad_h = self.pad_w = 0
+        self.w = None
+        self.scale = None
+        self.shift = None
+        self.has_bias = False
+
+
+# ================================================================================ AccFlow
+class AccFlowEngine:
+    """AccFlow.iter / forward (networks/AccFlow_.py:157-201) on the kernels."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device, gma: bool):
+        self.device = device
+        self.ofe = FlowEstimatorEngine(sd, device, "ofe.", gma)
+        self.k = self.ofe.k
+        self.repack(sd, repack_ofe=False)
+
+    def repack(self, sd, repack_ofe=True):
+        if repack_ofe:
+            self.ofe.repack(sd)
+        sd = {n: t.detach().to(self.device) for n, t in sd.items() if not n.startswith("ofe.")}
+
+        def pc(name, pad, **kw):
+            return PackedConv([sd[name + ".weight"]], [sd.get(name + ".bias")], 1, (pad, pad), **kw)
+
+        self.fe1 = pc("flow_encoder.conv1", 3)
+        self.fe1.w = sd["flow_encoder.conv1.weight"].to(F32).permute(2, 3, 1, 0).reshape(98, 128).contiguous()
+        self.fe2 = pc("flow_encoder.conv2", 1)
+        self.fe3 = pc("flow_encoder.conv3", 0)
+        self.context = EncoderPlan(sd, "context.", "none", 128)
+        a = "accplus."
+        self.a10, self.a12 = pc(a + "conv1.0", 1), pc(a + "conv1.2", 1)
+        self.a20, self.a22 = pc(a + "conv2.0", 1), pc(a + "conv2.2", 1)
+        self.a24 = pc(a + "conv2.4.conv", 1, out_scale=torch.exp(sd[a + "conv2.4.scale"].to(F32).reshape(-1) * 3))
+        dw = sd[a + "dconv.weight"]                                  # (128,128,3,3) -> 1x1 over 9*128
+        self.dcn = PackedConv([dw.permute(0, 2, 3, 1).reshape(dw.shape[0], -1, 1, 1)], [sd[a + "dconv.bias"]], 1, (0, 0))
+        self.a30, self.a32 = pc(a + "conv3.0", 1), pc(a + "conv3.2", 1)
+        self.a40, self.a42, self.a44 = pc(a + "conv4.0", 1), pc(a + "conv4.2", 1), pc(a + "conv4.4", 0)
+        self.bl0, self.bl2 = pc("blending.mask.0", 0), pc("blending.mask.2", 1)
+        self.df0, self.df2 = pc("flow_decoder.flow.0", 1), pc("flow_decoder.flow.2", 1)
+        self.dm0, self.dm2 = pc("flow_decoder.mask.0", 1), pc("flow_decoder.mask.2", 0)
+
+    def iter(self, I1, I2, In, F2n: Optional[torch.Tensor], iters=12):
+        """Returns (out_small NCHW (b,2,h,w), out NCHW (b,2,H,W)); F2n is NCHW (b,2,h,w) or None."""
+        k, s = self.k, _stream
+        dev = self.device
+        I1, I2, In = (t.to(device=dev, dtype=F32).contiguous() for t in (I1, I2, In))
+        b, _, H, W = I1.shape
+        assert H % 8 == 0 and W % 8 == 0
+        h, w = H // 8, W // 8
+        P = h * w
+        with torch.cuda.device(dev):
+            if F2n is None:
+                flows = self.ofe.forward(torch.cat([I1, I1, I2]), torch.cat([I2, In, In]), iters, tag="ofe3")
+                npair = 3
+            else:
+                flows = self.ofe.forward(torch.cat([I1, I1]), torch.cat([I2, In]), iters, tag="ofe2")
+                npair = 2
+            lr = k.buf("acc.lr", npair * b, P, 2)                       # [dflow | flow_ini | (F2n)]
+            L.call("accflow_downflow8_f32", flows.data_ptr(), npair * b, H, W, lr.data_ptr(), s())
+            fin = k.buf("acc.fin", 3 * b, P, 2)                          # encoder order: flow_ini, dflow, F2n
+            fin[0:b].copy_(lr[b:2 * b])
+            fin[b:2 * b].copy_(lr[0:b])
+            if F2n is None:
+                fin[2 * b:].copy_(lr[2 * b:])
+            else:
+                fin[2 * b:].copy_(F2n.to(device=dev, dtype=F32).permute(0, 2, 3, 1).reshape(b, P, 2))
+            dflow, flow_ini = fin[b:2 * b], fin[0:b]
+            # FlowEncoder (AccFlow_.py:56-65)
+            e1 = k.view("acc.e1", 3 * b, h, w, 128)
+            e2 = k.view("acc.e2", 3 * b, h, w, 256)
+            enc = k.view("acc.enc", 3 * b, h, w, 128)
+            k.conv_smallc(fin.data_ptr(), False, 3 * b, 2, h, w, self.fe1, L.ACT_RELU, e1)
+            k.conv(self.fe2, [e1], e2, act=L.ACT_RELU)
+            k.conv(self.fe3, [e2], enc)
+            f_ini, df, f = enc.rows(0, b), enc.rows(b, 2 * b), enc.rows(2 * b, 3 * b)
+            # context encoder (AccFlow_.py:193)
+            ctx = self.context.run(k, [I1, I2, In], "acc.ctx")
+            c1, c2, cn = ctx.rows(0, b), ctx.rows(b, 2 * b), ctx.rows(2 * b, 3 * b)
+            # occlusion + error maps (getOcc, AccFlow_.py:127-135,194,197)
+            occ = k.view("acc.occ", b, h, w, 1)
+            emap = k.view("acc.emap", b, h, w, 128)
+            L.call("accflow_warp_occ_f32", c1.ptr, c1.ld, c2.ptr, c2.ld, dflow.data_ptr(), b, h, w, 128, occ.ptr, 1,
+                   None, 0, s())
+            L.call("accflow_warp_occ_f32", c1.ptr, c1.ld, cn.ptr, cn.ld, flow_ini.data_ptr(), b, h, w, 128, None, 0,
+                   emap.ptr, emap.ld, s())
+            # AccPlus (AccFlow_.py:97-109)
+            t256 = k.view("acc.t256", b, h, w, 256)
+            x1 = k.view("acc.x1", b, h, w, 128)
+            x2 = k.view("acc.x2", b, h, w, 128)
+            om = k.view("acc.om", b, h, w, 28)
+            col = k.buf("acc.col", b, P, 9 * 128)
+            fdc = k.view("acc.fdc", b, h, w, 128)
+            k.conv(self.a10, [df, f, occ], t256, act=L.ACT_RELU)
+            k.conv(self.a12, [t256], x1)
+            k.conv(self.a20, [x1, c1], t256, act=L.ACT_RELU)
+            k.conv(self.a22, [t256], x2, act=L.ACT_RELU)
+            k.conv(self.a24, [x2], om.ch(0, 27))
+            L.call("accflow_deform_gather_f32", f.ptr, f.ld, om.ptr, om.ld, b, h, w, 128, col.data_ptr(), s())
+            k.conv(self.dcn, [View(col.view(b, h, w, 9 * 128))], fdc)
+            k.conv(self.a30, [fdc, df, occ], t256, act=L.ACT_RELU)
+            k.conv(self.a32, [t256], x1)
+            k.conv(self.a40, [x1, c1, fdc, df], t256, act=L.ACT_RELU)
+            k.conv(self.a42, [t256], x2, act=L.ACT_RELU)
+            f_acc = k.view("acc.facc", b, h, w, 128)
+            k.conv(self.a44, [x2], f_acc)
+            # Blending (AccFlow_.py:122-124)
+            m = k.view("acc.m", b, h, w, 1)
+            k.conv(self.bl0, [emap], t256, act=L.ACT_RELU)
+            k.conv(self.bl2, [t256], m, act=L.ACT_SIGMOID)
+            fuse = k.view("acc.fuse", b, h, w, 128)
+            L.call("accflow_blend_f32", f_ini.ptr, f_acc.ptr, m.ptr, 1, b * P, 128, fuse.ptr, s())
+            # FlowDecoder (AccFlow_.py:40-45)
+            small = torch.empty(b, h, w, 2, device=dev, dtype=F32)
+            k.conv(self.df0, [fuse], t256, act=L.ACT_RELU)
+            k.conv(self.df2, [t256], View(small))
+            mask = k.view("acc.mask", b, h, w, 576)
+            k.conv(self.dm0, [fuse], t256, act=L.ACT_RELU)
+            k.conv(self.dm2, [t256], mask)
+            out = torch.empty(b, 2, H, W, device=dev, dtype=F32)
+            L.call("accflow_convex_upsample_f32", small.data_ptr(), 2, 0, mask.ptr, mask.ld, b, h, w, out.data_ptr(), s())
+        return small.permute(0, 3, 1, 2).contiguous(), out
+
+    def forward(self, images: List[torch.Tensor], iters=12) -> List[torch.Tensor]:
+        flow = None
+        outs = []
+        for i in range(2, len(images)):
+            flow, up = self.iter(images[i], images[i - 1], images[0], flow, iters)
+            outs.append(up)
+        return outs

@@ -1,0 +1,64 @@
+"""Shared base of RAFT / RAFTGMA: parameter tree + CUDA engine dispatch."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .. import spec as S
+from . import _tree
+
+
+class FlowEstimatorBase(nn.Module):
+    _GMA = False
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.hidden_dim = 128
+        self.context_dim = 128
+        args.corr_levels = 4
+        args.corr_radius = 4
+        if "dropout" not in args:
+            args.dropout = 0
+        _tree.populate(self, S.gma_entries() if self._GMA else S.raft_entries())
+        self._engines = {}
+
+    # ---- reference API -------------------------------------------------------------------
+    def freeze_bn(self):
+        """Reference: put BatchNorm in eval mode.  This implementation always evaluates BN
+        with running statistics (inference path), so this is a no-op kept for API parity."""
+        return None
+
+    def initialize_flow(self, img):
+        """coords0, coords1 = pixel grids at 1/8 resolution, (N,2,H/8,W/8), channel 0 = x."""
+        n, _, h, w = img.shape
+        ys, xs = torch.meshgrid(torch.arange(h // 8, device=img.device), torch.arange(w // 8, device=img.device),
+                                indexing="ij")
+        grid = torch.stack([xs, ys], 0).float()[None].repeat(n, 1, 1, 1)
+        return grid, grid.clone()
+
+    def upsample_flow(self, flow, mask):
+        """Convex 8x upsampling of (N,2,h,w) flow with (N,576,h,w) mask logits -> (N,2,8h,8w)."""
+        from ..ops import convex_upsample
+        return convex_upsample(flow, mask)
+
+    def engine(self, device=None):
+        from ..engine import FlowEstimatorEngine
+        device = next(self.parameters()).device if device is None else device
+        if device.type != "cuda":
+            raise RuntimeError("accflow_b200 runs on CUDA (sm_100a) only; there is no CPU path — move the "
+                               "module to a GPU (.cuda()) before calling it")
+        sig = _tree.signature(self)
+        hit = self._engines.get(device)
+        if hit is None or hit[0] != sig:
+            sd = {k: v for k, v in self.state_dict().items()}
+            hit = (sig, FlowEstimatorEngine(sd, device, "", self._GMA))
+            if not getattr(self, "_is_replica", False):
+                self._engines[device] = hit
+        return hit[1]
+
+    @torch.no_grad()
+    def forward(self, image1, image2, iters=12, flow_init=None):
+        """Estimate optical flow between a pair of frames -> (B,2,H,W) fp32."""
+        eng = self.engine(image1.device if image1.is_cuda else None)
+        return eng.forward(image1, image2, iters, flow_init)

@@ -1,0 +1,168 @@
+/*
+ * accflow_b200 — C ABI of the B200 (sm_100a) kernels behind AccFlow's flow-estimation +
+ * backward-accumulation path.  This header is the drop-in boundary: plain pointers and
+ * sizes, no torch types.  The Python host (accflow_b200/_lib.py) binds it with ctypes; a
+ * reference maintainer would bind the same symbols.
+ *
+ * Conventions
+ *   - Every buffer is DEVICE memory owned by the caller (kernels never allocate or free).
+ *   - Activations are NHWC fp32 (or bf16 where a function says so): element (n,y,x,c) of a
+ *     "slice" lives at ptr[((n*H + y)*W + x)*ld + c]; `ld` >= channels lets several
+ *     producers write disjoint channel ranges of one buffer, which is how torch.cat([...],1)
+ *     in the reference is realised without a copy.
+ *   - All work is launched on `stream` (a cudaStream_t passed as void*); no implicit sync,
+ *     no default-stream use; safe for concurrent calls on different devices/streams.  The
+ *     caller selects the device (cudaSetDevice / torch.cuda.device).
+ *   - Return value: 0 = ok, <0 = invalid argument (see accflow_last_error), >0 = cudaError_t.
+ *     No C++ exception crosses the boundary.
+ *
+ * Each entry point cites the reference code (file:line under the upstream repo) it replaces.
+ */
+#ifndef ACCFLOW_B200_H_
+#define ACCFLOW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACCFLOW_ABI_VERSION 1
+#if defined(__GNUC__)
+#define ACCFLOW_API __attribute__((visibility("default")))
+#else
+#define ACCFLOW_API
+#endif
+
+/* activation codes */
+enum { ACCFLOW_ACT_NONE = 0, ACCFLOW_ACT_RELU = 1, ACCFLOW_ACT_SIGMOID = 2, ACCFLOW_ACT_TANH = 3 };
+/* epilogue modes of accflow_conv2d */
+enum {
+  ACCFLOW_EPI_STORE = 0,  /* out = post(res + act(acc*alpha*scale[c] + shift[c]))                 */
+  ACCFLOW_EPI_GRU_ZR = 1, /* cout = 2*hd: z=sigmoid -> z buffer; r=sigmoid -> out2 = r*h          */
+  ACCFLOW_EPI_GRU_Q = 2   /* q = tanh(.) ; h = (1-z)*h + z*q  (in place)                          */
+};
+
+#define ACCFLOW_MAX_SRC 4
+
+/* One convolution / GEMM launch.  Replaces every nn.Conv2d (+ following elementwise ops) on
+ * the path: raft/update.py:6-14,33-60,79-136; raft/extractor.py:54-63,201-225;
+ * gma/modules.py:57-74,105-113 (QK^T and attn@V as 1x1 "convs" with per-sample weights);
+ * AccFlow_.py:13-124; networks/modules.py:94-97. */
+typedef struct accflow_conv_desc {
+  /* input: nsrc NHWC slices concatenated along channels, all (batch, in_h, in_w) */
+  const float* src[ACCFLOW_MAX_SRC];
+  int src_c[ACCFLOW_MAX_SRC];
+  int src_ld[ACCFLOW_MAX_SRC];
+  int nsrc;
+  int batch, in_h, in_w;
+  /* filter: packed [kh*kw][sum(src_c)][cout_pad] fp32, cout contiguous, cout_pad % 4 == 0 */
+  const float* weight;
+  long long weight_batch_stride; /* elements between per-sample filters; 0 = shared */
+  int kh, kw, stride, pad_h, pad_w;
+  int cout, cout_pad;
+  /* epilogue */
+  float alpha;        /* scalar multiplier on the accumulator (1.0 if unused) */
+  const float* scale; /* [cout] or NULL (=1) */
+  const float* shift; /* [cout] or NULL (=0); carries the bias */
+  int act;            /* activation for channels < act_split (or all when act_split == 0) */
+  int act_split;      /* 0 = off; channels >= act_split use act2 and go to out2 (if non-NULL) */
+  int act2;
+  const float* residual; /* NHWC slice added after the activation, or NULL */
+  int res_ld;
+  int post_relu;      /* ReLU after the residual add */
+  int epilogue;       /* ACCFLOW_EPI_* */
+  float* out;  int out_ld;
+  float* out2; int out2_ld; /* split destination / GRU r*h destination */
+  float* h;    int h_ld;    /* GRU hidden state (read for ZR, read+written for Q) */
+  float* z;    int z_ld;    /* GRU update gate buffer (written by ZR, read by Q) */
+} accflow_conv_desc;
+
+ACCFLOW_API int accflow_abi_version(void);
+/* Copies the calling thread's last error message (NUL-terminated) into buf. */
+ACCFLOW_API int accflow_last_error(char* buf, size_t len);
+/* Number of kernels this library has launched since load / last reset (bench "gpu_launches"). */
+ACCFLOW_API long long accflow_launch_count(int reset);
+
+/* Generic fp32 convolution (exact-fp32 arithmetic on the FFMA pipe). */
+ACCFLOW_API int accflow_conv2d_f32(const accflow_conv_desc* d, void* stream);
+
+/* Small-input-channel KSxKS convolution (cin in {2,3}), fused affine + activation.
+ * 7x7/s2 stem of BasicEncoder (raft/extractor.py:163-167,209) reading NCHW images, and the
+ * 7x7 2->128 flow convs (raft/update.py:85,92; AccFlow_.py:51,62) reading NHWC flow.
+ * weight: packed [cin*ks*ks][cout] fp32 with k = (ky*ks + kx)*cin + c. */
+ACCFLOW_API int accflow_conv_smallc_f32(const float* in, int in_is_nchw, int batch, int cin, int in_h, int in_w,
+                            const float* weight, const float* scale, const float* shift, int ks,
+                            int stride, int cout, int act, float* out, int out_ld, void* stream);
+
+/* InstanceNorm2d(affine=False, eps) [+ReLU] [+residual, +ReLU] on NHWC, two-phase
+ * (raft/extractor.py:35-38,54-63,150-151,210).  partial: workspace >= batch*chunks*c*2 floats
+ * where chunks = accflow_instnorm_chunks(h*w); stats: >= batch*c*2 floats. */
+ACCFLOW_API int accflow_instnorm_chunks(int hw);
+ACCFLOW_API int accflow_instnorm_f32(const float* x, int batch, int hw, int c, float eps, int relu,
+                         const float* residual, int post_relu, float* out, float* partial,
+                         float* stats, void* stream);
+
+/* [B,HW,C] (NHWC slice) -> [B,C,HW]: fmap2 / k operand of the per-sample GEMMs
+ * (raft/corr.py:49-53 `fmap1.transpose(1,2) @ fmap2`; gma/modules.py:66-73). */
+ACCFLOW_API int accflow_nhwc_transpose_f32(const float* in, int batch, int hw, int c, int in_ld, float* out_nchw,
+                                           int out_ld, void* stream); /* out row (per channel) stride >= hw */
+
+/* 3x avg_pool2d(2,2) over the target dims of the level-0 correlation volume
+ * (raft/corr.py:20-22).  lvl0: [n_rows][h*w]; lvl1..3 written densely with floor sizes. */
+ACCFLOW_API int accflow_corr_pool_f32(const float* lvl0, long long n_rows, int h, int w, float* lvl1, float* lvl2,
+                          float* lvl3, void* stream);
+
+/* CorrBlock.__call__ (raft/corr.py:24-45 + raft/utils/utils.py:66-80): 4-level (2r+1)^2
+ * bilinear window lookup, zero padding.  coords: [B,h*w,2] (x,y).  out: NHWC slice with
+ * 4*(2r+1)^2 channels, channel = lvl*(2r+1)^2 + a*(2r+1) + b, a -> x offset, b -> y offset.
+ * Also emits flow = coords - grid (raft/raft.py:131) to flow_out [B,h*w,2] and, if mf_tail
+ * is non-NULL, into channels [0,2) of that slice (the cat([out, flow]) of update.py:97). */
+ACCFLOW_API int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                            int batch, int h, int w, int radius, const float* coords, float* out,
+                            int out_ld, float* flow_out, float* mf_tail, int mf_ld, void* stream);
+
+/* coords1 = grid + flow_init (raft/raft.py:121-124); flow_init NULL -> zeros.  NCHW (B,2,h,w) in. */
+ACCFLOW_API int accflow_coords_init_f32(const float* flow_init_nchw, int batch, int h, int w, float* coords, void* stream);
+/* coords += delta ([B,h*w,2] both; raft/raft.py:136) */
+ACCFLOW_API int accflow_axpy_f32(float* y, const float* x, float a, long long n, void* stream);
+
+/* Convex 8x upsampling (raft/raft.py:81-92, gma/gma.py:57-68, AccFlow_.py:27-38).
+ * flow: NHWC [B,h,w,2] slice (coords - grid if coords_mode), mask: NHWC [B,h,w,576] slice,
+ * out: NCHW (B,2,8h,8w) fp32. */
+ACCFLOW_API int accflow_convex_upsample_f32(const float* flow, int flow_ld, int coords_mode, const float* mask,
+                                int mask_ld, int batch, int h, int w, float* out_nchw, void* stream);
+
+/* downflow8 (AccFlow_.py:138-142): align_corners bilinear resize of NCHW (B,2,H,W) to 1/8,
+ * divided by 8, written NHWC [B,h,w,2]. */
+ACCFLOW_API int accflow_downflow8_f32(const float* flow_nchw, int batch, int H, int W, float* out_nhwc, void* stream);
+
+/* getOcc (AccFlow_.py:127-135) with backwarp (networks/utils.py:96-124), NHWC.
+ * occ_out (binary branch, [B,h*w] 0/1) and/or emap_out (|c1 - warp(c2)| NHWC) may be NULL. */
+ACCFLOW_API int accflow_warp_occ_f32(const float* c1, int c1_ld, const float* c2, int c2_ld, const float* flow,
+                         int batch, int h, int w, int c, float* occ_out, int occ_ld, float* emap_out,
+                         int emap_ld, void* stream);
+
+/* Generic backwarp of an NCHW tensor by an NCHW flow (networks/utils.py:96-124), used by the
+ * metric stage (test_cvo.py:53-78). */
+ACCFLOW_API int accflow_backwarp_nchw_f32(const float* img, const float* flow, int batch, int c, int h, int w,
+                              float* out, void* stream);
+
+/* Modulated deformable 3x3 gather (torchvision deform_conv2d sampling, AccFlow_.py:83,104):
+ * offmask NHWC slice with 27 channels (18 offsets dy,dx interleaved per tap, then 9 mask
+ * logits -> sigmoid applied here).  col: [B,h*w,9*c] (tap-major) for the following GEMM. */
+ACCFLOW_API int accflow_deform_gather_f32(const float* x, int x_ld, const float* offmask, int om_ld, int batch,
+                              int h, int w, int c, float* col, void* stream);
+
+/* Blending lerp (AccFlow_.py:124): out = f1*m + (1-m)*f2, m: [B,h*w] (already sigmoid). */
+ACCFLOW_API int accflow_blend_f32(const float* f1, const float* f2, const float* m, int m_ld, long long npix, int c,
+                      float* out, void* stream);
+
+/* Row softmax in place (gma/modules.py:74): x [rows][n]. */
+ACCFLOW_API int accflow_softmax_rows_f32(float* x, long long rows, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACCFLOW_B200_H_ */

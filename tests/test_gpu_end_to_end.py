@@ -1,0 +1,108 @@
+"""End-to-end parity of the CUDA path behind the reference's module API. Needs a GPU."""
+import pytest
+import torch
+
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+FLOW_TOL_PX = 1e-3       # north star: flows within 1e-3 px max-abs in fp32
+EPE_TOL_PX = 1e-4        # per-clip EPE within 1e-4 px
+
+
+def build(kind):
+    from accflow_b200.networks import build_flow_estimator
+    from accflow_b200.networks.AccFlow_ import AccFlow
+    m = build_flow_estimator(kind)
+    if kind.startswith("acc"):
+        m = AccFlow(m)
+    m.load_state_dict(cases.weights(kind))
+    return m.cuda().eval()
+
+
+def maxdiff(a, b):
+    return float((a.detach().float().cpu() - torch.as_tensor(b).float()).abs().max())
+
+
+@pytest.mark.parametrize("kind", ["raft", "gma"])
+def test_pair_matches_reference_golden(golden, kind):
+    g, _ = golden
+    m = build(kind)
+    i1, i2, finit = cases.pair_case()
+    flow = m(i1.cuda(), i2.cuda(), iters=12, flow_init=finit.cuda())
+    assert flow.shape == (1, 2, 128, 128) and flow.dtype == torch.float32
+    assert maxdiff(flow, g[f"{kind}.flow_up"]) < FLOW_TOL_PX
+    assert maxdiff(m(i1.cuda(), i2.cuda(), iters=3), g[f"{kind}.flow_up_noinit_it3"]) < FLOW_TOL_PX
+
+
+@pytest.mark.parametrize("kind", ["acc+raft", "acc+gma"])
+def test_clip_matches_reference_golden(golden, kind):
+    g, _ = golden
+    m = build(kind)
+    imgs = [t.cuda() for t in cases.clip_case()]
+    flows = m(images=imgs, test_mode=False)
+    assert len(flows) == 2
+    for i, f in enumerate(flows):
+        assert maxdiff(f, g[f"{kind}.flow{i}"]) < FLOW_TOL_PX, i
+
+
+def test_dataparallel_prefix_checkpoint_loads():
+    """test_cvo.py:17-20 loads checkpoints through nn.DataParallel ('module.' prefix)."""
+    from accflow_b200.networks import build_flow_estimator
+    from accflow_b200.networks.AccFlow_ import AccFlow
+    sd = cases.weights("acc+raft")
+    model = torch.nn.DataParallel(AccFlow(build_flow_estimator("acc|raft").cuda().eval()), device_ids=[0])
+    model.load_state_dict({"module." + k: v for k, v in sd.items()})
+    model.cuda().eval()
+    imgs = [t.cuda() for t in cases.clip_case(frames=3)]
+    out = model(images=imgs, test_mode=False)[-1]
+    assert out.shape == (1, 2, 128, 128)
+
+
+@pytest.mark.parametrize("kind,size,batch", [("raft", 512, 1), ("gma", 256, 2), ("raft", (384, 256), 2)])
+def test_pair_vs_oracle_full_size(kind, size, batch):
+    """BASELINE configs[0] shape (512x512, 12 iters) and non-square / batched variants vs the oracle."""
+    from accflow_b200.data import make_clip
+    from oracle import flow_oracle as fo
+    hw = (size, size) if isinstance(size, int) else size
+    clips = [make_clip(7 + i, size=max(hw)) for i in range(batch)]
+    i1 = torch.cat([c["imgs"][3] for c in clips])[..., : hw[0], : hw[1]].contiguous()
+    i2 = torch.cat([c["imgs"][0] for c in clips])[..., : hw[0], : hw[1]].contiguous()
+    sd = cases.weights(kind)
+    ref = fo.flow_estimator(sd, i1, i2, 12)
+    m = build(kind)
+    out = m(i1.cuda(), i2.cuda())
+    assert maxdiff(out, ref) < FLOW_TOL_PX
+    # the pair axis is independent: permuting the batch permutes the result
+    if batch > 1:
+        out2 = m(i1.flip(0).cuda(), i2.flip(0).cuda())
+        assert maxdiff(out2.flip(0), out.cpu()) < 1e-4
+
+
+def test_clip_vs_oracle_and_epe():
+    """7-frame clip (BASELINE configs[1] structure) at 256x256: flows + per-clip EPE."""
+    from accflow_b200.data import make_batch
+    from oracle import flow_oracle as fo
+    from oracle import ops
+    batch = make_batch([11, 12], size=256)
+    sd = cases.weights("acc+raft")
+    ref = fo.accflow_forward(sd, batch["imgs"])
+    m = build("acc+raft")
+    out = m(images=[t.cuda() for t in batch["imgs"]], test_mode=False)
+    assert len(out) == 5
+    for a, b in zip(out, ref):
+        assert maxdiff(a, b) < FLOW_TOL_PX
+    bflow, fflow = batch["bflows"][-1], batch["fflows"][-1]
+    occ_bw, _ = ops.calc_occ_mask(bflow, fflow)
+    e_ref = ops.cal_epe(ref[-1], bflow, occ_bw)
+    e_out = ops.cal_epe(out[-1].cpu(), bflow, occ_bw)
+    for a, b in zip(e_out, e_ref):
+        assert float((a - b).abs().max()) < EPE_TOL_PX
+
+
+def test_no_cpu_fallback():
+    from accflow_b200.networks import build_flow_estimator
+    m = build_flow_estimator("raft")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 128, 128), torch.zeros(1, 3, 128, 128))

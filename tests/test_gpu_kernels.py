@@ -1,0 +1,244 @@
+"""Per-kernel parity (CUDA path through the C ABI vs oracle / golden fixtures). Needs a GPU."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+@pytest.fixture(scope="module")
+def K():
+    from accflow_b200.engine import Kernels
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return Kernels(torch.device("cuda:0"))
+
+
+def dev(t):
+    return t.cuda()
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def maxdiff(a, b):
+    a = a.detach().float().cpu()
+    b = torch.as_tensor(b).float()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max())
+
+
+def test_library_loaded_and_counts_launches(K):
+    from accflow_b200 import _lib as L
+    L.call("accflow_launch_count", 1)
+    x = torch.zeros(4, device="cuda")
+    L.call("accflow_axpy_f32", x.data_ptr(), x.data_ptr(), 1.0, 4, None)
+    assert L.call("accflow_launch_count", 0) == 1
+
+
+# ------------------------------------------------------------------ generic convolution
+CONV_CASES = [
+    # (B, cins, H, W, cout, kh, kw, stride, pad_h, pad_w)
+    (2, [128], 16, 16, 256, 3, 3, 1, 1, 1),
+    (1, [324], 20, 18, 256, 1, 1, 1, 0, 0),
+    (2, [128, 128, 128], 16, 24, 256, 1, 5, 1, 0, 2),
+    (2, [128, 256], 24, 16, 128, 5, 1, 1, 2, 0),
+    (1, [128, 128, 1], 10, 12, 256, 3, 3, 1, 1, 1),      # AccPlus conv1.0: cat[df, f, o]
+    (1, [256], 17, 19, 2, 3, 3, 1, 1, 1),                # flow head conv2 (cout 2), ragged map
+    (2, [64], 32, 32, 96, 3, 3, 2, 1, 1),                # encoder stride-2 block
+    (2, [64], 32, 32, 96, 1, 1, 2, 0, 0),                # encoder downsample
+    (1, [128], 9, 7, 27, 3, 3, 1, 1, 1),                 # ZeroConv2d
+    (1, [130], 8, 8, 126, 3, 3, 1, 1, 1),                # cin not a multiple of 4 (scalar loader)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_matches_torch(K, case):
+    from accflow_b200 import _lib as L
+    from accflow_b200.engine import PackedConv, View
+    B, cins, H, W, cout, kh, kw, stride, ph, pw = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    xs = [torch.randn(B, c, H, W, generator=g) for c in cins]
+    w = torch.randn(cout, sum(cins), kh, kw, generator=g) / math.sqrt(sum(cins) * kh * kw)
+    b = torch.randn(cout, generator=g)
+    ref = torch.relu(F.conv2d(torch.cat(xs, 1), w, b, stride=stride, padding=(ph, pw)))
+    pc = PackedConv([dev(w)], [dev(b)], stride, (ph, pw))
+    srcs = [View(dev(nhwc(x))) for x in xs]
+    out = torch.empty(B, ref.shape[2], ref.shape[3], cout, device="cuda")
+    K.conv(pc, srcs, View(out), act=L.ACT_RELU)
+    torch.cuda.synchronize()
+    assert maxdiff(out.permute(0, 3, 1, 2), ref) < 2e-5
+
+
+def test_conv2d_channel_slices_and_residual(K):
+    """Sources / destinations that are channel slices of wider buffers (the cat-free layout)."""
+    from accflow_b200 import _lib as L
+    from accflow_b200.engine import PackedConv, View
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 2, 12, 14
+    wide = torch.randn(B, H, W, 200, generator=g).cuda()
+    res = torch.randn(B, H, W, 64, generator=g).cuda()
+    w = torch.randn(64, 96, 3, 3, generator=g) * 0.05
+    b = torch.randn(64, generator=g)
+    gam, beta = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g)
+    rm, rv = torch.randn(64, generator=g) * 0.1, torch.rand(64, generator=g) + 0.5
+    x = wide[..., 40:136].permute(0, 3, 1, 2).cpu()
+    y = F.conv2d(x, w, b, padding=1)
+    y = F.batch_norm(y, rm, rv, gam, beta, False, 0.0, 1e-5)
+    ref = torch.relu(res.cpu().permute(0, 3, 1, 2) + torch.relu(y))
+    pc = PackedConv([dev(w)], [dev(b)], 1, (1, 1), bn=(dev(gam), dev(beta), dev(rm), dev(rv), 1e-5))
+    outw = torch.zeros(B, H, W, 100, device="cuda")
+    K.conv(pc, [View(wide).ch(40, 136)], View(outw).ch(20, 84), act=L.ACT_RELU, residual=View(res), post_relu=True)
+    torch.cuda.synchronize()
+    assert maxdiff(outw[..., 20:84].permute(0, 3, 1, 2), ref) < 2e-5
+    assert float(outw[..., :20].abs().max()) == 0 and float(outw[..., 84:].abs().max()) == 0
+
+
+def test_gru_epilogues(K):
+    """SepConvGRU half-step (raft/update.py:45-52) through the fused ZR / Q epilogues."""
+    from accflow_b200 import _lib as L
+    from accflow_b200.engine import PackedConv, View
+    g = torch.Generator().manual_seed(4)
+    B, H, W = 2, 12, 16
+    h = torch.tanh(torch.randn(B, 128, H, W, generator=g))
+    x = torch.randn(B, 256, H, W, generator=g)
+    ws = [torch.randn(128, 384, 1, 5, generator=g) * 0.03 for _ in range(3)]
+    bs = [torch.randn(128, generator=g) * 0.1 for _ in range(3)]
+    hx = torch.cat([h, x], 1)
+    z = torch.sigmoid(F.conv2d(hx, ws[0], bs[0], padding=(0, 2)))
+    r = torch.sigmoid(F.conv2d(hx, ws[1], bs[1], padding=(0, 2)))
+    q = torch.tanh(F.conv2d(torch.cat([r * h, x], 1), ws[2], bs[2], padding=(0, 2)))
+    ref = (1 - z) * h + z * q
+    zr = PackedConv([dev(ws[0]), dev(ws[1])], [dev(bs[0]), dev(bs[1])], 1, (0, 2))
+    qc = PackedConv([dev(ws[2])], [dev(bs[2])], 1, (0, 2))
+    hv, xv = View(dev(nhwc(h))), View(dev(nhwc(x)))
+    zb, rh = View(torch.empty(B, H, W, 128, device="cuda")), View(torch.empty(B, H, W, 128, device="cuda"))
+    K.conv(zr, [hv, xv], epilogue=L.EPI_GRU_ZR, h=hv, z=zb, out2=rh)
+    K.conv(qc, [rh, xv], epilogue=L.EPI_GRU_Q, h=hv, z=zb)
+    torch.cuda.synchronize()
+    assert maxdiff(hv.t.permute(0, 3, 1, 2), ref) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [(3, 2, 64, True, 40, 56), (2, 1, 128, False, 18, 21)])
+def test_conv_smallc(K, cfg):
+    from accflow_b200 import _lib as L
+    from accflow_b200.engine import PackedConv, View
+    cin, stride, cout, is_nchw, H, W = cfg
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 7, 7, generator=g) * 0.1
+    b = torch.randn(cout, generator=g)
+    ref = torch.relu(F.conv2d(x, w, b, stride=stride, padding=3))
+    pc = PackedConv([dev(w)], [dev(b)], stride, (3, 3))
+    pc.w = dev(w).permute(2, 3, 1, 0).reshape(cin * 49, cout).contiguous()
+    xin = dev(x) if is_nchw else dev(nhwc(x))
+    out = torch.empty(2, ref.shape[2], ref.shape[3], cout, device="cuda")
+    K.conv_smallc(xin.data_ptr(), is_nchw, 2, cin, H, W, pc, L.ACT_RELU, View(out))
+    torch.cuda.synchronize()
+    assert maxdiff(out.permute(0, 3, 1, 2), ref) < 2e-5
+
+
+@pytest.mark.parametrize("c,hw", [(64, (40, 52)), (96, (33, 20)), (128, (16, 16))])
+def test_instance_norm(K, c, hw):
+    from accflow_b200.engine import View
+    from oracle import ops
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(3, c, *hw, generator=g) * 2 + 3.0           # large mean: cancellation check
+    res = torch.randn(3, c, *hw, generator=g)
+    ref = torch.relu(res + torch.relu(ops.instance_norm(x)))
+    xv = View(dev(nhwc(x)))
+    K.instnorm(xv, True, View(dev(nhwc(res))), True, xv)
+    torch.cuda.synchronize()
+    assert maxdiff(xv.t.permute(0, 3, 1, 2), ref) < 2e-5
+
+
+# ------------------------------------------------------------------ correlation
+def test_corr_pyramid_and_lookup(K, golden):
+    from accflow_b200 import _lib as L
+    from accflow_b200.engine import FlowEstimatorEngine, View
+    g, _ = golden
+    f1, f2, coords = cases.corr_case()
+    eng = FlowEstimatorEngine.__new__(FlowEstimatorEngine)
+    eng.k = K
+    lv = eng.corr_pyramid(View(dev(nhwc(f1))), View(dev(nhwc(f2))), "t")
+    torch.cuda.synchronize()
+    B, _, h, w = f1.shape
+    for i, t in enumerate(lv):
+        ref = g[f"corr.pyr{i}"]
+        assert maxdiff(t.reshape(ref.shape), ref) < 5e-6, i
+    out = torch.empty(B, h, w, 324, device="cuda")
+    flow = torch.empty(B, h * w, 2, device="cuda")
+    c = dev(coords.permute(0, 2, 3, 1).reshape(B, h * w, 2).contiguous())
+    L.call("accflow_corr_lookup_f32", lv[0].data_ptr(), lv[1].data_ptr(), lv[2].data_ptr(), lv[3].data_ptr(), B, h, w, 4,
+           c.data_ptr(), out.data_ptr(), 324, flow.data_ptr(), None, 0, None)
+    torch.cuda.synchronize()
+    assert maxdiff(out.permute(0, 3, 1, 2), g["corr.lookup"]) < 1e-5
+    from oracle import ops
+    assert maxdiff(flow.view(B, h, w, 2).permute(0, 3, 1, 2), coords - ops.coords_grid(B, h, w)) < 1e-6
+
+
+def test_convex_upsample(golden):
+    from accflow_b200 import ops as P
+    g, _ = golden
+    flow, mask = cases.upsample_case()
+    assert maxdiff(P.convex_upsample(dev(flow), dev(mask)), g["upsample.out"]) < 1e-5
+
+
+def test_backwarp_downflow_occ(golden):
+    from accflow_b200 import ops as P
+    g, _ = golden
+    img, flow = cases.warp_case()
+    assert maxdiff(P.backwarp(dev(img), dev(flow)), g["warp.out"]) < 2e-6
+    (fl,) = cases.downflow_case()
+    assert maxdiff(P.downflow8(dev(fl)), g["downflow.out"]) < 2e-6
+    oflow, c1, c2 = cases.occ_case()
+    assert maxdiff(P.get_occ(dev(oflow), dev(c1), dev(c2)), g["occ.binary"]) == 0
+    assert maxdiff(P.get_occ(dev(oflow), dev(c1), dev(c2), binary=False), g["occ.emap"]) < 2e-6
+
+
+def test_deform_conv(K, golden):
+    from accflow_b200 import _lib as L
+    from accflow_b200.engine import PackedConv, View
+    g, _ = golden
+    x, off, mask, wgt, bias = cases.dcn_case()
+    n, c, h, w = x.shape
+    # kernel takes mask *logits* (sigmoid fused): invert the fixture's probabilities
+    logits = torch.log(mask / (1 - mask))
+    om = torch.zeros(n, h, w, 28)
+    om[..., :18] = nhwc(off)
+    om[..., 18:27] = nhwc(logits)
+    col = torch.empty(n, h * w, 9 * c, device="cuda")
+    xv = dev(nhwc(x))
+    omv = dev(om)
+    L.call("accflow_deform_gather_f32", xv.data_ptr(), c, omv.data_ptr(), 28, n, h, w, c, col.data_ptr(), None)
+    pc = PackedConv([dev(wgt).permute(0, 2, 3, 1).reshape(wgt.shape[0], -1, 1, 1)], [dev(bias)], 1, (0, 0))
+    out = torch.empty(n, h, w, wgt.shape[0], device="cuda")
+    K.conv(pc, [View(col.view(n, h, w, 9 * c))], View(out))
+    torch.cuda.synchronize()
+    assert maxdiff(out.permute(0, 3, 1, 2), g["dcn.out"]) < 2e-5
+
+
+def test_softmax_and_transpose(K):
+    from accflow_b200.engine import View
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(37, 1000, generator=g) * 4
+    xd = dev(x).contiguous()
+    K.softmax_rows(xd, 37, 1000)
+    assert maxdiff(xd, torch.softmax(x, -1)) < 1e-6
+    t = torch.randn(2, 5, 7, 44, generator=g)
+    out = torch.zeros(2, 44, 36, device="cuda")
+    K.transpose(View(dev(t)), out, 36)
+    torch.cuda.synchronize()
+    assert maxdiff(out[:, :, :35], t.reshape(2, 35, 44).transpose(1, 2)) == 0
+
+
+def test_error_reporting():
+    from accflow_b200 import _lib as L
+    with pytest.raises(L.AccflowError, match="multiples of 8"):
+        L.call("accflow_downflow8_f32", 1, 1, 100, 64, 1, None)
