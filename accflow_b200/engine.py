@@ -88,6 +88,7 @@ class Kernels:
         self.device = device
         L.load()
         self._ws: Dict[tuple, torch.Tensor] = {}
+        self.profile = None      # bench.py: list of (start_event, end_event, flops) per conv launch
 
     # ---- workspace -----------------------------------------------------------------------
     def buf(self, name: str, *shape, zero: bool = False) -> torch.Tensor:
@@ -136,7 +137,16 @@ class Kernels:
             d.h, d.h_ld = h.ptr, h.ld
         if z is not None:
             d.z, d.z_ld = z.ptr, z.ld
+        if self.profile is None:
+            L.call("accflow_conv2d_f32", C.byref(d), _stream())
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        oh = (s0.h + 2 * pc.pad_h - pc.kh) // pc.stride + 1
+        ow = (s0.w + 2 * pc.pad_w - pc.kw) // pc.stride + 1
+        e0.record()
         L.call("accflow_conv2d_f32", C.byref(d), _stream())
+        e1.record()
+        self.profile.append((e0, e1, 2.0 * s0.b * oh * ow * d.cout * cin * pc.kh * pc.kw))
 
     def conv_smallc(self, x_ptr: int, nchw: bool, batch, cin, h, w, pc: PackedConv, act, out: View):
         L.call("accflow_conv_smallc_f32", x_ptr, int(nchw), batch, cin, h, w, pc.w.data_ptr(),
@@ -299,7 +309,7 @@ class FlowEstimatorEngine:
         inp = k.view(tag + ".inp", B, h, w, 128)
         self.cnet.run(k, [image1], tag + ".cnet", head_kwargs=dict(out=hid, out2=inp, act=L.ACT_TANH, act_split=128,
                                                                    act2=L.ACT_RELU))
-        st["h"], st["inp"] = hid, inp
+        st["hid"], st["inp"] = hid, inp
         if self.gma:
             st["attn"] = self.attention(inp, tag)
         return st
@@ -345,7 +355,7 @@ class FlowEstimatorEngine:
         B, h, w, P, H, W = st["B"], st["h"], st["w"], st["P"], st["H"], st["W"]
         s = _stream
         lv = st["pyr"]
-        hid, inp = st["h"], st["inp"]
+        hid, inp = st["hid"], st["inp"]
         coords = k.buf(tag + ".coords", B, P, 2)
         flow = k.buf(tag + ".flow", B, P, 2)
         corr = k.view(tag + ".corr", B, h, w, 324)

@@ -63,7 +63,7 @@ def test_conv2d_matches_torch(K, case):
     from accflow_b200 import _lib as L
     from accflow_b200.engine import PackedConv, View
     B, cins, H, W, cout, kh, kw, stride, ph, pw = case
-    g = torch.Generator().manual_seed(hash(case) % 1000)
+    g = torch.Generator().manual_seed(CONV_CASES.index(case))
     xs = [torch.randn(B, c, H, W, generator=g) for c in cins]
     w = torch.randn(cout, sum(cins), kh, kw, generator=g) / math.sqrt(sum(cins) * kh * kw)
     b = torch.randn(cout, generator=g)
