@@ -33,6 +33,11 @@ class ConvDesc(C.Structure):
     ]
 
 
+class TcWeights(C.Structure):
+    _fields_ = [("planes", fp), ("nplanes", C.c_int), ("rows", C.c_int), ("k", C.c_int), ("k_pitch", C.c_int),
+                ("t", C.c_int)]
+
+
 i, ll, f = C.c_int, C.c_longlong, C.c_float
 # name -> argtypes (restype is int unless listed in _RESTYPE); mirrors include/accflow_b200.h
 SIGNATURES = {
@@ -40,6 +45,8 @@ SIGNATURES = {
     "accflow_last_error": [C.c_char_p, C.c_size_t],
     "accflow_launch_count": [i],
     "accflow_conv2d_f32": [C.POINTER(ConvDesc), fp],
+    "accflow_conv2d_tc": [C.POINTER(ConvDesc), C.POINTER(TcWeights), i, fp],
+    "accflow_split_bf16_planes": [fp, ll, i, i, i, i, fp, fp],
     "accflow_conv_smallc_f32": [fp, i, i, i, i, i, fp, fp, fp, i, i, i, i, fp, i, fp],
     "accflow_instnorm_chunks": [i],
     "accflow_instnorm_f32": [fp, i, i, i, f, i, fp, i, fp, fp, fp, fp],

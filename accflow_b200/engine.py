@@ -55,6 +55,8 @@ class PackedConv:
                  pad=(0, 0), bn=None, out_scale: Optional[torch.Tensor] = None, mult: float = 1.0):
         w = torch.cat([x.detach().to(F32) for x in weights], 0)           # concat along cout
         dev = w.device
+        self.w_oihw = w
+        self._tc = None
         self.cout, self.cin, self.kh, self.kw = w.shape
         self.stride, self.pad_h, self.pad_w = stride, pad[0], pad[1]
         self.cout_pad = (self.cout + 3) // 4 * 4
@@ -80,12 +82,37 @@ class PackedConv:
         self.shift = shift.contiguous()
         self.has_bias = any(b is not None for b in biases) or bn is not None
 
+    def tc_weights(self) -> "L.TcWeights":
+        """bf16 planes [3][taps][cout][k_pitch] (w = p0 + p1 + p2) for accflow_conv2d_tc."""
+        if self._tc is None:
+            taps = self.kh * self.kw
+            pitch = (self.cin + 7) // 8 * 8
+            wt = torch.zeros(taps, self.cout, pitch, device=self.w_oihw.device, dtype=F32)
+            wt[:, :, : self.cin] = self.w_oihw.permute(2, 3, 0, 1).reshape(taps, self.cout, self.cin)
+            planes = split_planes_torch(wt)
+            tw = L.TcWeights(planes.data_ptr(), 3, self.cout, self.cin, pitch, taps)
+            self._tc = (tw, planes)
+        return self._tc[0]
+
+
+def split_planes_torch(x: torch.Tensor) -> torch.Tensor:
+    """x (fp32) -> stacked bf16 planes p0, p1, p2 with x ~= p0 + p1 + p2 (one-off weight packing)."""
+    p0 = x.to(torch.bfloat16)
+    r1 = x - p0.float()
+    p1 = r1.to(torch.bfloat16)
+    p2 = (r1 - p1.float()).to(torch.bfloat16)
+    return torch.stack([p0, p1, p2]).contiguous()
+
 
 class Kernels:
     """Thin typed wrappers over the C ABI.  One instance per device."""
 
-    def __init__(self, device: torch.device):
+    MODES = ("fp32", "bf16x3", "bf16")
+
+    def __init__(self, device: torch.device, precision: str = "fp32"):
+        assert precision in self.MODES, precision
         self.device = device
+        self.precision = precision       # fp32: FFMA kernels; bf16x3 / bf16: tcgen05 kernels (6 / 1 products)
         L.load()
         self._ws: Dict[tuple, torch.Tensor] = {}
         self.profile = None      # bench.py: list of (start_event, end_event, flops) per conv launch
@@ -107,7 +134,7 @@ class Kernels:
              act_split=0, act2=L.ACT_NONE, out2: Optional[View] = None, residual: Optional[View] = None,
              post_relu=False, epilogue=L.EPI_STORE, h: Optional[View] = None, z: Optional[View] = None,
              weight_ptr: Optional[int] = None, weight_batch_stride=0, cout=None, cout_pad=None,
-             use_affine=True):
+             use_affine=True, tc_b: Optional["L.TcWeights"] = None):
         d = L.ConvDesc()
         cin = 0
         for k, s in enumerate(srcs):
@@ -116,7 +143,9 @@ class Kernels:
         assert cin == pc.cin, f"conv expects {pc.cin} input channels, got {cin}"
         s0 = srcs[0]
         d.nsrc, d.batch, d.in_h, d.in_w = len(srcs), s0.b, s0.h, s0.w
-        d.weight = pc.w.data_ptr() if weight_ptr is None else weight_ptr
+        tc = self.precision != "fp32"
+        if not tc:
+            d.weight = pc.w.data_ptr() if weight_ptr is None else weight_ptr
         d.weight_batch_stride = weight_batch_stride
         d.kh, d.kw, d.stride, d.pad_h, d.pad_w = pc.kh, pc.kw, pc.stride, pc.pad_h, pc.pad_w
         d.cout = pc.cout if cout is None else cout
@@ -137,14 +166,19 @@ class Kernels:
             d.h, d.h_ld = h.ptr, h.ld
         if z is not None:
             d.z, d.z_ld = z.ptr, z.ld
+        if tc:
+            tw = tc_b if tc_b is not None else pc.tc_weights()
+            args = ("accflow_conv2d_tc", C.byref(d), C.byref(tw), 6 if self.precision == "bf16x3" else 1, _stream())
+        else:
+            args = ("accflow_conv2d_f32", C.byref(d), _stream())
         if self.profile is None:
-            L.call("accflow_conv2d_f32", C.byref(d), _stream())
+            L.call(*args)
             return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         oh = (s0.h + 2 * pc.pad_h - pc.kh) // pc.stride + 1
         ow = (s0.w + 2 * pc.pad_w - pc.kw) // pc.stride + 1
         e0.record()
-        L.call("accflow_conv2d_f32", C.byref(d), _stream())
+        L.call(*args)
         e1.record()
         self.profile.append((e0, e1, 2.0 * s0.b * oh * ow * d.cout * cin * pc.kh * pc.kw))
 
@@ -162,6 +196,53 @@ class Kernels:
         L.call("accflow_instnorm_f32", x.ptr, x.b, hw, x.c, eps, int(relu),
                None if residual is None else residual.ptr, int(post_relu), out.ptr, partial.data_ptr(),
                stats.data_ptr(), _stream())
+
+    def gemm_nt(self, tag: str, a: View, b: View, out: View, alpha=1.0):
+        """out[s, m, n] = alpha * sum_k a[s, m, k] * b[s, n, k]  (per sample s; b given row-major [n][k]).
+        corr volume (raft/corr.py:47-55) and q k^T (gma/modules.py:66-73)."""
+        B, K, N = a.b, a.c, b.h * b.w
+        assert b.c == K and b.b == B
+        if self.precision == "fp32":
+            Np = _p4(N)
+            bt = self.buf(tag + ".bt", B, K, Np, zero=True)
+            self.transpose(b, bt, Np)
+            self.conv(_Gemm(K, N, Np), [a], out, alpha=alpha, weight_ptr=bt.data_ptr(), weight_batch_stride=K * Np,
+                      use_affine=False)
+            return
+        npl = 3 if self.precision == "bf16x3" else 1
+        pitch = (K + 7) // 8 * 8
+        planes = self.buf16(tag + ".bpl", npl, B, N, pitch)
+        L.call("accflow_split_bf16_planes", b.ptr, B * N, K, b.ld, pitch, npl, planes.data_ptr(), _stream())
+        tw = L.TcWeights(planes.data_ptr(), npl, N, K, pitch, B)
+        self.conv(_Gemm(K, N, N), [a], out, alpha=alpha, weight_batch_stride=1, use_affine=False, tc_b=tw)
+
+    def gemm_nn(self, tag: str, a: View, b: View, out: View, alpha=1.0, residual: Optional[View] = None):
+        """out[s, m, n] = alpha * sum_k a[s, m, k] * b[s, k, n] (+ residual); b given as [k][n] (NHWC rows = k).
+        attn @ v (gma/modules.py:108)."""
+        B, K, N = a.b, a.c, b.c
+        assert b.h * b.w == K and b.b == B
+        if self.precision == "fp32":
+            assert b.ld == N
+            self.conv(_Gemm(K, N, N), [a], out, alpha=alpha, weight_ptr=b.ptr, weight_batch_stride=K * N,
+                      residual=residual, use_affine=False)
+            return
+        npl = 3 if self.precision == "bf16x3" else 1
+        Kp = (K + 7) // 8 * 8
+        bt = self.buf(tag + ".bt", B, N, Kp, zero=True)
+        self.transpose(b, bt, Kp)
+        planes = self.buf16(tag + ".bpl", npl, B, N, Kp)
+        L.call("accflow_split_bf16_planes", bt.data_ptr(), B * N, K, Kp, Kp, npl, planes.data_ptr(), _stream())
+        tw = L.TcWeights(planes.data_ptr(), npl, N, K, Kp, B)
+        self.conv(_Gemm(K, N, N), [a], out, alpha=alpha, weight_batch_stride=1, residual=residual, use_affine=False,
+                  tc_b=tw)
+
+    def buf16(self, name: str, *shape) -> torch.Tensor:
+        key = (name, "bf16") + tuple(shape)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.empty(*shape, device=self.device, dtype=torch.bfloat16)
+            self._ws[key] = t
+        return t
 
     def transpose(self, x: View, out: torch.Tensor, out_ld: int):
         L.call("accflow_nhwc_transpose_f32", x.ptr, x.b, x.h * x.w, x.c, x.ld, out.data_ptr(), out_ld, _stream())
@@ -256,8 +337,9 @@ class FlowEstimatorEngine:
 
     RADIUS = 4
 
-    def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device, pfx: str = "", gma: bool = False):
-        self.k = Kernels(device)
+    def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device, pfx: str = "", gma: bool = False,
+                 precision: str = "fp32"):
+        self.k = Kernels(device, precision)
         self.device, self.gma, self.pfx = device, gma, pfx
         self.repack(sd)
 
@@ -319,17 +401,12 @@ class FlowEstimatorEngine:
         k = self.k
         B, h, w, D = f1.b, f1.h, f1.w, f1.c
         P = h * w
-        Pp = _p4(P)
-        f2t = k.buf(tag + ".f2t", B, D, Pp, zero=True)
-        k.transpose(f2, f2t, Pp)
         lv = [k.buf(tag + ".pyr0", B * P, P)]
         hh, ww = h, w
         for l in range(1, 4):
             hh, ww = hh // 2, ww // 2
             lv.append(k.buf(f"{tag}.pyr{l}", B * P, hh * ww))
-        gemm = _Gemm(D, P, Pp)
-        k.conv(gemm, [f1], View(lv[0].view(B, h, w, P)), alpha=1.0 / math.sqrt(D), weight_ptr=f2t.data_ptr(),
-               weight_batch_stride=D * Pp, use_affine=False)
+        k.gemm_nt(tag + ".corr", f1, f2, View(lv[0].view(B, h, w, P)), alpha=1.0 / math.sqrt(D))
         L.call("accflow_corr_pool_f32", lv[0].data_ptr(), B * P, h, w, lv[1].data_ptr(), lv[2].data_ptr(),
                lv[3].data_ptr(), _stream())
         return lv
@@ -338,14 +415,11 @@ class FlowEstimatorEngine:
         """Attention.forward (gma/modules.py:54-76), heads=1, content only."""
         k = self.k
         B, h, w = inp.b, inp.h, inp.w
-        P, Pp = h * w, _p4(h * w)
+        P = h * w
         qk = k.view(tag + ".qk", B, h, w, 256)
         k.conv(self.to_qk, [inp], qk)
-        kt = k.buf(tag + ".kt", B, 128, Pp, zero=True)
-        k.transpose(qk.ch(128, 256), kt, Pp)
         attn = k.buf(tag + ".attn", B, P, P)
-        k.conv(_Gemm(128, P, Pp), [qk.ch(0, 128)], View(attn.view(B, h, w, P)), alpha=self.qk_scale,
-               weight_ptr=kt.data_ptr(), weight_batch_stride=128 * Pp, use_affine=False)
+        k.gemm_nt(tag + ".att", qk.ch(0, 128), qk.ch(128, 256), View(attn.view(B, h, w, P)), alpha=self.qk_scale)
         k.softmax_rows(attn, B * P, P)
         return attn
 
@@ -372,7 +446,6 @@ class FlowEstimatorEngine:
             vbuf = k.view(tag + ".v", B, h, w, 128)
             mfg = k.view(tag + ".mfg", B, h, w, 128)
             x_srcs = [inp, mf, mfg]
-            agg = _Gemm(P, 128, 128)
         if flow_init is not None:
             flow_init = flow_init.to(device=self.device, dtype=F32).contiguous()
             assert tuple(flow_init.shape) == (B, 2, h, w)
@@ -390,8 +463,7 @@ class FlowEstimatorEngine:
             if self.gma:
                 # Aggregate.forward (gma/modules.py:102-115): mf + gamma * (attn @ to_v(mf))
                 k.conv(self.to_v, [mf], vbuf)
-                k.conv(agg, [View(st["attn"].view(B, h, w, P))], mfg, alpha=self.gamma, weight_ptr=vbuf.ptr,
-                       weight_batch_stride=P * 128, residual=mf, use_affine=False)
+                k.gemm_nn(tag + ".agg", View(st["attn"].view(B, h, w, P)), vbuf, mfg, alpha=self.gamma, residual=mf)
             for zr, q in self.gru:
                 k.conv(zr, [hid] + x_srcs, epilogue=L.EPI_GRU_ZR, h=hid, z=z, out2=rh)
                 k.conv(q, [rh] + x_srcs, epilogue=L.EPI_GRU_Q, h=hid, z=z)
@@ -431,9 +503,9 @@ class _Gemm:
 class AccFlowEngine:
     """AccFlow.iter / forward (networks/AccFlow_.py:157-201) on the kernels."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device, gma: bool):
+    def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device, gma: bool, precision: str = "fp32"):
         self.device = device
-        self.ofe = FlowEstimatorEngine(sd, device, "ofe.", gma)
+        self.ofe = FlowEstimatorEngine(sd, device, "ofe.", gma, precision)
         self.k = self.ofe.k
         self.repack(sd, repack_ofe=False)
 

@@ -41,12 +41,14 @@ class AccFlow(nn.Module):
         device = next(self.parameters()).device if device is None else device
         if device.type != "cuda":
             raise RuntimeError("accflow_b200 runs on CUDA (sm_100a) only; there is no CPU path")
-        sig = _tree.signature(self)
-        hit = self._engines.get(device)
+        precision = self.ofe.precision
+        sig = (_tree.signature(self), precision)
+        key = (device, precision)
+        hit = self._engines.get(key)
         if hit is None or hit[0] != sig:
-            hit = (sig, AccFlowEngine(dict(self.state_dict()), device, self.ofe._GMA))
+            hit = (sig, AccFlowEngine(dict(self.state_dict()), device, self.ofe._GMA, precision))
             if not getattr(self, "_is_replica", False):
-                self._engines[device] = hit
+                self._engines[key] = hit
         return hit[1]
 
     @torch.no_grad()

@@ -1,6 +1,8 @@
 """Shared base of RAFT / RAFTGMA: parameter tree + CUDA engine dispatch."""
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -22,6 +24,9 @@ class FlowEstimatorBase(nn.Module):
             args.dropout = 0
         _tree.populate(self, S.gma_entries() if self._GMA else S.raft_entries())
         self._engines = {}
+        # arithmetic of the conv/GEMM kernels: "fp32" (FFMA, exact), "bf16x3" (tcgen05, bf16x3 split
+        # products = fp32-class), "bf16" (tcgen05, bf16 products = the reference's autocast class)
+        self.precision = os.environ.get("ACCFLOW_PRECISION", "fp32")
 
     # ---- reference API -------------------------------------------------------------------
     def freeze_bn(self):
@@ -48,13 +53,14 @@ class FlowEstimatorBase(nn.Module):
         if device.type != "cuda":
             raise RuntimeError("accflow_b200 runs on CUDA (sm_100a) only; there is no CPU path — move the "
                                "module to a GPU (.cuda()) before calling it")
-        sig = _tree.signature(self)
-        hit = self._engines.get(device)
+        sig = (_tree.signature(self), self.precision)
+        key = (device, self.precision)
+        hit = self._engines.get(key)
         if hit is None or hit[0] != sig:
             sd = {k: v for k, v in self.state_dict().items()}
-            hit = (sig, FlowEstimatorEngine(sd, device, "", self._GMA))
+            hit = (sig, FlowEstimatorEngine(sd, device, "", self._GMA, self.precision))
             if not getattr(self, "_is_replica", False):
-                self._engines[device] = hit
+                self._engines[key] = hit
         return hit[1]
 
     @torch.no_grad()

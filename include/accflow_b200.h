@@ -88,6 +88,29 @@ ACCFLOW_API long long accflow_launch_count(int reset);
 /* Generic fp32 convolution (exact-fp32 arithmetic on the FFMA pipe). */
 ACCFLOW_API int accflow_conv2d_f32(const accflow_conv_desc* d, void* stream);
 
+/* Weights (or the per-sample B operand) of a tensor-core convolution: up to three bf16 planes
+ * (w = p0 + p1 + p2), laid out [plane][t][rows][k_pitch] with K contiguous.  t indexes filter
+ * taps (ky*kw + kx), or samples when accflow_conv_desc.weight_batch_stride != 0. */
+typedef struct accflow_tc_weights {
+  const void* planes; /* bf16 */
+  int nplanes;        /* 1 or 3 */
+  int rows;           /* cout rows stored per t */
+  int k;              /* logical K per t (sum of source channels) */
+  int k_pitch;        /* elements between rows, multiple of 8 */
+  int t;              /* taps or samples */
+} accflow_tc_weights;
+
+/* Same contract as accflow_conv2d_f32 (the descriptor's `weight`/`cout_pad` are ignored) on the
+ * 5th-gen tensor cores: tcgen05.mma with TMEM accumulators, weights by TMA, fp32 activations
+ * split to bf16 planes in-kernel.  nprod = 1: bf16 products; nprod = 6: bf16x3 split products
+ * (fp32-class accuracy, fp32 accumulate). */
+ACCFLOW_API int accflow_conv2d_tc(const accflow_conv_desc* d, const accflow_tc_weights* w, int nprod, void* stream);
+
+/* fp32 [rows][k] (row stride ld) -> bf16 planes [nplanes][rows][k_pitch] (zero padded): prepares
+ * the per-sample B operands (fmap2 of raft/corr.py:47-55, k / v of gma/modules.py:57-113). */
+ACCFLOW_API int accflow_split_bf16_planes(const float* x, long long rows, int k, int ld, int k_pitch, int nplanes,
+                                          void* out_planes, void* stream);
+
 /* Small-input-channel KSxKS convolution (cin in {2,3}), fused affine + activation.
  * 7x7/s2 stem of BasicEncoder (raft/extractor.py:163-167,209) reading NCHW images, and the
  * 7x7 2->128 flow convs (raft/update.py:85,92; AccFlow_.py:51,62) reading NHWC flow.
