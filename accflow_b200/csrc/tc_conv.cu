@@ -162,6 +162,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtenso
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t bar_w[MAX_STAGES], bar_a[MAX_STAGES], bar_free[MAX_STAGES], bar_acc;
   __shared__ uint32_t tmem_slot;
+  __shared__ int4 rowinfo[BM];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int taps = p.kh * p.kw;
@@ -250,173 +251,205 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtenso
     }
   } else {
     // ================================ converters, then epilogue ================================
-    const int cw = warp - 2;                       // 0..7
-    const int row = 32 * (warp & 3) + lane;        // TMEM lane quarter = warp % 4
-    const int half = cw >> 2;                      // which 32-channel half of the chunk / column half of the tile
-    const int pm = m0 + row;
-    const bool row_ok = pm < p.m_total;
-    int b = sample, oy = 0, ox = 0;
+    // Gather mapping (coalesced): converter warp cw owns rows [32*(cw%4), +32) and the 32-channel
+    // half (cw/4) of every chunk.  One warp-wide LDG.128 reads 4 rows x 128 contiguous bytes:
+    // lane l -> row group q = l/8, 4-channel group c4 = l%8; instruction j -> row 16*(j/4)+4*q+(j%4)
+    // (rows of one instruction differ by 4, which lands their swizzled stores in different banks).
+    const int cw = warp - 2;
+    const int half = cw >> 2;
+    const int q = lane >> 3, c4 = lane & 7;
+    const int rbase = 32 * (cw & 3) + 4 * q;
     {
-      int r = pm;
-      const int opix = p.out_h * p.out_w;
-      if (!p.per_sample) { b = r / opix; r -= b * opix; }
-      oy = r / p.out_w;
-      ox = r - oy * p.out_w;
+      // per-row im2col origin, shared by all converter threads
+      const int t = tid - 64;
+      if (t < BM) {
+        int r = m0 + t, b = sample;
+        const int opix = p.out_h * p.out_w;
+        const int ok = r < p.m_total;
+        if (!p.per_sample) { b = r / opix; r -= b * opix; }
+        const int oy = r / p.out_w, ox = r - oy * p.out_w;
+        rowinfo[t] = make_int4(b, oy * p.stride - p.pad_h, ox * p.stride - p.pad_w, ok);
+      }
+      asm volatile("bar.sync 3, 256;" ::: "memory");
     }
-    const int iy0 = oy * p.stride - p.pad_h, ix0 = ox * p.stride - p.pad_w;
 
-    float4 v[8];
-    auto gather = [&](const Chunk& ck) {
+    auto gather = [&](const Chunk& ck, float4* v) {
       const int ky = ck.tap / p.kw, kx = ck.tap - ky * p.kw;
-      const int iy = iy0 + ky, ix = ix0 + kx;
       const int C = p.src_c[ck.s];
-      const int cb = ck.c0 + 32 * half;
+      const int ld = p.src_ld[ck.s];
+      const float* sp = p.src[ck.s];
+      const int c = ck.c0 + 32 * half + 4 * c4;
+      const bool vec = p.src_vec[ck.s] && c + 3 < C;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row_ok && iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w && cb < C) {
-        const float* ptr = p.src[ck.s] + ((long long)(b * p.in_h + iy) * p.in_w + ix) * p.src_ld[ck.s] + cb;
-        if (p.src_vec[ck.s] && cb + 32 <= C) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(ptr) + j);
-        } else {
-          float* vf = reinterpret_cast<float*>(v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (cb + j < C) vf[j] = __ldg(ptr + j);
+      for (int j = 0; j < 8; ++j) {
+        const int4 ri = rowinfo[rbase + 16 * (j >> 2) + (j & 3)];
+        const int iy = ri.y + ky, ix = ri.z + kx;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ri.w && iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w && c < C) {
+          const float* ptr = sp + ((long long)(ri.x * p.in_h + iy) * p.in_w + ix) * ld + c;
+          if (vec) {
+            x = __ldg(reinterpret_cast<const float4*>(ptr));
+          } else {
+            x.x = __ldg(ptr);
+            if (c + 1 < C) x.y = __ldg(ptr + 1);
+            if (c + 2 < C) x.z = __ldg(ptr + 2);
+            if (c + 3 < C) x.w = __ldg(ptr + 3);
+          }
         }
+        v[j] = x;
       }
     };
-    auto split_store = [&](int s) {
-      uint8_t* a_base = smem + (size_t)s * stage_bytes + row * 128;
+    auto split_store = [&](int s, const float4* v) {
+      uint8_t* a_stage = smem + (size_t)s * stage_bytes;
+      const int unit = 4 * half + (c4 >> 1), sub = (c4 & 1) * 8;
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const float f[8] = {v[2 * jj].x, v[2 * jj].y, v[2 * jj].z, v[2 * jj].w,
-                            v[2 * jj + 1].x, v[2 * jj + 1].y, v[2 * jj + 1].z, v[2 * jj + 1].w};
-        const int chunk16 = ((4 * half + jj) ^ (row & 7)) << 4;   // SWIZZLE_128B: 16-byte unit ^= row % 8
-        uint32_t q0[4];
-        float r1[8];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-          q0[e] = *reinterpret_cast<uint32_t*>(&t);
-          r1[2 * e] = f[2 * e] - __bfloat162float(t.x);
-          r1[2 * e + 1] = f[2 * e + 1] - __bfloat162float(t.y);
-        }
-        *reinterpret_cast<uint4*>(a_base + chunk16) = make_uint4(q0[0], q0[1], q0[2], q0[3]);
+      for (int j = 0; j < 8; ++j) {
+        const int row = rbase + 16 * (j >> 2) + (j & 3);
+        uint8_t* dst = a_stage + row * 128 + (((unit ^ (row & 7)) << 4) | sub);   // SWIZZLE_128B
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[j].x, v[j].y), h23 = __floats2bfloat162_rn(v[j].z, v[j].w);
+        *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
         if (NPL > 1) {
-          uint32_t q1[4], q2[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 t = __floats2bfloat162_rn(r1[2 * e], r1[2 * e + 1]);
-            q1[e] = *reinterpret_cast<uint32_t*>(&t);
-            q2[e] = pack_bf16(r1[2 * e] - __bfloat162float(t.x), r1[2 * e + 1] - __bfloat162float(t.y));
-          }
-          *reinterpret_cast<uint4*>(a_base + A_PLANE_BYTES + chunk16) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
-          *reinterpret_cast<uint4*>(a_base + 2 * A_PLANE_BYTES + chunk16) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
+          const float r0 = v[j].x - __bfloat162float(h01.x), r1 = v[j].y - __bfloat162float(h01.y);
+          const float r2 = v[j].z - __bfloat162float(h23.x), r3 = v[j].w - __bfloat162float(h23.y);
+          const __nv_bfloat162 m01 = __floats2bfloat162_rn(r0, r1), m23 = __floats2bfloat162_rn(r2, r3);
+          *reinterpret_cast<uint2*>(dst + A_PLANE_BYTES) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&m01), *reinterpret_cast<const uint32_t*>(&m23));
+          *reinterpret_cast<uint2*>(dst + 2 * A_PLANE_BYTES) =
+              make_uint2(pack_bf16(r0 - __bfloat162float(m01.x), r1 - __bfloat162float(m01.y)),
+                         pack_bf16(r2 - __bfloat162float(m23.x), r3 - __bfloat162float(m23.y)));
         }
       }
     };
 
+    // two chunks of global loads in flight per thread (va / vb alternate)
+    float4 va[8], vb[8];
     Chunk ck{0, 0, 0};
-    gather(ck);
-    for (int i = 0; i < nchunks; ++i) {
-      const int s = i % S, round = i / S;
-      if (round > 0) mbar_wait(&bar_free[s], (round - 1) & 1);
-      split_store(s);
-      const bool more = ck.next(p, taps);
-      if (more) gather(ck);          // next chunk's global loads fly while the MMA consumes this one
-      fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_a[s]);
+    bool more = true;
+    gather(ck, va);
+    more = ck.next(p, taps);
+    if (more) gather(ck, vb);
+    for (int i = 0; i < nchunks; i += 2) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int ii = i + u;
+        if (ii < nchunks) {
+          const int s = ii % S, round = ii / S;
+          if (round > 0) mbar_wait(&bar_free[s], (round - 1) & 1);
+          split_store(s, u == 0 ? va : vb);
+          if (more) more = ck.next(p, taps);
+          if (more) gather(ck, u == 0 ? va : vb);
+          fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_a[s]);
+        }
+      }
     }
 
     // ------------------------------------ epilogue ------------------------------------------
+    // Phase 1: TMEM -> registers (MAIN + CORR) -> padded smem panel.  Phase 2: coalesced global
+    // traffic (4 rows x 128 B per warp instruction) with the affine / activation / GRU math.
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
+    constexpr int PITCH = 36;                                   // floats; conflict-free for both phases
+    float* stg = reinterpret_cast<float*>(smem + (size_t)half * stage_bytes);
+    const int trow = 32 * (warp & 3) + lane;                    // TMEM lane owned by this thread
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
-    const long long pix = p.per_sample ? ((long long)sample * p.m_total + pm) : (long long)pm;
+    const int st = tid - 64 - 128 * half;                       // 0..127 inside this warp set
     const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
-    for (int c = cbeg; c < cend; c += 16) {
-      float acc[16];
-      tmem_ld16(lane_addr + c, acc);
-      if (p.nprod > 1) {
-        float corr[16];
-        tmem_ld16(lane_addr + BN + c, corr);
+    for (int c = cbeg; c < cend; c += 32) {
+      const int pw = min(32, cend - c);
+      for (int g = 0; g < pw; g += 16) {
+        float acc[16];
+        tmem_ld16(lane_addr + c + g, acc);
+        if (p.nprod > 1) {
+          float corr[16];
+          tmem_ld16(lane_addr + BN + c + g, corr);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] += corr[j];
+          for (int j = 0; j < 16; ++j) acc[j] += corr[j];
+        }
+        float4* d4 = reinterpret_cast<float4*>(stg + trow * PITCH + g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
       }
-      const int nb = n0 + c;
-      if (!row_ok || nb >= p.cout) continue;
-      float y[16];
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+      const int pc4 = st & 7;
+      if (pc4 * 4 < pw) {
+        const int nb = n0 + c + pc4 * 4;
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 16 + (st >> 3);
+          const int pm = m0 + row;
+          if (pm >= p.m_total || nb >= p.cout) continue;
+          const long long pix = p.per_sample ? ((long long)sample * p.m_total + pm) : (long long)pm;
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
+          float y[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = nb + j;
-        const bool ok = n < p.cout;
-        const float sc = p.alpha * ((p.scale && ok) ? __ldg(p.scale + n) : 1.f);
-        const float sh = (p.shift && ok) ? __ldg(p.shift + n) : 0.f;
-        y[j] = fmaf(acc[j], sc, sh);
-      }
-      if (p.epilogue == ACCFLOW_EPI_STORE) {
-        if (p.out_vec && nb + 15 < p.cout) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) y[j] = act_apply(y[j], p.act);
-          if (p.residual) {
-            const float4* rp = reinterpret_cast<const float4*>(p.residual + pix * p.res_ld + nb);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4 r = rp[q];
-              y[4 * q] += r.x; y[4 * q + 1] += r.y; y[4 * q + 2] += r.z; y[4 * q + 3] += r.w;
-            }
-          }
-          if (p.post_relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
-          }
-          float4* op = reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) op[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 4; ++j) {
             const int n = nb + j;
-            if (n < p.cout) {
-              const bool second = p.act_split > 0 && n >= p.act_split;
-              float o = act_apply(y[j], second ? p.act2 : p.act);
-              if (p.residual) o += p.residual[pix * p.res_ld + n];
-              if (p.post_relu) o = fmaxf(o, 0.f);
-              if (second && p.out2) p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
-              else p.out[pix * p.out_ld + n] = o;
+            const bool ok = n < p.cout;
+            const float sc = p.alpha * ((p.scale && ok) ? __ldg(p.scale + n) : 1.f);
+            const float sh = (p.shift && ok) ? __ldg(p.shift + n) : 0.f;
+            y[j] = fmaf(y[j], sc, sh);
+          }
+          if (p.epilogue == ACCFLOW_EPI_STORE) {
+            if (p.out_vec && nb + 3 < p.cout) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) y[j] = act_apply(y[j], p.act);
+              if (p.residual) {
+                const float4 r = *reinterpret_cast<const float4*>(p.residual + pix * p.res_ld + nb);
+                y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
+              }
+              if (p.post_relu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
+              }
+              *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int n = nb + j;
+                if (n < p.cout) {
+                  const bool second = p.act_split > 0 && n >= p.act_split;
+                  float o = act_apply(y[j], second ? p.act2 : p.act);
+                  if (p.residual) o += p.residual[pix * p.res_ld + n];
+                  if (p.post_relu) o = fmaxf(o, 0.f);
+                  if (second && p.out2) p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
+                  else p.out[pix * p.out_ld + n] = o;
+                }
+              }
+            }
+          } else if (p.epilogue == ACCFLOW_EPI_GRU_ZR) {
+            const int hd = p.cout >> 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = nb + j;
+              if (n < p.cout) {
+                const float gte = 1.f / (1.f + expf(-y[j]));
+                if (n < hd) p.z[pix * p.z_ld + n] = gte;
+                else p.out2[pix * p.out2_ld + (n - hd)] = gte * p.h[pix * p.h_ld + (n - hd)];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = nb + j;
+              if (n < p.cout) {
+                const float qv = tanhf(y[j]);
+                const float zz = p.z[pix * p.z_ld + n];
+                const float hh = p.h[pix * p.h_ld + n];
+                p.h[pix * p.h_ld + n] = (1.f - zz) * hh + zz * qv;
+              }
             }
           }
         }
-      } else if (p.epilogue == ACCFLOW_EPI_GRU_ZR) {
-        const int hd = p.cout >> 1;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = nb + j;
-          if (n < p.cout) {
-            const float g = 1.f / (1.f + expf(-y[j]));
-            if (n < hd) p.z[pix * p.z_ld + n] = g;
-            else p.out2[pix * p.out2_ld + (n - hd)] = g * p.h[pix * p.h_ld + (n - hd)];
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = nb + j;
-          if (n < p.cout) {
-            const float q = tanhf(y[j]);
-            const float zz = p.z[pix * p.z_ld + n];
-            const float hh = p.h[pix * p.h_ld + n];
-            p.h[pix * p.h_ld + n] = (1.f - zz) * hh + zz * q;
-          }
-        }
       }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
     }
     tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
