@@ -38,6 +38,13 @@ class TcWeights(C.Structure):
                 ("t", C.c_int)]
 
 
+class TcIO(C.Structure):
+    _fields_ = [("src_planes", fp * MAX_SRC), ("src_pitch", C.c_int * MAX_SRC), ("src_plane_stride", C.c_longlong * MAX_SRC),
+                ("out_planes", fp), ("out_pitch", C.c_int), ("out_plane_stride", C.c_longlong),
+                ("out2_planes", fp), ("out2_pitch", C.c_int), ("out2_plane_stride", C.c_longlong),
+                ("h_planes", fp), ("h_pitch", C.c_int), ("h_plane_stride", C.c_longlong)]
+
+
 i, ll, f = C.c_int, C.c_longlong, C.c_float
 # name -> argtypes (restype is int unless listed in _RESTYPE); mirrors include/accflow_b200.h
 SIGNATURES = {
@@ -45,8 +52,8 @@ SIGNATURES = {
     "accflow_last_error": [C.c_char_p, C.c_size_t],
     "accflow_launch_count": [i],
     "accflow_conv2d_f32": [C.POINTER(ConvDesc), fp],
-    "accflow_conv2d_tc": [C.POINTER(ConvDesc), C.POINTER(TcWeights), i, fp],
-    "accflow_split_bf16_planes": [fp, ll, i, i, i, i, fp, fp],
+    "accflow_conv2d_tc": [C.POINTER(ConvDesc), C.POINTER(TcIO), C.POINTER(TcWeights), i, fp],
+    "accflow_split_bf16_planes": [fp, ll, i, i, i, i, ll, i, fp, fp],
     "accflow_conv_smallc_f32": [fp, i, i, i, i, i, fp, fp, fp, i, i, i, i, fp, i, fp],
     "accflow_instnorm_chunks": [i],
     "accflow_instnorm_f32": [fp, i, i, i, f, i, fp, i, fp, fp, fp, fp],

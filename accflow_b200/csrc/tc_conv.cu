@@ -2,19 +2,21 @@
 //
 //   D[128 pixels x BN couts] (fp32, TMEM)  +=  A[128 x 64] (bf16, smem)  *  W[BN x 64]^T (bf16, smem)
 //
-// Activations stay fp32 NHWC in HBM.  Eight converter warps gather the im2col rows of the CTA's
-// 128 output pixels (zero padding, stride, channel-concatenated sources), split every fp32
-// value into up to three bf16 planes (x = p0 + p1 + p2, 24 mantissa bits) and write them into
-// shared memory in the K-major SWIZZLE_128B layout tcgen05.mma reads.  Weights are pre-split
-// into the same planes on the host and arrive by TMA.  One elected thread issues the MMAs:
+// Operands are bf16 "planes" (x = p0 + p1 + p2, 24 mantissa bits) kept next to the fp32 NHWC
+// activations in HBM.  Both operands arrive by TMA into the K-major SWIZZLE_128B layout
+// tcgen05.mma reads: the weight tile from a [plane][tap][cout][cin] tensor, the activation
+// tile as an im2col box (channels x TW x TH pixels, shifted by the filter tap, strided for
+// stride-2 convs) whose out-of-bounds elements TMA fills with zeros - that is the padding.
+// One elected thread issues the MMAs:
 //   nprod = 1 : p0*w0                                  (bf16 arithmetic, fp32 accumulate)
 //   nprod = 6 : MAIN += p0*w0 ; CORR += p0*w1 + p1*w0 + p1*w1 + p0*w2 + p2*w0   (fp32-class)
-// The two accumulators (large and small terms) live in separate TMEM column ranges and are
-// added in fp32 in the epilogue, so the small terms are not lost to the accumulator's rounding.
-// Epilogue: tcgen05.ld -> affine / activation / residual / GRU gate math -> global stores.
+// tcgen05 accumulation truncates (measured: scripts/probe_tmem_rounding.py), so the small terms
+// get their own TMEM accumulator and are added in fp32 (round-to-nearest) in the epilogue.
+// Epilogue: tcgen05.ld -> padded smem panel -> coalesced affine / activation / residual / GRU
+// math -> fp32 stores (+ bf16 planes of the result for the next convolution).
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..9 = converters during the main loop, epilogue afterwards.
+// warps 2..9 = epilogue (two sets of four warps, one per half of the N tile).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -29,13 +31,18 @@ constexpr int A_PLANE_BYTES = BM * KC * 2;  // 16 KB
 constexpr int MAX_STAGES = 6;
 constexpr int NTHREADS = 320;
 
+struct PlaneOut {  // optional bf16 planes written next to an fp32 output
+  __nv_bfloat16* ptr;
+  int pitch;                // elements between pixels
+  long long plane_stride;   // elements between planes
+};
+
 struct Params {
-  const float* src[ACCFLOW_MAX_SRC];
-  int src_c[ACCFLOW_MAX_SRC], src_ld[ACCFLOW_MAX_SRC], src_off[ACCFLOW_MAX_SRC], src_vec[ACCFLOW_MAX_SRC];
-  int nsrc, batch, in_h, in_w, out_h, out_w;
+  int src_c[ACCFLOW_MAX_SRC], src_off[ACCFLOW_MAX_SRC];
+  int nsrc, batch, out_h, out_w;
   int kh, kw, stride, pad_h, pad_w;
-  int per_sample;  // grid.z = sample; weights' T coordinate = sample
-  int m_total;     // rows of the implicit GEMM covered by grid.x (all pixels, or pixels of one sample)
+  int tw, th, tw_shift, tiles_x, tiles_y;   // spatial tile of 128 output pixels (tw * th = 128)
+  int per_sample;                           // weights' T coordinate = sample instead of tap
   int cout, bn, nplanes, nprod, stages;
   float alpha;
   const float* scale;
@@ -47,6 +54,12 @@ struct Params {
   float* out2; int out2_ld;
   float* h; int h_ld;
   float* z; int z_ld;
+  PlaneOut out_pl, out2_pl, h_pl;
+};
+
+struct alignas(64) TmapPack {
+  CUtensorMap w;
+  CUtensorMap a[ACCFLOW_MAX_SRC];
 };
 
 // ---------------------------------------------------------------------------------- PTX helpers
@@ -89,6 +102,14 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 
@@ -157,12 +178,39 @@ struct Chunk {  // iterator over (tap, source, 64-channel block)
   }
 };
 
+// Writes 4 consecutive channels of one pixel into the bf16 planes of an output.
+__device__ __forceinline__ void store_planes4(const PlaneOut& po, int nplanes, long long pix, int n, const float* y) {
+  __nv_bfloat16* base = po.ptr + pix * po.pitch + n;
+  const __nv_bfloat162 a01 = __floats2bfloat162_rn(y[0], y[1]), a23 = __floats2bfloat162_rn(y[2], y[3]);
+  *reinterpret_cast<uint2*>(base) = make_uint2(*reinterpret_cast<const uint32_t*>(&a01), *reinterpret_cast<const uint32_t*>(&a23));
+  if (nplanes > 1) {
+    const float r0 = y[0] - __bfloat162float(a01.x), r1 = y[1] - __bfloat162float(a01.y);
+    const float r2 = y[2] - __bfloat162float(a23.x), r3 = y[3] - __bfloat162float(a23.y);
+    const __nv_bfloat162 b01 = __floats2bfloat162_rn(r0, r1), b23 = __floats2bfloat162_rn(r2, r3);
+    *reinterpret_cast<uint2*>(base + po.plane_stride) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&b01), *reinterpret_cast<const uint32_t*>(&b23));
+    *reinterpret_cast<uint2*>(base + 2 * po.plane_stride) =
+        make_uint2(pack_bf16(r0 - __bfloat162float(b01.x), r1 - __bfloat162float(b01.y)),
+                   pack_bf16(r2 - __bfloat162float(b23.x), r3 - __bfloat162float(b23.y)));
+  }
+}
+__device__ __forceinline__ void store_planes1(const PlaneOut& po, int nplanes, long long pix, int n, float y) {
+  __nv_bfloat16* base = po.ptr + pix * po.pitch + n;
+  const __nv_bfloat16 a = __float2bfloat16_rn(y);
+  base[0] = a;
+  if (nplanes > 1) {
+    const float r = y - __bfloat162float(a);
+    const __nv_bfloat16 b = __float2bfloat16_rn(r);
+    base[po.plane_stride] = b;
+    base[2 * po.plane_stride] = __float2bfloat16_rn(r - __bfloat162float(b));
+  }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap wmap) {
+conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPack maps) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
-  __shared__ __align__(8) uint64_t bar_w[MAX_STAGES], bar_a[MAX_STAGES], bar_free[MAX_STAGES], bar_acc;
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_free[MAX_STAGES], bar_acc;
   __shared__ uint32_t tmem_slot;
-  __shared__ int4 rowinfo[BM];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int taps = p.kh * p.kw;
@@ -171,8 +219,13 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtenso
   const int stage_bytes = NPL * (A_PLANE_BYTES + w_plane_bytes);
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int sample = p.per_sample ? blockIdx.z : 0;
+  // tile -> (sample, tile_y, tile_x)
+  int t = blockIdx.x;
+  const int tile_x = t % p.tiles_x; t /= p.tiles_x;
+  const int tile_y = t % p.tiles_y;
+  const int sample = t / p.tiles_y;
+  const int ox0 = tile_x * p.tw, oy0 = tile_y * p.th;
+  const int n0 = blockIdx.y * BN;
 
   int nchunks = 0;
   for (int s = 0; s < p.nsrc; ++s) nchunks += (p.src_c[s] + KC - 1) / KC;
@@ -186,13 +239,13 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtenso
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&bar_w[s], 1);
-      mbar_init(&bar_a[s], 8);
+      mbar_init(&bar_full[s], 1);
       mbar_init(&bar_free[s], 1);
     }
     mbar_init(&bar_acc, 1);
     fence_barrier_init();
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
+    for (int s = 0; s < p.nsrc; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
   }
   if (warp == 1) tmem_alloc(&tmem_slot, tmem_cols);
   tc_fence_before();
@@ -201,17 +254,23 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtenso
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    // ================================ TMA producer (weights) =================================
+    // ================================ TMA producer ============================================
     if (lane == 0) {
       Chunk ck{0, 0, 0};
       for (int i = 0; i < nchunks; ++i) {
         const int s = i % S, round = i / S;
         if (round > 0) mbar_wait(&bar_free[s], (round - 1) & 1);
-        uint8_t* wdst = smem + (size_t)s * stage_bytes + NPL * A_PLANE_BYTES;
-        mbar_expect_tx(&bar_w[s], (uint32_t)(NPL * w_plane_bytes));
+        uint8_t* adst = smem + (size_t)s * stage_bytes;
+        uint8_t* wdst = adst + NPL * A_PLANE_BYTES;
+        mbar_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
+        const int ky = ck.tap / p.kw, kx = ck.tap - ky * p.kw;
+        const int ix = ox0 * p.stride + kx - p.pad_w, iy = oy0 * p.stride + ky - p.pad_h;
         const int kcoord = p.src_off[ck.s] + ck.c0;
-        const int t = p.per_sample ? sample : ck.tap;
-        for (int pl = 0; pl < NPL; ++pl) tma_load_4d(wdst + pl * w_plane_bytes, &wmap, &bar_w[s], kcoord, n0, t, pl);
+        const int tw_ = p.per_sample ? sample : ck.tap;
+        for (int pl = 0; pl < NPL; ++pl) {
+          tma_load_5d(adst + pl * A_PLANE_BYTES, &maps.a[ck.s], &bar_full[s], ck.c0, ix, iy, sample, pl);
+          tma_load_4d(wdst + pl * w_plane_bytes, &maps.w, &bar_full[s], kcoord, n0, tw_, pl);
+        }
         ck.next(p, taps);
       }
     }
@@ -223,8 +282,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtenso
       uint32_t first_main = 0, first_corr = 0;  // 0 -> overwrite accumulator
       for (int i = 0; i < nchunks; ++i) {
         const int s = i % S, round = i / S;
-        mbar_wait(&bar_w[s], round & 1);
-        mbar_wait(&bar_a[s], round & 1);
+        mbar_wait(&bar_full[s], round & 1);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t w_base = a_base + NPL * A_PLANE_BYTES;
@@ -250,104 +308,10 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtenso
       umma_commit(&bar_acc);
     }
   } else {
-    // ================================ converters, then epilogue ================================
-    // Gather mapping (coalesced): converter warp cw owns rows [32*(cw%4), +32) and the 32-channel
-    // half (cw/4) of every chunk.  One warp-wide LDG.128 reads 4 rows x 128 contiguous bytes:
-    // lane l -> row group q = l/8, 4-channel group c4 = l%8; instruction j -> row 16*(j/4)+4*q+(j%4)
-    // (rows of one instruction differ by 4, which lands their swizzled stores in different banks).
-    const int cw = warp - 2;
-    const int half = cw >> 2;
-    const int q = lane >> 3, c4 = lane & 7;
-    const int rbase = 32 * (cw & 3) + 4 * q;
-    {
-      // per-row im2col origin, shared by all converter threads
-      const int t = tid - 64;
-      if (t < BM) {
-        int r = m0 + t, b = sample;
-        const int opix = p.out_h * p.out_w;
-        const int ok = r < p.m_total;
-        if (!p.per_sample) { b = r / opix; r -= b * opix; }
-        const int oy = r / p.out_w, ox = r - oy * p.out_w;
-        rowinfo[t] = make_int4(b, oy * p.stride - p.pad_h, ox * p.stride - p.pad_w, ok);
-      }
-      asm volatile("bar.sync 3, 256;" ::: "memory");
-    }
-
-    auto gather = [&](const Chunk& ck, float4* v) {
-      const int ky = ck.tap / p.kw, kx = ck.tap - ky * p.kw;
-      const int C = p.src_c[ck.s];
-      const int ld = p.src_ld[ck.s];
-      const float* sp = p.src[ck.s];
-      const int c = ck.c0 + 32 * half + 4 * c4;
-      const bool vec = p.src_vec[ck.s] && c + 3 < C;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int4 ri = rowinfo[rbase + 16 * (j >> 2) + (j & 3)];
-        const int iy = ri.y + ky, ix = ri.z + kx;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ri.w && iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w && c < C) {
-          const float* ptr = sp + ((long long)(ri.x * p.in_h + iy) * p.in_w + ix) * ld + c;
-          if (vec) {
-            x = __ldg(reinterpret_cast<const float4*>(ptr));
-          } else {
-            x.x = __ldg(ptr);
-            if (c + 1 < C) x.y = __ldg(ptr + 1);
-            if (c + 2 < C) x.z = __ldg(ptr + 2);
-            if (c + 3 < C) x.w = __ldg(ptr + 3);
-          }
-        }
-        v[j] = x;
-      }
-    };
-    auto split_store = [&](int s, const float4* v) {
-      uint8_t* a_stage = smem + (size_t)s * stage_bytes;
-      const int unit = 4 * half + (c4 >> 1), sub = (c4 & 1) * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int row = rbase + 16 * (j >> 2) + (j & 3);
-        uint8_t* dst = a_stage + row * 128 + (((unit ^ (row & 7)) << 4) | sub);   // SWIZZLE_128B
-        const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[j].x, v[j].y), h23 = __floats2bfloat162_rn(v[j].z, v[j].w);
-        *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-        if (NPL > 1) {
-          const float r0 = v[j].x - __bfloat162float(h01.x), r1 = v[j].y - __bfloat162float(h01.y);
-          const float r2 = v[j].z - __bfloat162float(h23.x), r3 = v[j].w - __bfloat162float(h23.y);
-          const __nv_bfloat162 m01 = __floats2bfloat162_rn(r0, r1), m23 = __floats2bfloat162_rn(r2, r3);
-          *reinterpret_cast<uint2*>(dst + A_PLANE_BYTES) =
-              make_uint2(*reinterpret_cast<const uint32_t*>(&m01), *reinterpret_cast<const uint32_t*>(&m23));
-          *reinterpret_cast<uint2*>(dst + 2 * A_PLANE_BYTES) =
-              make_uint2(pack_bf16(r0 - __bfloat162float(m01.x), r1 - __bfloat162float(m01.y)),
-                         pack_bf16(r2 - __bfloat162float(m23.x), r3 - __bfloat162float(m23.y)));
-        }
-      }
-    };
-
-    // two chunks of global loads in flight per thread (va / vb alternate)
-    float4 va[8], vb[8];
-    Chunk ck{0, 0, 0};
-    bool more = true;
-    gather(ck, va);
-    more = ck.next(p, taps);
-    if (more) gather(ck, vb);
-    for (int i = 0; i < nchunks; i += 2) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int ii = i + u;
-        if (ii < nchunks) {
-          const int s = ii % S, round = ii / S;
-          if (round > 0) mbar_wait(&bar_free[s], (round - 1) & 1);
-          split_store(s, u == 0 ? va : vb);
-          if (more) more = ck.next(p, taps);
-          if (more) gather(ck, u == 0 ? va : vb);
-          fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_a[s]);
-        }
-      }
-    }
-
-    // ------------------------------------ epilogue ------------------------------------------
+    // ================================ epilogue ================================================
     // Phase 1: TMEM -> registers (MAIN + CORR) -> padded smem panel.  Phase 2: coalesced global
-    // traffic (4 rows x 128 B per warp instruction) with the affine / activation / GRU math.
+    // traffic (4 pixels x 128 B per warp instruction) with the affine / activation / GRU math.
+    const int half = (warp - 2) >> 2;
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
     constexpr int PITCH = 36;                                   // floats; conflict-free for both phases
@@ -356,6 +320,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtenso
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     const int st = tid - 64 - 128 * half;                       // 0..127 inside this warp set
     const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
+    const int pc4 = st & 7;
     for (int c = cbeg; c < cend; c += 32) {
       const int pw = min(32, cend - c);
       for (int g = 0; g < pw; g += 16) {
@@ -372,27 +337,26 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtenso
         for (int j = 0; j < 4; ++j) d4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
       }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-      const int pc4 = st & 7;
-      if (pc4 * 4 < pw) {
-        const int nb = n0 + c + pc4 * 4;
+      const int nb = n0 + c + pc4 * 4;
+      if (pc4 * 4 < pw && nb < p.cout) {
+        float sc[4], sh[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = nb + j < p.cout;
+          sc[j] = p.alpha * ((p.scale && ok) ? __ldg(p.scale + nb + j) : 1.f);
+          sh[j] = (p.shift && ok) ? __ldg(p.shift + nb + j) : 0.f;
+        }
+        const bool vec4 = nb + 3 < p.cout;
 #pragma unroll 2
         for (int it = 0; it < 8; ++it) {
           const int row = it * 16 + (st >> 3);
-          const int pm = m0 + row;
-          if (pm >= p.m_total || nb >= p.cout) continue;
-          const long long pix = p.per_sample ? ((long long)sample * p.m_total + pm) : (long long)pm;
+          const int oy = oy0 + (row >> p.tw_shift), ox = ox0 + (row & (p.tw - 1));
+          if (oy >= p.out_h || ox >= p.out_w) continue;
+          const long long pix = ((long long)sample * p.out_h + oy) * p.out_w + ox;
           const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
-          float y[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int n = nb + j;
-            const bool ok = n < p.cout;
-            const float sc = p.alpha * ((p.scale && ok) ? __ldg(p.scale + n) : 1.f);
-            const float sh = (p.shift && ok) ? __ldg(p.shift + n) : 0.f;
-            y[j] = fmaf(y[j], sc, sh);
-          }
+          float y[4] = {fmaf(a4.x, sc[0], sh[0]), fmaf(a4.y, sc[1], sh[1]), fmaf(a4.z, sc[2], sh[2]), fmaf(a4.w, sc[3], sh[3])};
           if (p.epilogue == ACCFLOW_EPI_STORE) {
-            if (p.out_vec && nb + 3 < p.cout) {
+            if (p.out_vec && vec4) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) y[j] = act_apply(y[j], p.act);
               if (p.residual) {
@@ -404,6 +368,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtenso
                 for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
               }
               *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
+              if (p.out_pl.ptr) store_planes4(p.out_pl, NPL, pix, nb, y);
             } else {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -413,33 +378,37 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtenso
                   float o = act_apply(y[j], second ? p.act2 : p.act);
                   if (p.residual) o += p.residual[pix * p.res_ld + n];
                   if (p.post_relu) o = fmaxf(o, 0.f);
-                  if (second && p.out2) p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
-                  else p.out[pix * p.out_ld + n] = o;
+                  if (second && p.out2) {
+                    p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
+                    if (p.out2_pl.ptr) store_planes1(p.out2_pl, NPL, pix, n - p.act_split, o);
+                  } else {
+                    p.out[pix * p.out_ld + n] = o;
+                    if (p.out_pl.ptr) store_planes1(p.out_pl, NPL, pix, n, o);
+                  }
                 }
               }
             }
           } else if (p.epilogue == ACCFLOW_EPI_GRU_ZR) {
-            const int hd = p.cout >> 1;
+            const int hd = p.cout >> 1;   // multiple of 4 (checked on the host): a group never straddles z | r
+            float g4[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int n = nb + j;
-              if (n < p.cout) {
-                const float gte = 1.f / (1.f + expf(-y[j]));
-                if (n < hd) p.z[pix * p.z_ld + n] = gte;
-                else p.out2[pix * p.out2_ld + (n - hd)] = gte * p.h[pix * p.h_ld + (n - hd)];
-              }
+            for (int j = 0; j < 4; ++j) g4[j] = 1.f / (1.f + expf(-y[j]));
+            if (nb < hd) {
+              *reinterpret_cast<float4*>(p.z + pix * p.z_ld + nb) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+            } else {
+              const int n = nb - hd;
+              const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + n);
+              float o[4] = {g4[0] * hh.x, g4[1] * hh.y, g4[2] * hh.z, g4[3] * hh.w};
+              *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
+              if (p.out2_pl.ptr) store_planes4(p.out2_pl, NPL, pix, n, o);
             }
           } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int n = nb + j;
-              if (n < p.cout) {
-                const float qv = tanhf(y[j]);
-                const float zz = p.z[pix * p.z_ld + n];
-                const float hh = p.h[pix * p.h_ld + n];
-                p.h[pix * p.h_ld + n] = (1.f - zz) * hh + zz * qv;
-              }
-            }
+            const float4 zz = *reinterpret_cast<const float4*>(p.z + pix * p.z_ld + nb);
+            const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + nb);
+            float o[4] = {(1.f - zz.x) * hh.x + zz.x * tanhf(y[0]), (1.f - zz.y) * hh.y + zz.y * tanhf(y[1]),
+                          (1.f - zz.z) * hh.z + zz.z * tanhf(y[2]), (1.f - zz.w) * hh.w + zz.w * tanhf(y[3])};
+            *reinterpret_cast<float4*>(p.h + pix * p.h_ld + nb) = make_float4(o[0], o[1], o[2], o[3]);
+            if (p.h_pl.ptr) store_planes4(p.h_pl, NPL, pix, nb, o);
           }
         }
       }
@@ -455,21 +424,23 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtenso
   }
 }
 
-// fp32 [rows][k] (row stride ld) -> up to three bf16 planes [plane][rows][k_pitch], zero padded.
-__global__ void split_planes_kernel(const float* __restrict__ x, long long rows, int k, int ld, int k_pitch,
-                                    int nplanes, __nv_bfloat16* __restrict__ out) {
+// fp32 [rows][k] (row stride ld) -> bf16 planes: out[pl*plane_stride + row*pitch + c], c < k_fill
+// (columns k..k_fill-1 are zero-filled so TMA never reads uninitialised padding).
+__global__ void split_planes_kernel(const float* __restrict__ x, long long rows, int k, int ld, int k_fill, int pitch,
+                                    long long plane_stride, int nplanes, __nv_bfloat16* __restrict__ out) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i >= rows * k_pitch) return;
-  const long long r = i / k_pitch;
-  const int c = (int)(i - r * k_pitch);
+  if (i >= rows * k_fill) return;
+  const long long r = i / k_fill;
+  const int c = (int)(i - r * k_fill);
   const float v = c < k ? __ldg(x + r * ld + c) : 0.f;
+  const long long o = r * pitch + c;
   const __nv_bfloat16 p0 = __float2bfloat16_rn(v);
-  out[i] = p0;
+  out[o] = p0;
   if (nplanes > 1) {
     const float r1 = v - __bfloat162float(p0);
     const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
-    out[rows * k_pitch + i] = p1;
-    out[2 * rows * k_pitch + i] = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+    out[plane_stride + o] = p1;
+    out[2 * plane_stride + o] = __float2bfloat16_rn(r1 - __bfloat162float(p1));
   }
 }
 
@@ -496,56 +467,63 @@ static EncodeTiledFn encode_fn() {
 
 using namespace accflow;
 
-extern "C" int accflow_split_bf16_planes(const float* x, long long rows, int k, int ld, int k_pitch, int nplanes,
-                                         void* out_planes, void* stream) {
-  ACCFLOW_REQUIRE(x && out_planes && rows > 0 && k > 0 && ld >= k && k_pitch >= k && k_pitch % 8 == 0,
+extern "C" int accflow_split_bf16_planes(const float* x, long long rows, int k, int ld, int k_fill, int pitch,
+                                         long long plane_stride, int nplanes, void* out_planes, void* stream) {
+  ACCFLOW_REQUIRE(x && out_planes && rows > 0 && k > 0 && ld >= k && k_fill >= k && pitch >= k_fill,
                   "split_bf16_planes: bad arguments");
   ACCFLOW_REQUIRE(nplanes == 1 || nplanes == 3, "split_bf16_planes: nplanes must be 1 or 3");
-  tc::split_planes_kernel<<<cdiv(rows * k_pitch, 256), 256, 0, (cudaStream_t)stream>>>(
-      x, rows, k, ld, k_pitch, nplanes, reinterpret_cast<__nv_bfloat16*>(out_planes));
+  tc::split_planes_kernel<<<cdiv(rows * k_fill, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, rows, k, ld, k_fill, pitch, plane_stride, nplanes, reinterpret_cast<__nv_bfloat16*>(out_planes));
   return launched("split_bf16_planes");
 }
 
-extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_weights* wp, int nprod, void* stream) {
-  ACCFLOW_REQUIRE(dp && wp, "conv2d_tc: null descriptor");
+extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_io* iop, const accflow_tc_weights* wp,
+                                 int nprod, void* stream) {
+  ACCFLOW_REQUIRE(dp && wp && iop, "conv2d_tc: null descriptor");
   const accflow_conv_desc& d = *dp;
   const accflow_tc_weights& w = *wp;
+  const accflow_tc_io& io = *iop;
   ACCFLOW_REQUIRE(nprod == 1 || nprod == 6, "conv2d_tc: nprod must be 1 (bf16) or 6 (bf16x3 split)");
   ACCFLOW_REQUIRE(w.planes && aligned16(w.planes) && w.nplanes >= (nprod == 1 ? 1 : 3), "conv2d_tc: weight planes missing");
   ACCFLOW_REQUIRE(w.k_pitch % 8 == 0 && w.k_pitch >= w.k && w.rows > 0 && w.t > 0, "conv2d_tc: bad weight geometry");
   ACCFLOW_REQUIRE(d.nsrc >= 1 && d.nsrc <= ACCFLOW_MAX_SRC, "conv2d_tc: nsrc=%d out of range", d.nsrc);
-  ACCFLOW_REQUIRE(d.batch > 0 && d.in_h > 0 && d.in_w > 0 && d.kh > 0 && d.kw > 0 && d.stride > 0, "conv2d_tc: bad geometry");
+  ACCFLOW_REQUIRE(d.batch > 0 && d.in_h > 0 && d.in_w > 0 && d.kh > 0 && d.kw > 0 && d.stride > 0 && d.stride <= 2,
+                  "conv2d_tc: bad geometry");
   ACCFLOW_REQUIRE(d.cout > 0 && d.cout <= w.rows, "conv2d_tc: cout=%d exceeds packed rows %d", d.cout, w.rows);
   tc::Params p;
   memset(&p, 0, sizeof(p));
+  const int nplanes = nprod == 1 ? 1 : 3;
   int cin = 0;
   for (int s = 0; s < d.nsrc; ++s) {
-    ACCFLOW_REQUIRE(d.src[s] && d.src_c[s] > 0 && d.src_ld[s] >= d.src_c[s], "conv2d_tc: bad source %d", s);
-    p.src[s] = d.src[s]; p.src_c[s] = d.src_c[s]; p.src_ld[s] = d.src_ld[s]; p.src_off[s] = cin;
-    p.src_vec[s] = aligned16(d.src[s]) && d.src_ld[s] % 4 == 0;
+    ACCFLOW_REQUIRE(d.src_c[s] > 0, "conv2d_tc: bad source %d", s);
+    ACCFLOW_REQUIRE(io.src_planes[s] && aligned16(io.src_planes[s]) && io.src_pitch[s] % 8 == 0 &&
+                        io.src_pitch[s] >= d.src_c[s] && io.src_plane_stride[s] % 8 == 0,
+                    "conv2d_tc: source %d planes must be 16B aligned with a pitch that is a multiple of 8", s);
+    p.src_c[s] = d.src_c[s]; p.src_off[s] = cin;
     cin += d.src_c[s];
   }
   ACCFLOW_REQUIRE(cin == w.k, "conv2d_tc: sources carry %d channels, weights expect %d", cin, w.k);
   const bool per_sample = d.weight_batch_stride != 0;
   ACCFLOW_REQUIRE(w.t == (per_sample ? d.batch : d.kh * d.kw), "conv2d_tc: weight T dimension mismatch");
-  p.nsrc = d.nsrc; p.batch = d.batch; p.in_h = d.in_h; p.in_w = d.in_w;
+  p.nsrc = d.nsrc; p.batch = d.batch;
   p.kh = d.kh; p.kw = d.kw; p.stride = d.stride; p.pad_h = d.pad_h; p.pad_w = d.pad_w;
   p.out_h = (d.in_h + 2 * d.pad_h - d.kh) / d.stride + 1;
   p.out_w = (d.in_w + 2 * d.pad_w - d.kw) / d.stride + 1;
   ACCFLOW_REQUIRE(p.out_h > 0 && p.out_w > 0, "conv2d_tc: empty output");
+  int tw = 8, sh = 3;
+  while (tw < p.out_w && tw < 128) { tw <<= 1; ++sh; }
+  p.tw = tw; p.tw_shift = sh; p.th = tc::BM / tw;
+  p.tiles_x = cdiv(p.out_w, p.tw); p.tiles_y = cdiv(p.out_h, p.th);
   p.per_sample = per_sample;
-  const long long mt = (long long)p.out_h * p.out_w * (per_sample ? 1 : d.batch);
-  ACCFLOW_REQUIRE(mt < (1ll << 31), "conv2d_tc: too many output pixels");
-  p.m_total = (int)mt;
   p.cout = d.cout;
   p.nprod = nprod;
-  p.nplanes = nprod == 1 ? 1 : 3;
+  p.nplanes = nplanes;
   // N tile: multiple of 32; the split mode keeps two accumulators and three weight planes resident
   const int bn_cap = nprod == 1 ? 256 : 128;
   int ntiles = cdiv(d.cout, bn_cap);
   int bn = cdiv(cdiv(d.cout, ntiles), 32) * 32;
   p.bn = bn;
-  const int stage_bytes = p.nplanes * (tc::A_PLANE_BYTES + bn * tc::KC * 2);
+  const int stage_bytes = nplanes * (tc::A_PLANE_BYTES + bn * tc::KC * 2);
   int stages = (200 * 1024) / stage_bytes;
   if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
   ACCFLOW_REQUIRE(stages >= 2, "conv2d_tc: tile does not fit shared memory");
@@ -555,12 +533,24 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_w
   p.residual = d.residual; p.res_ld = d.res_ld; p.post_relu = d.post_relu; p.epilogue = d.epilogue;
   p.out = d.out; p.out_ld = d.out_ld; p.out2 = d.out2; p.out2_ld = d.out2_ld;
   p.h = d.h; p.h_ld = d.h_ld; p.z = d.z; p.z_ld = d.z_ld;
+  auto plane_out = [](void* ptr, int pitch, long long ps, tc::PlaneOut& po) -> bool {
+    po.ptr = reinterpret_cast<__nv_bfloat16*>(ptr); po.pitch = pitch; po.plane_stride = ps;
+    return !ptr || ((reinterpret_cast<uintptr_t>(ptr) & 7u) == 0 && pitch % 4 == 0 && ps % 4 == 0);
+  };
+  ACCFLOW_REQUIRE(plane_out(io.out_planes, io.out_pitch, io.out_plane_stride, p.out_pl) &&
+                      plane_out(io.out2_planes, io.out2_pitch, io.out2_plane_stride, p.out2_pl) &&
+                      plane_out(io.h_planes, io.h_pitch, io.h_plane_stride, p.h_pl),
+                  "conv2d_tc: output planes must be 8B aligned with pitch % 4 == 0");
   if (d.epilogue == ACCFLOW_EPI_STORE) {
     ACCFLOW_REQUIRE(d.out != nullptr, "conv2d_tc: null output");
   } else if (d.epilogue == ACCFLOW_EPI_GRU_ZR) {
-    ACCFLOW_REQUIRE(d.z && d.h && d.out2 && d.cout % 2 == 0, "conv2d_tc: GRU_ZR needs z, h, out2");
+    ACCFLOW_REQUIRE(d.z && d.h && d.out2 && d.cout % 8 == 0, "conv2d_tc: GRU_ZR needs z, h, out2 and cout % 8 == 0");
+    ACCFLOW_REQUIRE(aligned16(d.z) && aligned16(d.h) && aligned16(d.out2) && d.z_ld % 4 == 0 && d.h_ld % 4 == 0 &&
+                        d.out2_ld % 4 == 0, "conv2d_tc: GRU buffers must be 16B aligned");
   } else if (d.epilogue == ACCFLOW_EPI_GRU_Q) {
-    ACCFLOW_REQUIRE(d.z && d.h, "conv2d_tc: GRU_Q needs z, h");
+    ACCFLOW_REQUIRE(d.z && d.h && d.cout % 4 == 0, "conv2d_tc: GRU_Q needs z, h and cout % 4 == 0");
+    ACCFLOW_REQUIRE(aligned16(d.z) && aligned16(d.h) && d.z_ld % 4 == 0 && d.h_ld % 4 == 0,
+                    "conv2d_tc: GRU buffers must be 16B aligned");
   } else {
     return fail(-1, "conv2d_tc: unknown epilogue %d", d.epilogue);
   }
@@ -569,16 +559,32 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_w
 
   tc::EncodeTiledFn enc = tc::encode_fn();
   ACCFLOW_REQUIRE(enc != nullptr, "conv2d_tc: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
-  CUtensorMap map;
-  const cuuint64_t gdim[4] = {(cuuint64_t)w.k, (cuuint64_t)w.rows, (cuuint64_t)w.t, (cuuint64_t)w.nplanes};
-  const cuuint64_t gstr[3] = {(cuuint64_t)w.k_pitch * 2, (cuuint64_t)w.k_pitch * 2 * w.rows,
-                              (cuuint64_t)w.k_pitch * 2 * w.rows * w.t};
-  const cuuint32_t box[4] = {(cuuint32_t)tc::KC, (cuuint32_t)bn, 1, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w.planes), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  ACCFLOW_REQUIRE(cr == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  tc::TmapPack maps;
+  memset(&maps, 0, sizeof(maps));
+  {
+    const cuuint64_t gdim[4] = {(cuuint64_t)w.k, (cuuint64_t)w.rows, (cuuint64_t)w.t, (cuuint64_t)w.nplanes};
+    const cuuint64_t gstr[3] = {(cuuint64_t)w.k_pitch * 2, (cuuint64_t)w.k_pitch * 2 * w.rows,
+                                (cuuint64_t)w.k_pitch * 2 * w.rows * w.t};
+    const cuuint32_t box[4] = {(cuuint32_t)tc::KC, (cuuint32_t)bn, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = enc(&maps.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w.planes), gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACCFLOW_REQUIRE(cr == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(weights) failed (%d)", (int)cr);
+  }
+  for (int s = 0; s < d.nsrc; ++s) {
+    // activation planes [plane][batch][in_h][in_w][pitch]; box = 64 channels x (tw x th) pixels, strided
+    const cuuint64_t pitchb = (cuuint64_t)io.src_pitch[s] * 2;
+    const cuuint64_t gdim[5] = {(cuuint64_t)d.src_c[s], (cuuint64_t)d.in_w, (cuuint64_t)d.in_h, (cuuint64_t)d.batch,
+                                (cuuint64_t)nplanes};
+    const cuuint64_t gstr[4] = {pitchb, pitchb * d.in_w, pitchb * d.in_w * d.in_h, (cuuint64_t)io.src_plane_stride[s] * 2};
+    const cuuint32_t box[5] = {(cuuint32_t)tc::KC, (cuuint32_t)(p.tw * d.stride), (cuuint32_t)(p.th * d.stride), 1, 1};
+    const cuuint32_t estr[5] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1, 1};
+    CUresult cr = enc(&maps.a[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(io.src_planes[s]), gdim, gstr, box,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACCFLOW_REQUIRE(cr == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(source %d) failed (%d)", s, (int)cr);
+  }
 
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   static thread_local int cfg_dev = -1;
@@ -589,7 +595,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_w
     if (e != cudaSuccess) return fail((int)e, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
     cfg_dev = dev;
   }
-  dim3 grid(cdiv(p.m_total, tc::BM), cdiv(d.cout, bn), per_sample ? d.batch : 1);
-  tc::conv_tc_kernel<<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, map);
+  dim3 grid(p.tiles_x * p.tiles_y * d.batch, cdiv(d.cout, bn), 1);
+  tc::conv_tc_kernel<<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
   return launched("conv2d_tc");
 }

@@ -25,23 +25,28 @@ def _stream():
 
 
 class View:
-    """A channel slice of an NHWC fp32 tensor: (ptr, batch, h, w, channels, ld)."""
-    __slots__ = ("t", "ptr", "b", "h", "w", "c", "ld")
+    """A (batch-range, channel-range) slice of an NHWC fp32 tensor ``t`` [B, h, w, ld]."""
+    __slots__ = ("t", "b0", "b", "h", "w", "c0", "c", "ld", "ptr")
 
-    def __init__(self, t: torch.Tensor, ptr=None, b=None, c=None):
+    def __init__(self, t: torch.Tensor, b0: int = 0, b: Optional[int] = None, c0: int = 0, c: Optional[int] = None):
         assert t.dtype == F32 and t.is_contiguous() and t.dim() == 4
         self.t = t
-        self.b, self.h, self.w, self.ld = (t.shape[0] if b is None else b), t.shape[1], t.shape[2], t.shape[3]
-        self.c = self.ld if c is None else c
-        self.ptr = t.data_ptr() if ptr is None else ptr
+        self.h, self.w, self.ld = t.shape[1], t.shape[2], t.shape[3]
+        self.b0, self.b = b0, (t.shape[0] - b0 if b is None else b)
+        self.c0, self.c = c0, (self.ld - c0 if c is None else c)
+        self.ptr = t.data_ptr() + 4 * (b0 * self.h * self.w * self.ld + c0)
 
     def ch(self, c0: int, c1: int) -> "View":
         assert 0 <= c0 < c1 <= self.c
-        return View(self.t, self.ptr + 4 * c0, self.b, c1 - c0)
+        return View(self.t, self.b0, self.b, self.c0 + c0, c1 - c0)
 
     def rows(self, b0: int, b1: int) -> "View":
         assert 0 <= b0 < b1 <= self.b
-        return View(self.t, self.ptr + 4 * b0 * self.h * self.w * self.ld, b1 - b0, self.c)
+        return View(self.t, self.b0 + b0, b1 - b0, self.c0, self.c)
+
+    @property
+    def full_rows(self) -> bool:
+        return self.b0 == 0 and self.b == self.t.shape[0]
 
     @property
     def npix(self):
@@ -115,6 +120,11 @@ class Kernels:
         self.precision = precision       # fp32: FFMA kernels; bf16x3 / bf16: tcgen05 kernels (6 / 1 products)
         L.load()
         self._ws: Dict[tuple, torch.Tensor] = {}
+        # bf16 planes that accompany fp32 activations consumed by the tensor-core convs:
+        # root data_ptr -> planes tensor [3, B, h, w, Cp] and the channel ranges whose planes are stale
+        self._planes: Dict[int, torch.Tensor] = {}
+        self._stale: Dict[int, list] = {}
+        self._roots: Dict[int, torch.Tensor] = {}   # keeps the fp32 root alive so its address cannot be recycled
         self.profile = None      # bench.py: list of (start_event, end_event, flops) per conv launch
 
     # ---- workspace -----------------------------------------------------------------------
@@ -128,6 +138,73 @@ class Kernels:
 
     def view(self, name: str, b: int, h: int, w: int, c: int) -> View:
         return View(self.buf(name, b, h, w, c))
+
+    # ---- bf16 planes bookkeeping ---------------------------------------------------------
+    @property
+    def tc(self) -> bool:
+        return self.precision != "fp32"
+
+    @property
+    def nplanes(self) -> int:
+        return 3 if self.precision == "bf16x3" else 1
+
+    def wrote(self, v: Optional[View]):
+        """A non-tensor-core kernel wrote ``v``: its planes (if any exist) are stale."""
+        if v is None or not self.tc:
+            return
+        key = v.t.data_ptr()
+        if key in self._planes:
+            rng = (v.c0, v.c0 + v.c)
+            st = self._stale[key]
+            if rng not in st:
+                st.append(rng)
+
+    def _plane_geom(self, v: View):
+        cp = (v.ld + 7) // 8 * 8
+        return cp, v.t.shape[0] * v.h * v.w * cp
+
+    def planes_ptr(self, v: View, create: bool):
+        """-> (ptr of the slice's first element in plane 0, pitch, plane_stride) or None."""
+        key = v.t.data_ptr()
+        pl = self._planes.get(key)
+        if pl is None:
+            if not create:
+                return None
+            cp, _ = self._plane_geom(v)
+            pl = torch.empty(3, v.t.shape[0], v.h, v.w, cp, device=self.device, dtype=torch.bfloat16)
+            self._planes[key] = pl
+            self._stale[key] = [(0, v.ld)]
+            self._roots[key] = v.t
+        cp, stride = self._plane_geom(v)
+        return pl.data_ptr() + 2 * (v.b0 * v.h * v.w * cp + v.c0), cp, stride
+
+    def release_planes(self):
+        """Drop all plane buffers (they are rebuilt on demand)."""
+        self._planes.clear()
+        self._stale.clear()
+        self._roots.clear()
+
+    def ensure_planes(self, v: View):
+        """Make the planes of ``v`` current (split pass over the stale channel ranges it overlaps)."""
+        ptr, cp, stride = self.planes_ptr(v, create=True)
+        key = v.t.data_ptr()
+        st = self._stale[key]
+        lo, hi = v.c0, v.c0 + v.c
+        for rng in [r for r in st if r[0] < hi and r[1] > lo]:
+            r0, r1 = rng
+            rows = v.t.shape[0] * v.h * v.w
+            L.call("accflow_split_bf16_planes", v.t.data_ptr() + 4 * r0, rows, r1 - r0, v.ld, r1 - r0, cp, stride,
+                   self.nplanes, self._planes[key].data_ptr() + 2 * r0, _stream())
+            st.remove(rng)
+        return ptr, cp, stride
+
+    def _fresh(self, v: View):
+        """The tensor-core epilogue just wrote the planes of ``v``."""
+        if not v.full_rows:
+            return
+        key = v.t.data_ptr()
+        lo, hi = v.c0, v.c0 + v.c
+        self._stale[key] = [r for r in self._stale[key] if not (r[0] >= lo and r[1] <= hi)]
 
     # ---- convolution ---------------------------------------------------------------------
     def conv(self, pc: PackedConv, srcs: Sequence[View], out: Optional[View] = None, act=L.ACT_NONE, alpha=1.0,
@@ -143,7 +220,7 @@ class Kernels:
         assert cin == pc.cin, f"conv expects {pc.cin} input channels, got {cin}"
         s0 = srcs[0]
         d.nsrc, d.batch, d.in_h, d.in_w = len(srcs), s0.b, s0.h, s0.w
-        tc = self.precision != "fp32"
+        tc = self.tc
         if not tc:
             d.weight = pc.w.data_ptr() if weight_ptr is None else weight_ptr
         d.weight_batch_stride = weight_batch_stride
@@ -167,25 +244,51 @@ class Kernels:
         if z is not None:
             d.z, d.z_ld = z.ptr, z.ld
         if tc:
+            io = L.TcIO()
+            for k, sv in enumerate(srcs):
+                io.src_planes[k], io.src_pitch[k], io.src_plane_stride[k] = self.ensure_planes(sv)
+            written = []
+            if epilogue == L.EPI_STORE:
+                targets = (("out", out), ("out2", out2 if act_split else None))
+            elif epilogue == L.EPI_GRU_ZR:
+                targets = (("out2", out2),)
+            else:
+                targets = (("h", h),)
+            for name, tv in targets:
+                if tv is None:
+                    continue
+                got = self.planes_ptr(tv, create=False)
+                if got is not None and tv.c0 % 4 == 0:
+                    setattr(io, name + "_planes", got[0])
+                    setattr(io, name + "_pitch", got[1])
+                    setattr(io, name + "_plane_stride", got[2])
+                    written.append(tv)
+                else:
+                    self.wrote(tv)
             tw = tc_b if tc_b is not None else pc.tc_weights()
-            args = ("accflow_conv2d_tc", C.byref(d), C.byref(tw), 6 if self.precision == "bf16x3" else 1, _stream())
+            args = ("accflow_conv2d_tc", C.byref(d), C.byref(io), C.byref(tw), 6 if self.precision == "bf16x3" else 1,
+                    _stream())
         else:
             args = ("accflow_conv2d_f32", C.byref(d), _stream())
+            written = []
         if self.profile is None:
             L.call(*args)
-            return
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        oh = (s0.h + 2 * pc.pad_h - pc.kh) // pc.stride + 1
-        ow = (s0.w + 2 * pc.pad_w - pc.kw) // pc.stride + 1
-        e0.record()
-        L.call(*args)
-        e1.record()
-        self.profile.append((e0, e1, 2.0 * s0.b * oh * ow * d.cout * cin * pc.kh * pc.kw))
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            oh = (s0.h + 2 * pc.pad_h - pc.kh) // pc.stride + 1
+            ow = (s0.w + 2 * pc.pad_w - pc.kw) // pc.stride + 1
+            e0.record()
+            L.call(*args)
+            e1.record()
+            self.profile.append((e0, e1, 2.0 * s0.b * oh * ow * d.cout * cin * pc.kh * pc.kw))
+        for tv in written:
+            self._fresh(tv)
 
     def conv_smallc(self, x_ptr: int, nchw: bool, batch, cin, h, w, pc: PackedConv, act, out: View):
         L.call("accflow_conv_smallc_f32", x_ptr, int(nchw), batch, cin, h, w, pc.w.data_ptr(),
                None if pc.scale is None else pc.scale.data_ptr(), pc.shift.data_ptr(), pc.kh, pc.stride, pc.cout,
                act, out.ptr, out.ld, _stream())
+        self.wrote(out)
 
     def instnorm(self, x: View, relu: bool, residual: Optional[View], post_relu: bool, out: View, eps=1e-5):
         assert x.c == x.ld and out.c == out.ld
@@ -196,6 +299,7 @@ class Kernels:
         L.call("accflow_instnorm_f32", x.ptr, x.b, hw, x.c, eps, int(relu),
                None if residual is None else residual.ptr, int(post_relu), out.ptr, partial.data_ptr(),
                stats.data_ptr(), _stream())
+        self.wrote(out)
 
     def gemm_nt(self, tag: str, a: View, b: View, out: View, alpha=1.0):
         """out[s, m, n] = alpha * sum_k a[s, m, k] * b[s, n, k]  (per sample s; b given row-major [n][k]).
@@ -212,7 +316,8 @@ class Kernels:
         npl = 3 if self.precision == "bf16x3" else 1
         pitch = (K + 7) // 8 * 8
         planes = self.buf16(tag + ".bpl", npl, B, N, pitch)
-        L.call("accflow_split_bf16_planes", b.ptr, B * N, K, b.ld, pitch, npl, planes.data_ptr(), _stream())
+        L.call("accflow_split_bf16_planes", b.ptr, B * N, K, b.ld, K, pitch, B * N * pitch, npl, planes.data_ptr(),
+               _stream())
         tw = L.TcWeights(planes.data_ptr(), npl, N, K, pitch, B)
         self.conv(_Gemm(K, N, N), [a], out, alpha=alpha, weight_batch_stride=1, use_affine=False, tc_b=tw)
 
@@ -231,7 +336,8 @@ class Kernels:
         bt = self.buf(tag + ".bt", B, N, Kp, zero=True)
         self.transpose(b, bt, Kp)
         planes = self.buf16(tag + ".bpl", npl, B, N, Kp)
-        L.call("accflow_split_bf16_planes", bt.data_ptr(), B * N, K, Kp, Kp, npl, planes.data_ptr(), _stream())
+        L.call("accflow_split_bf16_planes", bt.data_ptr(), B * N, K, Kp, K, Kp, B * N * Kp, npl, planes.data_ptr(),
+               _stream())
         tw = L.TcWeights(planes.data_ptr(), npl, N, K, Kp, B)
         self.conv(_Gemm(K, N, N), [a], out, alpha=alpha, weight_batch_stride=1, residual=residual, use_affine=False,
                   tc_b=tw)
@@ -249,6 +355,9 @@ class Kernels:
 
     def softmax_rows(self, t: torch.Tensor, rows: int, n: int):
         L.call("accflow_softmax_rows_f32", t.data_ptr(), rows, n, _stream())
+        key = t.data_ptr()
+        if key in self._planes:
+            self._stale[key] = [(0, t.shape[-1])]
 
 
 def _p4(n: int) -> int:
@@ -455,6 +564,8 @@ class FlowEstimatorEngine:
             L.call("accflow_corr_lookup_f32", lv[0].data_ptr(), lv[1].data_ptr(), lv[2].data_ptr(), lv[3].data_ptr(),
                    B, h, w, self.RADIUS, coords.data_ptr(), corr.ptr, corr.ld, flow.data_ptr(), mf.ch(126, 128).ptr,
                    mf.ld, s())
+            k.wrote(corr)
+            k.wrote(mf.ch(126, 128))
             k.conv(self.convc1, [corr], cor1, act=L.ACT_RELU)
             k.conv(self.convc2, [cor1], cf.ch(0, 192), act=L.ACT_RELU)
             k.conv_smallc(flow.data_ptr(), False, B, 2, h, w, self.convf1, L.ACT_RELU, flo1)
@@ -578,6 +689,8 @@ class AccFlowEngine:
                    None, 0, s())
             L.call("accflow_warp_occ_f32", c1.ptr, c1.ld, cn.ptr, cn.ld, flow_ini.data_ptr(), b, h, w, 128, None, 0,
                    emap.ptr, emap.ld, s())
+            k.wrote(occ)
+            k.wrote(emap)
             # AccPlus (AccFlow_.py:97-109)
             t256 = k.view("acc.t256", b, h, w, 256)
             x1 = k.view("acc.x1", b, h, w, 128)
@@ -591,7 +704,9 @@ class AccFlowEngine:
             k.conv(self.a22, [t256], x2, act=L.ACT_RELU)
             k.conv(self.a24, [x2], om.ch(0, 27))
             L.call("accflow_deform_gather_f32", f.ptr, f.ld, om.ptr, om.ld, b, h, w, 128, col.data_ptr(), s())
-            k.conv(self.dcn, [View(col.view(b, h, w, 9 * 128))], fdc)
+            colv = View(col.view(b, h, w, 9 * 128))
+            k.wrote(colv)
+            k.conv(self.dcn, [colv], fdc)
             k.conv(self.a30, [fdc, df, occ], t256, act=L.ACT_RELU)
             k.conv(self.a32, [t256], x1)
             k.conv(self.a40, [x1, c1, fdc, df], t256, act=L.ACT_RELU)
@@ -604,6 +719,7 @@ class AccFlowEngine:
             k.conv(self.bl2, [t256], m, act=L.ACT_SIGMOID)
             fuse = k.view("acc.fuse", b, h, w, 128)
             L.call("accflow_blend_f32", f_ini.ptr, f_acc.ptr, m.ptr, 1, b * P, 128, fuse.ptr, s())
+            k.wrote(fuse)
             # FlowDecoder (AccFlow_.py:40-45)
             small = torch.empty(b, h, w, 2, device=dev, dtype=F32)
             k.conv(self.df0, [fuse], t256, act=L.ACT_RELU)

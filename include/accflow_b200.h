@@ -100,16 +100,31 @@ typedef struct accflow_tc_weights {
   int t;              /* taps or samples */
 } accflow_tc_weights;
 
-/* Same contract as accflow_conv2d_f32 (the descriptor's `weight`/`cout_pad` are ignored) on the
- * 5th-gen tensor cores: tcgen05.mma with TMEM accumulators, weights by TMA, fp32 activations
- * split to bf16 planes in-kernel.  nprod = 1: bf16 products; nprod = 6: bf16x3 split products
- * (fp32-class accuracy, fp32 accumulate). */
-ACCFLOW_API int accflow_conv2d_tc(const accflow_conv_desc* d, const accflow_tc_weights* w, int nprod, void* stream);
+/* bf16 planes that travel next to the fp32 activations (x = p0 + p1 + p2): element (plane, pixel,
+ * channel) of a slice lives at planes[plane*plane_stride + pixel*pitch + channel].  Sources are
+ * mandatory (the tensor cores read only planes); the planes of the outputs are optional and
+ * are written by the epilogue so that the next convolution can consume them without a pass. */
+typedef struct accflow_tc_io {
+  const void* src_planes[ACCFLOW_MAX_SRC];
+  int src_pitch[ACCFLOW_MAX_SRC];
+  long long src_plane_stride[ACCFLOW_MAX_SRC];
+  void* out_planes;  int out_pitch;  long long out_plane_stride;
+  void* out2_planes; int out2_pitch; long long out2_plane_stride;
+  void* h_planes;    int h_pitch;    long long h_plane_stride;
+} accflow_tc_io;
 
-/* fp32 [rows][k] (row stride ld) -> bf16 planes [nplanes][rows][k_pitch] (zero padded): prepares
+/* Same contract as accflow_conv2d_f32 (the descriptor's fp32 `src` pointers, `weight` and
+ * `cout_pad` are ignored) on the 5th-gen tensor cores: tcgen05.mma with TMEM accumulators, both
+ * operands by TMA (im2col boxes with zero fill for the activations).
+ * nprod = 1: bf16 products; nprod = 6: bf16x3 split products (fp32-class accuracy). */
+ACCFLOW_API int accflow_conv2d_tc(const accflow_conv_desc* d, const accflow_tc_io* io, const accflow_tc_weights* w,
+                                  int nprod, void* stream);
+
+/* fp32 [rows][k] (row stride ld) -> bf16 planes out[pl*plane_stride + row*pitch + c] for c < k_fill
+ * (zero for k <= c < k_fill).  Used for activations produced by non-tensor-core kernels and for
  * the per-sample B operands (fmap2 of raft/corr.py:47-55, k / v of gma/modules.py:57-113). */
-ACCFLOW_API int accflow_split_bf16_planes(const float* x, long long rows, int k, int ld, int k_pitch, int nplanes,
-                                          void* out_planes, void* stream);
+ACCFLOW_API int accflow_split_bf16_planes(const float* x, long long rows, int k, int ld, int k_fill, int pitch,
+                                          long long plane_stride, int nplanes, void* out_planes, void* stream);
 
 /* Small-input-channel KSxKS convolution (cin in {2,3}), fused affine + activation.
  * 7x7/s2 stem of BasicEncoder (raft/extractor.py:163-167,209) reading NCHW images, and the
