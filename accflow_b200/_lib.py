@@ -51,6 +51,7 @@ SIGNATURES = {
     "accflow_abi_version": [],
     "accflow_last_error": [C.c_char_p, C.c_size_t],
     "accflow_launch_count": [i],
+    "accflow_launch_count_add": [ll],
     "accflow_conv2d_f32": [C.POINTER(ConvDesc), fp],
     "accflow_conv2d_tc": [C.POINTER(ConvDesc), C.POINTER(TcIO), C.POINTER(TcWeights), i, fp],
     "accflow_split_bf16_planes": [fp, ll, i, i, i, i, ll, i, fp, fp],
@@ -70,8 +71,9 @@ SIGNATURES = {
     "accflow_blend_f32": [fp, fp, fp, i, ll, i, fp, fp],
     "accflow_softmax_rows_f32": [fp, ll, i, fp],
 }
-_RESTYPE = {"accflow_launch_count": ll}
-_NO_CHECK = {"accflow_abi_version", "accflow_last_error", "accflow_launch_count", "accflow_instnorm_chunks"}
+_RESTYPE = {"accflow_launch_count": ll, "accflow_launch_count_add": ll}
+_NO_CHECK = {"accflow_abi_version", "accflow_last_error", "accflow_launch_count", "accflow_launch_count_add",
+             "accflow_instnorm_chunks"}
 
 _lib = None
 

@@ -439,6 +439,10 @@ extern "C" long long accflow_launch_count(int reset) {
   return v;
 }
 
+extern "C" long long accflow_launch_count_add(long long n) {
+  return launch_counter().fetch_add(n) + n;
+}
+
 extern "C" int accflow_instnorm_chunks(int hw) { return cdiv(hw, IN_CHUNK); }
 
 extern "C" int accflow_instnorm_f32(const float* x, int batch, int hw, int c, float eps, int relu,

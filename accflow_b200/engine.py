@@ -364,6 +364,47 @@ def _p4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
+class GraphCache:
+    """CUDA-graph replay of a whole forward pass.
+
+    The eager pass issues ~1.7k kernel launches per clip batch through ctypes; replaying them as
+    one captured graph removes the host from the critical path (SURVEY.md §7 hard part 5).
+    Inputs are copied into static buffers, the captured outputs are cloned for the caller.
+    Capture happens on the third call with a given key (two eager warm-ups first, so that every
+    workspace / plane buffer exists and the plane-freshness state is in its steady cycle).
+    """
+
+    def __init__(self):
+        self.entries = {}
+
+    def run(self, key, inputs: Sequence[Optional[torch.Tensor]], fn):
+        ent = self.entries.get(key)
+        if ent is None:
+            static_in = [None if t is None else torch.empty_like(t) for t in inputs]
+            ent = self.entries[key] = {"in": static_in, "graph": None, "out": None, "warm": 0}
+        for dst, src in zip(ent["in"], inputs):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        if ent["graph"] is None:
+            if ent["warm"] < 2:
+                ent["warm"] += 1
+                return fn(*ent["in"])
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = L.call("accflow_launch_count", 0)
+            with torch.cuda.graph(graph):
+                out = fn(*ent["in"])
+            ent["graph"], ent["out"] = graph, out
+            ent["launches"] = L.call("accflow_launch_count", 0) - n0
+            L.call("accflow_launch_count_add", -ent["launches"])     # capture itself executed nothing
+        ent["graph"].replay()
+        L.call("accflow_launch_count_add", ent["launches"])
+        out = ent["out"]
+        if isinstance(out, (list, tuple)):
+            return [o.clone() for o in out]
+        return out.clone()
+
+
 # ================================================================================ encoders
 class EncoderPlan:
     """BasicEncoder (raft/extractor.py:137-225) with norm in {'instance','batch','none'}."""
@@ -450,6 +491,7 @@ class FlowEstimatorEngine:
                  precision: str = "fp32"):
         self.k = Kernels(device, precision)
         self.device, self.gma, self.pfx = device, gma, pfx
+        self.graphs = GraphCache()
         self.repack(sd)
 
     def repack(self, sd):
@@ -589,12 +631,21 @@ class FlowEstimatorEngine:
         L.call("accflow_convex_upsample_f32", coords.data_ptr(), 2, 1, mask.ptr, mask.ld, B, h, w, out.data_ptr(), s())
         return out
 
-    def forward(self, image1, image2, iters=12, flow_init=None, tag="fe"):
+    def forward(self, image1, image2, iters=12, flow_init=None, tag="fe", graph=False):
         image1 = image1.to(device=self.device, dtype=F32).contiguous()
         image2 = image2.to(device=self.device, dtype=F32).contiguous()
+        if flow_init is not None:
+            flow_init = flow_init.to(device=self.device, dtype=F32).contiguous()
+
+        def eager(i1, i2, fi):
+            st = self.features(i1, i2, tag)
+            return self.iterate(st, iters, fi, tag)
+
         with torch.cuda.device(self.device):
-            st = self.features(image1, image2, tag)
-            return self.iterate(st, iters, flow_init, tag)
+            if not graph:
+                return eager(image1, image2, flow_init)
+            key = (tuple(image1.shape), iters, flow_init is not None, tag)
+            return self.graphs.run(key, [image1, image2, flow_init], eager)
 
 
 class _Gemm:
@@ -618,6 +669,7 @@ class AccFlowEngine:
         self.device = device
         self.ofe = FlowEstimatorEngine(sd, device, "ofe.", gma, precision)
         self.k = self.ofe.k
+        self.graphs = GraphCache()
         self.repack(sd, repack_ofe=False)
 
     def repack(self, sd, repack_ofe=True):
@@ -731,10 +783,19 @@ class AccFlowEngine:
             L.call("accflow_convex_upsample_f32", small.data_ptr(), 2, 0, mask.ptr, mask.ld, b, h, w, out.data_ptr(), s())
         return small.permute(0, 3, 1, 2).contiguous(), out
 
-    def forward(self, images: List[torch.Tensor], iters=12) -> List[torch.Tensor]:
-        flow = None
-        outs = []
-        for i in range(2, len(images)):
-            flow, up = self.iter(images[i], images[i - 1], images[0], flow, iters)
-            outs.append(up)
-        return outs
+    def forward(self, images: List[torch.Tensor], iters=12, graph=False) -> List[torch.Tensor]:
+        images = [t.to(device=self.device, dtype=F32).contiguous() for t in images]
+
+        def eager(*imgs):
+            flow = None
+            outs = []
+            for i in range(2, len(imgs)):
+                flow, up = self.iter(imgs[i], imgs[i - 1], imgs[0], flow, iters)
+                outs.append(up)
+            return outs
+
+        if not graph:
+            return eager(*images)
+        with torch.cuda.device(self.device):
+            key = (tuple(images[0].shape), len(images), iters)
+            return self.graphs.run(key, images, eager)

@@ -60,4 +60,5 @@ class AccFlow(nn.Module):
     def forward(self, images, test_mode=False):
         """[I0, I1, ..., In] -> [F(2->0), F(3->0), ..., F(n->0)] (``test_mode`` is ignored, as in the reference)."""
         images = list(images)
-        return self.engine(images[0].device if images[0].is_cuda else None).forward(images, self.iters)
+        eng = self.engine(images[0].device if images[0].is_cuda else None)
+        return eng.forward(images, self.iters, graph=self.ofe.use_cuda_graph)

@@ -26,7 +26,9 @@ class FlowEstimatorBase(nn.Module):
         self._engines = {}
         # arithmetic of the conv/GEMM kernels: "fp32" (FFMA, exact), "bf16x3" (tcgen05, bf16x3 split
         # products = fp32-class), "bf16" (tcgen05, bf16 products = the reference's autocast class)
-        self.precision = os.environ.get("ACCFLOW_PRECISION", "fp32")
+        self.precision = os.environ.get("ACCFLOW_PRECISION", "bf16x3")
+        # replay whole forwards as CUDA graphs (captured on the third call per input shape)
+        self.use_cuda_graph = os.environ.get("ACCFLOW_GRAPH", "1") != "0"
 
     # ---- reference API -------------------------------------------------------------------
     def freeze_bn(self):
@@ -67,4 +69,4 @@ class FlowEstimatorBase(nn.Module):
     def forward(self, image1, image2, iters=12, flow_init=None):
         """Estimate optical flow between a pair of frames -> (B,2,H,W) fp32."""
         eng = self.engine(image1.device if image1.is_cuda else None)
-        return eng.forward(image1, image2, iters, flow_init)
+        return eng.forward(image1, image2, iters, flow_init, graph=self.use_cuda_graph)

@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--ofe", default="raft", choices=["raft", "gma"])
+    ap.add_argument("--precision", default=os.environ.get("ACCFLOW_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
+                    help="conv/GEMM arithmetic: bf16x3 = tcgen05 split products (fp32-class, parity-gated at 1e-3 px)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -162,6 +164,7 @@ def run_b200(args):
     model.load_state_dict(make_state_dict(kind, seed=2))
     model = model.to(dev).eval()
     model.iters = args.iters
+    model.ofe.precision = args.precision
     b = args.clips
     # clip-parallel sharding: rank r owns clips r*b .. r*b+b-1 of each step
     batch = make_inputs([rank * b + i for i in range(b)], args.size)
@@ -225,16 +228,21 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (implicit-GEMM convolution), measured live ----------
     eng = model.engine(dev)
+    model.ofe.use_cuda_graph = False           # per-launch events need the eager path
     prof = eng.k.profile = []
     step_resident()
     torch.cuda.synchronize()
     eng.k.profile = None
+    model.ofe.use_cuda_graph = True
     conv_ms = sum(a.elapsed_time(z) for a, z, _ in prof)
     conv_flop = sum(f for _, _, f in prof)
     pk, pk_kind = peaks()
     achieved = conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     peak = pk["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": "conv_f32_kernel (implicit-GEMM conv, exact-fp32 FFMA path)",
+    kname = {"fp32": "conv_f32_kernel (implicit-GEMM conv, exact-fp32 FFMA path)",
+             "bf16x3": "conv_tc_kernel (tcgen05 implicit-GEMM conv, bf16x3 split: 6 MMAs per algorithmic MAC)",
+             "bf16": "conv_tc_kernel (tcgen05 implicit-GEMM conv, bf16 products)"}[args.precision]
+    roofline = {"bound": "tensor", "kernel": kname, "issued_mma_tflops": achieved * (6 if args.precision == "bf16x3" else 1),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_kind": f"bf16 dense sustained, {pk_kind}", "launches": len(prof), "ms_in_step": conv_ms,
                 "share_of_step": conv_ms / (ms / args.steps), "traffic": None}
@@ -243,7 +251,8 @@ def run_b200(args):
     if rank == 0:
         line = {"metric": "long-range flow pairs/sec", "value": value, "unit": "flows/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "bf16x3": "bf16x3", "bf16": "bf16"}[args.precision], "data": "synthetic",
                 "config": workload_config(args, b), "clips_per_s": value / FLOWS_PER_CLIP,
                 "pair_evals_per_s": value / FLOWS_PER_CLIP * 11, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "flows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

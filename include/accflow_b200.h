@@ -84,6 +84,9 @@ ACCFLOW_API int accflow_abi_version(void);
 ACCFLOW_API int accflow_last_error(char* buf, size_t len);
 /* Number of kernels this library has launched since load / last reset (bench "gpu_launches"). */
 ACCFLOW_API long long accflow_launch_count(int reset);
+/* Account for kernels that run as part of a replayed CUDA graph (captured launches are counted
+ * once at capture; the host adds them again per replay). */
+ACCFLOW_API long long accflow_launch_count_add(long long n);
 
 /* Generic fp32 convolution (exact-fp32 arithmetic on the FFMA pipe). */
 ACCFLOW_API int accflow_conv2d_f32(const accflow_conv_desc* d, void* stream);

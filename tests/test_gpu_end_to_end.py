@@ -101,6 +101,53 @@ def test_clip_vs_oracle_and_epe():
         assert float((a - b).abs().max()) < EPE_TOL_PX
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_cuda_graph_replay_matches_eager_and_oracle(golden, precision):
+    """Third and later calls replay a captured CUDA graph; results must not change."""
+    g, _ = golden
+    m = build("acc+raft")
+    m.ofe.precision = precision
+    imgs = [t.cuda() for t in cases.clip_case()]
+    m.ofe.use_cuda_graph = False
+    eager = m(images=imgs)
+    m.ofe.use_cuda_graph = True
+    outs = [m(images=imgs) for _ in range(4)]            # 2 eager warm-ups, capture, replay
+    for o in outs:
+        for a, b in zip(o, eager):
+            assert maxdiff(a, b.cpu()) == 0.0
+    # replay with new inputs (static buffers are refreshed)
+    imgs2 = [t.flip(-1).contiguous() for t in imgs]
+    m.ofe.use_cuda_graph = False
+    eager2 = m(images=imgs2)
+    m.ofe.use_cuda_graph = True
+    rep2 = m(images=imgs2)
+    for a, b in zip(rep2, eager2):
+        assert maxdiff(a, b.cpu()) == 0.0
+    for i, f in enumerate(outs[-1]):
+        assert maxdiff(f, g[f"acc+raft.flow{i}"]) < FLOW_TOL_PX
+
+
+def test_exact_fp32_mode_matches_reference(golden):
+    g, _ = golden
+    m = build("raft")
+    m.precision = "fp32"
+    i1, i2, finit = cases.pair_case()
+    assert maxdiff(m(i1.cuda(), i2.cuda(), iters=12, flow_init=finit.cuda()), g["raft.flow_up"]) < 1e-4
+
+
+def test_bf16_mode_stated_tolerance(golden):
+    """bf16 products (the reference's autocast class): stated tolerance 0.6 px max-abs, 0.05 px mean EPE."""
+    g, _ = golden
+    for kind in ("raft", "gma"):
+        m = build(kind)
+        m.precision = "bf16"
+        i1, i2, finit = cases.pair_case()
+        out = m(i1.cuda(), i2.cuda(), iters=12, flow_init=finit.cuda())
+        ref = torch.as_tensor(g[f"{kind}.flow_up"])
+        assert maxdiff(out, ref) < 0.6
+        assert float((out.cpu() - ref).norm(dim=1).mean()) < 0.05
+
+
 def test_no_cpu_fallback():
     from accflow_b200.networks import build_flow_estimator
     m = build_flow_estimator("raft")
