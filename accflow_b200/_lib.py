@@ -60,7 +60,8 @@ SIGNATURES = {
     "accflow_instnorm_f32": [fp, i, i, i, f, i, fp, i, fp, fp, fp, fp],
     "accflow_nhwc_transpose_f32": [fp, i, i, i, i, fp, i, fp],
     "accflow_corr_pool_f32": [fp, ll, i, i, fp, fp, fp, fp],
-    "accflow_corr_lookup_f32": [fp, fp, fp, fp, i, i, i, i, fp, fp, i, fp, fp, i, fp],
+    "accflow_corr_lookup_f32": [fp, fp, fp, fp, i, i, i, i, fp, fp, i, fp, fp, i, fp, i, ll, i, fp],
+    "accflow_conv3x3_smallcout_f32": [fp, i, i, i, i, i, fp, fp, fp, i, i, fp, i, fp],
     "accflow_coords_init_f32": [fp, i, i, i, fp, fp],
     "accflow_axpy_f32": [fp, fp, f, ll, fp],
     "accflow_convex_upsample_f32": [fp, i, i, fp, i, i, i, i, fp, fp],

@@ -264,6 +264,60 @@ __global__ void __launch_bounds__(256) conv_smallc_kernel(const float* __restric
   }
 }
 
+// ---- 3x3 convolution with <= 4 output channels (flow heads 256->2, blending mask 256->1) -------
+// A GEMM tile would be >90 % padding; this is a bandwidth kernel instead: one warp per output
+// pixel, lanes stride over 4-channel groups of the 9 taps, weights (9*cin*4 floats) in shared
+// memory, warp-shuffle reduction, fused affine + activation.
+__global__ void __launch_bounds__(256) conv3x3_smallcout_kernel(const float* __restrict__ x, int x_ld, int batch, int h,
+                                                                int w, int cin, const float* __restrict__ wgt,
+                                                                const float* __restrict__ scale,
+                                                                const float* __restrict__ shift, int cout, int act,
+                                                                float* __restrict__ out, int out_ld, int pix_per_warp) {
+  extern __shared__ __align__(16) float ws[];  // [9][cin][4]
+  for (int i = threadIdx.x; i < 9 * cin; i += 256)
+    reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(wgt) + i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total = (long long)batch * h * w;
+  const long long first = ((long long)blockIdx.x * 8 + warp) * pix_per_warp;
+  const int c4n = cin >> 2;
+  for (int i = 0; i < pix_per_warp; ++i) {
+    const long long pix = first + i;
+    if (pix >= total) break;
+    const int hw = h * w;
+    const int b = (int)(pix / hw), pl = (int)(pix - (long long)b * hw);
+    const int py = pl / w, px = pl - py * w;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int iy = py + t / 3 - 1, ix = px + t % 3 - 1;
+      if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
+      const float4* src = reinterpret_cast<const float4*>(x + ((long long)(b * h + iy) * w + ix) * x_ld);
+      const float4* wt = reinterpret_cast<const float4*>(ws) + (long long)t * cin;
+      for (int c4 = lane; c4 < c4n; c4 += 32) {
+        const float4 v = __ldg(src + c4);
+        const float4 w0 = wt[4 * c4], w1 = wt[4 * c4 + 1], w2 = wt[4 * c4 + 2], w3 = wt[4 * c4 + 3];
+        a0 = fmaf(v.x, w0.x, a0); a1 = fmaf(v.x, w0.y, a1); a2 = fmaf(v.x, w0.z, a2); a3 = fmaf(v.x, w0.w, a3);
+        a0 = fmaf(v.y, w1.x, a0); a1 = fmaf(v.y, w1.y, a1); a2 = fmaf(v.y, w1.z, a2); a3 = fmaf(v.y, w1.w, a3);
+        a0 = fmaf(v.z, w2.x, a0); a1 = fmaf(v.z, w2.y, a1); a2 = fmaf(v.z, w2.z, a2); a3 = fmaf(v.z, w2.w, a3);
+        a0 = fmaf(v.w, w3.x, a0); a1 = fmaf(v.w, w3.y, a1); a2 = fmaf(v.w, w3.z, a2); a3 = fmaf(v.w, w3.w, a3);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    }
+    if (lane < cout) {
+      float v = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : a3;
+      v = fmaf(v, scale ? __ldg(scale + lane) : 1.f, shift ? __ldg(shift + lane) : 0.f);
+      out[pix * out_ld + lane] = act_apply(v, act);
+    }
+  }
+}
+
 template <int CIN, int KS, int STRIDE, int COUT, bool NCHW>
 static int launch_smallc(const float* in, int batch, int in_h, int in_w, const float* w, const float* scale,
                          const float* shift, int act, float* out, int out_ld, cudaStream_t st) {
@@ -340,4 +394,28 @@ extern "C" int accflow_conv_smallc_f32(const float* in, int in_is_nchw, int batc
     return launch_smallc<2, 7, 1, 128, false>(in, batch, in_h, in_w, weight, scale, shift, act, out, out_ld, st);
   return fail(-1, "conv_smallc: unsupported configuration cin=%d ks=%d stride=%d cout=%d nchw=%d", cin, ks, stride,
               cout, in_is_nchw);
+}
+
+extern "C" int accflow_conv3x3_smallcout_f32(const float* x, int x_ld, int batch, int h, int w, int cin,
+                                             const float* weight, const float* scale, const float* shift, int cout,
+                                             int act, float* out, int out_ld, void* stream) {
+  ACCFLOW_REQUIRE(x && weight && out && aligned16(x) && aligned16(weight), "conv3x3_smallcout: null/unaligned pointer");
+  ACCFLOW_REQUIRE(batch > 0 && h > 0 && w > 0 && cin % 4 == 0 && x_ld % 4 == 0 && x_ld >= cin && cout >= 1 && cout <= 4 &&
+                      out_ld >= cout, "conv3x3_smallcout: bad shape (cin %% 4 == 0, cout <= 4)");
+  const size_t smem = (size_t)9 * cin * 4 * sizeof(float);
+  ACCFLOW_REQUIRE(smem <= 160 * 1024, "conv3x3_smallcout: cin=%d too large", cin);
+  static thread_local int cfg_dev = -1;
+  static thread_local size_t cfg_smem = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > 48 * 1024 && (cfg_dev != dev || cfg_smem < smem)) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_smallcout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "conv3x3_smallcout: smem attribute: %s", cudaGetErrorString(e));
+    cfg_dev = dev; cfg_smem = smem;
+  }
+  const long long total = (long long)batch * h * w;
+  const int ppw = 16;
+  conv3x3_smallcout_kernel<<<cdiv(total, 8 * ppw), 256, smem, (cudaStream_t)stream>>>(
+      x, x_ld, batch, h, w, cin, weight, scale, shift, cout, act, out, out_ld, ppw);
+  return launched("conv3x3_smallcout");
 }

@@ -1,4 +1,6 @@
 // Gather / resample / normalisation kernels of the flow path (all HBM- or latency-bound).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace accflow {
@@ -8,32 +10,47 @@ constexpr int IN_CHUNK = 1024;  // pixels per partial-reduction block
 
 __global__ void __launch_bounds__(256) instnorm_partial_kernel(const float* __restrict__ x, int hw, int c,
                                                                float* __restrict__ partial, int chunks) {
-  __shared__ float red[2][256];
+  // thread -> one 4-channel group, strided over the chunk's pixels; 4 pixels in flight per thread
+  __shared__ float4 red[2][256];
   const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
-  const int groups = 256 / c;  // c <= 256
-  const int ch = tid % c, g = tid / c;
-  const float* xb = x + (long long)b * hw * c;
-  float s = 0.f, q = 0.f;
+  const int c4n = c >> 2;
+  const int groups = 256 / c4n;
+  const int c4 = tid % c4n, g = tid / c4n;
+  const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * hw * c);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
   if (g < groups) {
-    const float ref = __ldg(xb + ch);  // shift by the first pixel: avoids E[x^2]-E[x]^2 cancellation
+    const float4 ref = __ldg(xb + c4);  // shift by the first pixel: avoids E[x^2]-E[x]^2 cancellation
     const int p1 = min(hw, (chunk + 1) * IN_CHUNK);
-    for (int p = chunk * IN_CHUNK + g; p < p1; p += groups) {
-      float v = __ldg(xb + (long long)p * c + ch) - ref;
-      s += v;
-      q = fmaf(v, v, q);
+    int p = chunk * IN_CHUNK + g;
+    for (; p + 3 * groups < p1; p += 4 * groups) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(xb + (long long)(p + u * groups) * c4n + c4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float a0 = v[u].x - ref.x, a1 = v[u].y - ref.y, a2 = v[u].z - ref.z, a3 = v[u].w - ref.w;
+        s.x += a0; s.y += a1; s.z += a2; s.w += a3;
+        q.x = fmaf(a0, a0, q.x); q.y = fmaf(a1, a1, q.y); q.z = fmaf(a2, a2, q.z); q.w = fmaf(a3, a3, q.w);
+      }
+    }
+    for (; p < p1; p += groups) {
+      const float4 v = __ldg(xb + (long long)p * c4n + c4);
+      const float a0 = v.x - ref.x, a1 = v.y - ref.y, a2 = v.z - ref.z, a3 = v.w - ref.w;
+      s.x += a0; s.y += a1; s.z += a2; s.w += a3;
+      q.x = fmaf(a0, a0, q.x); q.y = fmaf(a1, a1, q.y); q.z = fmaf(a2, a2, q.z); q.w = fmaf(a3, a3, q.w);
     }
   }
   red[0][tid] = s;
   red[1][tid] = q;
   __syncthreads();
-  if (tid < c) {
+  if (tid < c4n) {
     for (int k = 1; k < groups; ++k) {
-      s += red[0][tid + k * c];
-      q += red[1][tid + k * c];
+      const float4 a = red[0][tid + k * c4n], d = red[1][tid + k * c4n];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      q.x += d.x; q.y += d.y; q.z += d.z; q.w += d.w;
     }
-    float* o = partial + (((long long)b * chunks + chunk) * c + tid) * 2;
-    o[0] = s;
-    o[1] = q;
+    float* o = partial + (((long long)b * chunks + chunk) * c + tid * 4) * 2;
+    o[0] = s.x; o[1] = q.x; o[2] = s.y; o[3] = q.y; o[4] = s.z; o[5] = q.z; o[6] = s.w; o[7] = q.w;
   }
 }
 
@@ -146,6 +163,7 @@ struct LookupP {
   const float* coords;
   float* out; int out_ld;
   float* flow_out; float* mf_tail; int mf_ld;
+  __nv_bfloat16* out_pl; int pl_pitch; long long pl_stride; int nplanes;
 };
 
 __device__ __forceinline__ float bilinear_zeros(const float* __restrict__ img, int H, int W, float x, float y) {
@@ -165,23 +183,71 @@ __device__ __forceinline__ float bilinear_zeros(const float* __restrict__ img, i
   return r;
 }
 
+// One warp per source pixel.  Per level the warp stages the (2r+3)^2 patch of the pixel's target
+// map around floor(coords / 2^l) in shared memory (rows are contiguous in HBM, zero outside the
+// map), then every lane interpolates its taps from the patch.  The per-tap coordinate arithmetic
+// is the reference's (normalise / un-normalise round trip per tap), only the four corner reads
+// move from HBM to shared memory.  Output channels of a level are written as one coalesced run;
+// optional bf16 planes of the output feed the tensor-core 1x1 conv that follows (convc1).
 __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupP p) {
-  const int k1 = 2 * p.radius + 1, k2 = k1 * k1, nch = 4 * k2;
-  const long long total = (long long)p.batch * p.h * p.w * nch;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= total) return;
-  const long long pix = idx / nch;
-  const int ch = (int)(idx - pix * nch);
-  const int lvl = ch / k2, t = ch - lvl * k2;
-  const int a = t / k1, bb = t - a * k1;
+  constexpr int MAXP = 19 * 19;                 // radius <= 8
+  __shared__ float patch[8][MAXP];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pix = (long long)blockIdx.x * 8 + wib;
+  if (pix >= (long long)p.batch * p.h * p.w) return;
+  const int r = p.radius, k1 = 2 * r + 1, k2 = k1 * k1, pd = k1 + 2;
   const float cx = __ldg(p.coords + pix * 2), cy = __ldg(p.coords + pix * 2 + 1);
-  const float inv = 1.f / (float)(1 << lvl);  // exact power of two
-  const float x = __fadd_rn(cx * inv, (float)(a - p.radius));
-  const float y = __fadd_rn(cy * inv, (float)(bb - p.radius));
-  const int H = p.lh[lvl], W = p.lw[lvl];
-  const float* img = p.lvl[lvl] + pix * (long long)(H * W);
-  p.out[pix * p.out_ld + ch] = bilinear_zeros(img, H, W, grid_roundtrip(x, W), grid_roundtrip(y, H));
-  if (ch == 0) {
+  float* pt = patch[wib];
+  float* orow = p.out + pix * p.out_ld;
+  for (int lvl = 0; lvl < 4; ++lvl) {
+    const int H = p.lh[lvl], W = p.lw[lvl];
+    const float inv = 1.f / (float)(1 << lvl);
+    const float bx = cx * inv, by = cy * inv;
+    // patch origin: one texel of slack on each side of the nominal window
+    const float fxo = floorf(fminf(fmaxf(bx, -1.0e6f), 1.0e6f)), fyo = floorf(fminf(fmaxf(by, -1.0e6f), 1.0e6f));
+    const int x0 = (int)fxo - r - 1, y0 = (int)fyo - r - 1;
+    const float* img = p.lvl[lvl] + pix * (long long)(H * W);
+    __syncwarp();
+    for (int i = lane; i < pd * pd; i += 32) {
+      const int yy = i / pd, xx = i - yy * pd;
+      const int gx = x0 + xx, gy = y0 + yy;
+      pt[i] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? __ldg(img + gy * W + gx) : 0.f;
+    }
+    __syncwarp();
+    for (int t = lane; t < k2; t += 32) {
+      const int a = t / k1, bb = t - a * k1;
+      const float x = grid_roundtrip(__fadd_rn(bx, (float)(a - r)), W);
+      const float y = grid_roundtrip(__fadd_rn(by, (float)(bb - r)), H);
+      float v = 0.f;
+      if (x > -2.f && x < (float)W + 1.f && y > -2.f && y < (float)H + 1.f) {
+        const float xf = floorf(x), yf = floorf(y);
+        const int xi = (int)xf - x0, yi = (int)yf - y0;       // position inside the patch
+        const float wx1 = x - xf, wy1 = y - yf, wx0 = (xf + 1.f) - x, wy0 = (yf + 1.f) - y;
+        if (xi >= 0 && xi + 1 < pd && yi >= 0 && yi + 1 < pd) {
+          const float* q = pt + yi * pd + xi;
+          v = q[0] * (wx0 * wy0);
+          v += q[1] * (wx1 * wy0);
+          v += q[pd] * (wx0 * wy1);
+          v += q[pd + 1] * (wx1 * wy1);
+        } else {
+          v = bilinear_zeros(img, H, W, x, y);                 // never taken for finite coords; kept for safety
+        }
+      }
+      orow[lvl * k2 + t] = v;
+      if (p.out_pl) {
+        __nv_bfloat16* po = p.out_pl + pix * p.pl_pitch + lvl * k2 + t;
+        const __nv_bfloat16 p0 = __float2bfloat16_rn(v);
+        po[0] = p0;
+        if (p.nplanes > 1) {
+          const float r1 = v - __bfloat162float(p0);
+          const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+          po[p.pl_stride] = p1;
+          po[2 * p.pl_stride] = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+        }
+      }
+    }
+  }
+  if (lane == 0) {
     const int pl = (int)(pix % ((long long)p.h * p.w));
     const float fx = cx - (float)(pl % p.w), fy = cy - (float)(pl / p.w);
     if (p.flow_out) { p.flow_out[pix * 2] = fx; p.flow_out[pix * 2 + 1] = fy; }
@@ -490,7 +556,8 @@ extern "C" int accflow_corr_pool_f32(const float* lvl0, long long n_rows, int h,
 
 extern "C" int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                        int batch, int h, int w, int radius, const float* coords, float* out,
-                                       int out_ld, float* flow_out, float* mf_tail, int mf_ld, void* stream) {
+                                       int out_ld, float* flow_out, float* mf_tail, int mf_ld, void* out_planes,
+                                       int pl_pitch, long long pl_stride, int nplanes, void* stream) {
   ACCFLOW_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && coords && out, "corr_lookup: null pointer");
   ACCFLOW_REQUIRE(batch > 0 && h >= 8 && w >= 8 && radius >= 0 && radius <= 8, "corr_lookup: bad shape");
   const int nch = 4 * (2 * radius + 1) * (2 * radius + 1);
@@ -501,8 +568,9 @@ extern "C" int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, con
   for (int l = 0; l < 4; ++l) { p.lh[l] = hh; p.lw[l] = ww; hh >>= 1; ww >>= 1; }
   p.batch = batch; p.h = h; p.w = w; p.radius = radius; p.coords = coords;
   p.out = out; p.out_ld = out_ld; p.flow_out = flow_out; p.mf_tail = mf_tail; p.mf_ld = mf_ld;
-  const long long total = (long long)batch * h * w * nch;
-  corr_lookup_kernel<<<cdiv(total, 256), 256, 0, ST>>>(p);
+  ACCFLOW_REQUIRE(!out_planes || (nplanes == 1 || nplanes == 3), "corr_lookup: nplanes must be 1 or 3");
+  p.out_pl = reinterpret_cast<__nv_bfloat16*>(out_planes); p.pl_pitch = pl_pitch; p.pl_stride = pl_stride; p.nplanes = nplanes;
+  corr_lookup_kernel<<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(p);
   return launched("corr_lookup");
 }
 

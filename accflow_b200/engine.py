@@ -290,6 +290,27 @@ class Kernels:
                act, out.ptr, out.ld, _stream())
         self.wrote(out)
 
+    def conv_smallcout(self, pc: PackedConv, x: View, out: View, act=L.ACT_NONE):
+        """3x3 conv with <= 4 output channels on the bandwidth kernel (always fp32 arithmetic)."""
+        assert pc.kh == 3 and pc.kw == 3 and pc.stride == 1 and pc.cout <= 4 and pc.cout_pad == 4 and x.c == pc.cin
+        L.call("accflow_conv3x3_smallcout_f32", x.ptr, x.ld, x.b, x.h, x.w, x.c, pc.w.data_ptr(),
+               None if pc.scale is None else pc.scale.data_ptr(), pc.shift.data_ptr(), pc.cout, act, out.ptr, out.ld,
+               _stream())
+        self.wrote(out)
+
+    def corr_lookup(self, lv, radius: int, coords: torch.Tensor, out: View, flow: torch.Tensor, mf_tail: View):
+        """CorrBlock.__call__ for all four levels; also emits flow = coords - grid."""
+        got = self.planes_ptr(out, create=False) if self.tc else None
+        pl_ptr, pl_pitch, pl_stride = got if got is not None else (None, 0, 0)
+        L.call("accflow_corr_lookup_f32", lv[0].data_ptr(), lv[1].data_ptr(), lv[2].data_ptr(), lv[3].data_ptr(),
+               out.b, out.h, out.w, radius, coords.data_ptr(), out.ptr, out.ld, flow.data_ptr(), mf_tail.ptr, mf_tail.ld,
+               pl_ptr, pl_pitch, pl_stride, self.nplanes, _stream())
+        if got is not None:
+            self._fresh(out)
+        else:
+            self.wrote(out)
+        self.wrote(mf_tail)
+
     def instnorm(self, x: View, relu: bool, residual: Optional[View], post_relu: bool, out: View, eps=1e-5):
         assert x.c == x.ld and out.c == out.ld
         hw = x.h * x.w
@@ -528,24 +549,37 @@ class FlowEstimatorEngine:
             self.qk_scale = 128 ** -0.5
 
     # ------------------------------------------------------------------------------------
-    def features(self, image1: torch.Tensor, image2: torch.Tensor, tag="fe"):
-        """fnet on both images + correlation pyramid + cnet (+ GMA attention)."""
+    def run_fnet(self, images: Sequence[torch.Tensor], tag: str) -> View:
+        """Feature encoder (InstanceNorm) on a list of (n_i,3,H,W) images -> [sum n_i, h, w, 256]."""
+        return self.fnet.run(self.k, images, tag + ".fnet")
+
+    def run_cnet(self, images: Sequence[torch.Tensor], tag: str):
+        """Context encoder (eval BatchNorm) -> (tanh(net), relu(inp)), each [N, h, w, 128] (raft.py:115-119)."""
         k = self.k
-        B, _, H, W = image1.shape
-        assert H % 8 == 0 and W % 8 == 0 and H >= 128 and W >= 128, "H, W must be multiples of 8 and >= 128"
-        h, w = H // 8, W // 8
-        P = h * w
-        fm = self.fnet.run(k, [image1, image2], tag + ".fnet")
-        st = dict(B=B, h=h, w=w, P=P, H=H, W=W)
-        st["pyr"] = self.corr_pyramid(fm.rows(0, B), fm.rows(B, 2 * B), tag)
-        hid = k.view(tag + ".h", B, h, w, 128)
-        inp = k.view(tag + ".inp", B, h, w, 128)
-        self.cnet.run(k, [image1], tag + ".cnet", head_kwargs=dict(out=hid, out2=inp, act=L.ACT_TANH, act_split=128,
-                                                                   act2=L.ACT_RELU))
-        st["hid"], st["inp"] = hid, inp
+        n = sum(int(im.shape[0]) for im in images)
+        h, w = int(images[0].shape[-2]) // 8, int(images[0].shape[-1]) // 8
+        hid = k.view(tag + ".h", n, h, w, 128)
+        inp = k.view(tag + ".inp", n, h, w, 128)
+        self.cnet.run(k, images, tag + ".cnet", head_kwargs=dict(out=hid, out2=inp, act=L.ACT_TANH, act_split=128,
+                                                                 act2=L.ACT_RELU))
+        return hid, inp
+
+    def prepare(self, f1: View, f2: View, hid: View, inp: View, H: int, W: int, tag: str):
+        """Correlation pyramid (+ GMA attention) for a batch of pairs whose features are given."""
+        B, h, w = f1.b, f1.h, f1.w
+        st = dict(B=B, h=h, w=w, P=h * w, H=H, W=W, hid=hid, inp=inp)
+        st["pyr"] = self.corr_pyramid(f1, f2, tag)
         if self.gma:
             st["attn"] = self.attention(inp, tag)
         return st
+
+    def features(self, image1: torch.Tensor, image2: torch.Tensor, tag="fe"):
+        """fnet on both images + correlation pyramid + cnet (+ GMA attention)."""
+        B, _, H, W = image1.shape
+        assert H % 8 == 0 and W % 8 == 0 and H >= 128 and W >= 128, "H, W must be multiples of 8 and >= 128"
+        fm = self.run_fnet([image1, image2], tag)
+        hid, inp = self.run_cnet([image1], tag)
+        return self.prepare(fm.rows(0, B), fm.rows(B, 2 * B), hid, inp, H, W, tag)
 
     def corr_pyramid(self, f1: View, f2: View, tag: str):
         """CorrBlock.__init__ (raft/corr.py:8-22)."""
@@ -603,11 +637,7 @@ class FlowEstimatorEngine:
         L.call("accflow_coords_init_f32", None if flow_init is None else flow_init.data_ptr(), B, h, w,
                coords.data_ptr(), s())
         for _ in range(iters):
-            L.call("accflow_corr_lookup_f32", lv[0].data_ptr(), lv[1].data_ptr(), lv[2].data_ptr(), lv[3].data_ptr(),
-                   B, h, w, self.RADIUS, coords.data_ptr(), corr.ptr, corr.ld, flow.data_ptr(), mf.ch(126, 128).ptr,
-                   mf.ld, s())
-            k.wrote(corr)
-            k.wrote(mf.ch(126, 128))
+            k.corr_lookup(lv, self.RADIUS, coords, corr, flow, mf.ch(126, 128))
             k.conv(self.convc1, [corr], cor1, act=L.ACT_RELU)
             k.conv(self.convc2, [cor1], cf.ch(0, 192), act=L.ACT_RELU)
             k.conv_smallc(flow.data_ptr(), False, B, 2, h, w, self.convf1, L.ACT_RELU, flo1)
@@ -621,7 +651,7 @@ class FlowEstimatorEngine:
                 k.conv(zr, [hid] + x_srcs, epilogue=L.EPI_GRU_ZR, h=hid, z=z, out2=rh)
                 k.conv(q, [rh] + x_srcs, epilogue=L.EPI_GRU_Q, h=hid, z=z)
             k.conv(self.fh1, [hid], fh, act=L.ACT_RELU)
-            k.conv(self.fh2, [fh], delta)
+            k.conv_smallcout(self.fh2, fh, delta)
             L.call("accflow_axpy_f32", coords.data_ptr(), delta.ptr, 1.0, B * P * 2, s())
         # mask head + convex upsample: only the last iteration's is observable (raft.py:139-146)
         k.conv(self.mk1, [hid], fh, act=L.ACT_RELU)
@@ -699,20 +729,27 @@ class AccFlowEngine:
 
     def iter(self, I1, I2, In, F2n: Optional[torch.Tensor], iters=12):
         """Returns (out_small NCHW (b,2,h,w), out NCHW (b,2,H,W)); F2n is NCHW (b,2,h,w) or None."""
-        k, s = self.k, _stream
         dev = self.device
         I1, I2, In = (t.to(device=dev, dtype=F32).contiguous() for t in (I1, I2, In))
-        b, _, H, W = I1.shape
-        assert H % 8 == 0 and W % 8 == 0
-        h, w = H // 8, W // 8
-        P = h * w
+        b = I1.shape[0]
         with torch.cuda.device(dev):
             if F2n is None:
                 flows = self.ofe.forward(torch.cat([I1, I1, I2]), torch.cat([I2, In, In]), iters, tag="ofe3")
-                npair = 3
             else:
                 flows = self.ofe.forward(torch.cat([I1, I1]), torch.cat([I2, In]), iters, tag="ofe2")
-                npair = 2
+            ctx = self.context.run(self.k, [I1, I2, In], "acc.ctx")
+            return self._accumulate(flows, b, ctx.rows(0, b), ctx.rows(b, 2 * b), ctx.rows(2 * b, 3 * b), F2n)
+
+    def _accumulate(self, flows: torch.Tensor, b: int, c1: View, c2: View, cn: View, F2n: Optional[torch.Tensor]):
+        """Everything of AccFlow.iter after the ofe call (AccFlow_.py:185-201), given the context features."""
+        k, s = self.k, _stream
+        dev = self.device
+        H, W = int(flows.shape[-2]), int(flows.shape[-1])
+        assert H % 8 == 0 and W % 8 == 0
+        h, w = H // 8, W // 8
+        P = h * w
+        npair = int(flows.shape[0]) // b
+        if True:
             lr = k.buf("acc.lr", npair * b, P, 2)                       # [dflow | flow_ini | (F2n)]
             L.call("accflow_downflow8_f32", flows.data_ptr(), npair * b, H, W, lr.data_ptr(), s())
             fin = k.buf("acc.fin", 3 * b, P, 2)                          # encoder order: flow_ini, dflow, F2n
@@ -731,9 +768,6 @@ class AccFlowEngine:
             k.conv(self.fe2, [e1], e2, act=L.ACT_RELU)
             k.conv(self.fe3, [e2], enc)
             f_ini, df, f = enc.rows(0, b), enc.rows(b, 2 * b), enc.rows(2 * b, 3 * b)
-            # context encoder (AccFlow_.py:193)
-            ctx = self.context.run(k, [I1, I2, In], "acc.ctx")
-            c1, c2, cn = ctx.rows(0, b), ctx.rows(b, 2 * b), ctx.rows(2 * b, 3 * b)
             # occlusion + error maps (getOcc, AccFlow_.py:127-135,194,197)
             occ = k.view("acc.occ", b, h, w, 1)
             emap = k.view("acc.emap", b, h, w, 128)
@@ -768,14 +802,14 @@ class AccFlowEngine:
             # Blending (AccFlow_.py:122-124)
             m = k.view("acc.m", b, h, w, 1)
             k.conv(self.bl0, [emap], t256, act=L.ACT_RELU)
-            k.conv(self.bl2, [t256], m, act=L.ACT_SIGMOID)
+            k.conv_smallcout(self.bl2, t256, m, act=L.ACT_SIGMOID)
             fuse = k.view("acc.fuse", b, h, w, 128)
             L.call("accflow_blend_f32", f_ini.ptr, f_acc.ptr, m.ptr, 1, b * P, 128, fuse.ptr, s())
             k.wrote(fuse)
             # FlowDecoder (AccFlow_.py:40-45)
             small = torch.empty(b, h, w, 2, device=dev, dtype=F32)
             k.conv(self.df0, [fuse], t256, act=L.ACT_RELU)
-            k.conv(self.df2, [t256], View(small))
+            k.conv_smallcout(self.df2, t256, View(small))
             mask = k.view("acc.mask", b, h, w, 576)
             k.conv(self.dm0, [fuse], t256, act=L.ACT_RELU)
             k.conv(self.dm2, [t256], mask)
@@ -784,18 +818,48 @@ class AccFlowEngine:
         return small.permute(0, 3, 1, 2).contiguous(), out
 
     def forward(self, images: List[torch.Tensor], iters=12, graph=False) -> List[torch.Tensor]:
+        """AccFlow.forward (AccFlow_.py:157-175) with every encoder evaluated once per distinct frame.
+
+        The reference re-runs fnet / cnet / context on the same frames at every accumulation step
+        (22 / 11 / 15 image passes per 7-frame clip for 7 / 6 / 7 distinct frames, SURVEY.md §3.2);
+        all three encoders are per-sample functions, so the cached features are identical.
+        """
         images = [t.to(device=self.device, dtype=F32).contiguous() for t in images]
 
         def eager(*imgs):
-            flow = None
-            outs = []
-            for i in range(2, len(imgs)):
-                flow, up = self.iter(imgs[i], imgs[i - 1], imgs[0], flow, iters)
+            k, ofe = self.k, self.ofe
+            n, b = len(imgs), int(imgs[0].shape[0])
+            H, W = int(imgs[0].shape[-2]), int(imgs[0].shape[-1])
+            assert H % 8 == 0 and W % 8 == 0 and H >= 128 and W >= 128, "H, W must be multiples of 8 and >= 128"
+            fm = ofe.run_fnet(list(imgs), "clip")                    # frame f -> rows [f*b, (f+1)*b)
+            hid_all, inp_all = ofe.run_cnet(list(imgs[1:]), "clip")  # frame f (>=1) -> rows [(f-1)*b, f*b)
+            ctx = self.context.run(k, list(imgs), "clip.ctx")
+            h, w = fm.h, fm.w
+
+            def gather(src: View, frames, name):
+                dst = k.view(name, len(frames) * b, h, w, src.c)
+                for j, f in enumerate(frames):
+                    dst.t[j * b:(j + 1) * b].copy_(src.t[f * b:(f + 1) * b])
+                k.wrote(dst)
+                return dst
+
+            flow, outs = None, []
+            for i in range(2, n):
+                pairs = [(i, i - 1), (i, 0), (i - 1, 0)] if flow is None else [(i, i - 1), (i, 0)]
+                tag = f"ofe{len(pairs)}"
+                f1 = gather(fm, [p[0] for p in pairs], tag + ".f1")
+                f2 = gather(fm, [p[1] for p in pairs], tag + ".f2")
+                hid = gather(hid_all, [p[0] - 1 for p in pairs], tag + ".hid")
+                inp = gather(inp_all, [p[0] - 1 for p in pairs], tag + ".inpg")
+                st = ofe.prepare(f1, f2, hid, inp, H, W, tag)
+                flows = ofe.iterate(st, iters, None, tag)
+                flow, up = self._accumulate(flows, b, ctx.rows(i * b, (i + 1) * b), ctx.rows((i - 1) * b, i * b),
+                                            ctx.rows(0, b), flow)
                 outs.append(up)
             return outs
 
-        if not graph:
-            return eager(*images)
         with torch.cuda.device(self.device):
+            if not graph:
+                return eager(*images)
             key = (tuple(images[0].shape), len(images), iters)
             return self.graphs.run(key, images, eager)

@@ -137,6 +137,13 @@ ACCFLOW_API int accflow_conv_smallc_f32(const float* in, int in_is_nchw, int bat
                             const float* weight, const float* scale, const float* shift, int ks,
                             int stride, int cout, int act, float* out, int out_ld, void* stream);
 
+/* 3x3 / stride 1 / pad 1 convolution with cout <= 4 (FlowHead.conv2 raft/update.py:10,
+ * FlowDecoder.flow[2] AccFlow_.py:19, Blending.mask[2] AccFlow_.py:118), fused affine + activation.
+ * weight: packed [9][cin][4] fp32 (the accflow_conv2d_f32 layout with cout_pad = 4). */
+ACCFLOW_API int accflow_conv3x3_smallcout_f32(const float* x, int x_ld, int batch, int h, int w, int cin,
+                                              const float* weight, const float* scale, const float* shift, int cout,
+                                              int act, float* out, int out_ld, void* stream);
+
 /* InstanceNorm2d(affine=False, eps) [+ReLU] [+residual, +ReLU] on NHWC, two-phase
  * (raft/extractor.py:35-38,54-63,150-151,210).  partial: workspace >= batch*chunks*c*2 floats
  * where chunks = accflow_instnorm_chunks(h*w); stats: >= batch*c*2 floats. */
@@ -162,7 +169,9 @@ ACCFLOW_API int accflow_corr_pool_f32(const float* lvl0, long long n_rows, int h
  * is non-NULL, into channels [0,2) of that slice (the cat([out, flow]) of update.py:97). */
 ACCFLOW_API int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                             int batch, int h, int w, int radius, const float* coords, float* out,
-                            int out_ld, float* flow_out, float* mf_tail, int mf_ld, void* stream);
+                            int out_ld, float* flow_out, float* mf_tail, int mf_ld,
+                            void* out_planes /* optional bf16 planes of `out` */, int pl_pitch,
+                            long long pl_plane_stride, int nplanes, void* stream);
 
 /* coords1 = grid + flow_init (raft/raft.py:121-124); flow_init NULL -> zeros.  NCHW (B,2,h,w) in. */
 ACCFLOW_API int accflow_coords_init_f32(const float* flow_init_nchw, int batch, int h, int w, float* coords, void* stream);

@@ -190,7 +190,7 @@ def test_corr_pyramid_and_lookup(KP, golden):
     flow = torch.empty(B, h * w, 2, device="cuda")
     c = dev(coords.permute(0, 2, 3, 1).reshape(B, h * w, 2).contiguous())
     L.call("accflow_corr_lookup_f32", lv[0].data_ptr(), lv[1].data_ptr(), lv[2].data_ptr(), lv[3].data_ptr(), B, h, w, 4,
-           c.data_ptr(), out.data_ptr(), 324, flow.data_ptr(), None, 0, None)
+           c.data_ptr(), out.data_ptr(), 324, flow.data_ptr(), None, 0, None, 0, 0, 1, None)
     torch.cuda.synchronize()
     assert maxdiff(out.permute(0, 3, 1, 2), g["corr.lookup"]) < tol
     from oracle import ops
@@ -236,6 +236,22 @@ def test_deform_conv(K, golden):
     K.conv(pc, [View(col.view(n, h, w, 9 * c))], View(out))
     torch.cuda.synchronize()
     assert maxdiff(out.permute(0, 3, 1, 2), g["dcn.out"]) < 2e-5
+
+
+def test_conv3x3_smallcout(K):
+    """Flow-head style 3x3 conv with 2 / 1 output channels on the bandwidth kernel."""
+    from accflow_b200 import _lib as L
+    from accflow_b200.engine import PackedConv, View
+    g = torch.Generator().manual_seed(9)
+    for cout, act, tact in ((2, L.ACT_NONE, lambda t: t), (1, L.ACT_SIGMOID, torch.sigmoid)):
+        x = torch.randn(2, 256, 13, 11, generator=g)
+        w = torch.randn(cout, 256, 3, 3, generator=g) * 0.03
+        b = torch.randn(cout, generator=g)
+        ref = tact(F.conv2d(x, w, b, padding=1))
+        out = torch.empty(2, 13, 11, cout, device="cuda")
+        K.conv_smallcout(PackedConv([dev(w)], [dev(b)], 1, (1, 1)), View(dev(nhwc(x))), View(out), act=act)
+        torch.cuda.synchronize()
+        assert maxdiff(out.permute(0, 3, 1, 2), ref) < 1e-5
 
 
 def test_softmax_and_transpose(K):
