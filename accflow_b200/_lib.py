@@ -55,12 +55,12 @@ SIGNATURES = {
     "accflow_conv2d_f32": [C.POINTER(ConvDesc), fp],
     "accflow_conv2d_tc": [C.POINTER(ConvDesc), C.POINTER(TcIO), C.POINTER(TcWeights), i, fp],
     "accflow_split_bf16_planes": [fp, ll, i, i, i, i, ll, i, fp, fp],
-    "accflow_conv_smallc_f32": [fp, i, i, i, i, i, fp, fp, fp, i, i, i, i, fp, i, fp],
+    "accflow_conv_smallc_f32": [fp, i, i, i, i, i, fp, fp, fp, i, i, i, i, fp, i, fp, i, ll, i, fp],
     "accflow_instnorm_chunks": [i],
     "accflow_instnorm_f32": [fp, i, i, i, f, i, fp, i, fp, fp, fp, fp],
     "accflow_nhwc_transpose_f32": [fp, i, i, i, i, fp, i, fp],
     "accflow_corr_pool_f32": [fp, ll, i, i, fp, fp, fp, fp],
-    "accflow_corr_lookup_f32": [fp, fp, fp, fp, i, i, i, i, fp, fp, i, fp, fp, i, fp, i, ll, i, fp],
+    "accflow_corr_lookup_f32": [fp, fp, fp, fp, i, i, i, i, fp, fp, i, fp, fp, i, fp, i, ll, fp, i, ll, i, fp],
     "accflow_conv3x3_smallcout_f32": [fp, i, i, i, i, i, fp, fp, fp, i, i, fp, i, fp],
     "accflow_coords_init_f32": [fp, i, i, i, fp, fp],
     "accflow_axpy_f32": [fp, fp, f, ll, fp],

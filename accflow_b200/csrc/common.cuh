@@ -1,5 +1,6 @@
 // Shared helpers for the accflow_b200 kernels (sm_100a).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
@@ -62,6 +63,18 @@ __device__ __forceinline__ float grid_roundtrip(float x, int size) {
   float s = (float)(size - 1);
   float xn = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, x), s), 1.f);
   return __fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.f), 2.f), s);
+}
+
+// bf16 planes (x = p0 + p1 + p2) written next to an fp32 value for the tensor-core convolutions.
+__device__ __forceinline__ void store_planes(__nv_bfloat16* dst, long long plane_stride, int nplanes, float v) {
+  const __nv_bfloat16 p0 = __float2bfloat16_rn(v);
+  dst[0] = p0;
+  if (nplanes > 1) {
+    const float r1 = v - __bfloat162float(p0);
+    const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+    dst[plane_stride] = p1;
+    dst[2 * plane_stride] = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+  }
 }
 
 }  // namespace accflow

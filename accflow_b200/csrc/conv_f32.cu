@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(256) conv_smallc_kernel(const float* __restric
                                                           const float* __restrict__ scale,
                                                           const float* __restrict__ shift, int act,
                                                           float* __restrict__ out, int out_ld, int out_h,
-                                                          int out_w) {
+                                                          int out_w, __nv_bfloat16* __restrict__ out_pl, int pl_pitch,
+                                                          long long pl_stride, int nplanes) {
   constexpr int TILE = 8, PATCH = (TILE - 1) * STRIDE + KS, K = CIN * KS * KS, CG = COUT / 4, PAD = KS / 2;
   extern __shared__ __align__(16) float sm[];
   float* Ws = sm;                   // [K][COUT]
@@ -260,7 +261,9 @@ __global__ void __launch_bounds__(256) conv_smallc_kernel(const float* __restric
     int n = g * CG + j;
     float v = acc[j];
     v = fmaf(v, scale ? __ldg(scale + n) : 1.f, shift ? __ldg(shift + n) : 0.f);
-    op[j] = act_apply(v, act);
+    v = act_apply(v, act);
+    op[j] = v;
+    if (out_pl) store_planes(out_pl + ((long long)(b * out_h + oy) * out_w + ox) * pl_pitch + n, pl_stride, nplanes, v);
   }
 }
 
@@ -268,39 +271,48 @@ __global__ void __launch_bounds__(256) conv_smallc_kernel(const float* __restric
 // A GEMM tile would be >90 % padding; this is a bandwidth kernel instead: one warp per output
 // pixel, lanes stride over 4-channel groups of the 9 taps, weights (9*cin*4 floats) in shared
 // memory, warp-shuffle reduction, fused affine + activation.
+template <int CPL>  // float4 groups per lane per tap = cin / 128
 __global__ void __launch_bounds__(256) conv3x3_smallcout_kernel(const float* __restrict__ x, int x_ld, int batch, int h,
-                                                                int w, int cin, const float* __restrict__ wgt,
+                                                                int w, const float* __restrict__ wgt,
                                                                 const float* __restrict__ scale,
                                                                 const float* __restrict__ shift, int cout, int act,
                                                                 float* __restrict__ out, int out_ld, int pix_per_warp) {
+  constexpr int CIN = CPL * 128;
   extern __shared__ __align__(16) float ws[];  // [9][cin][4]
-  for (int i = threadIdx.x; i < 9 * cin; i += 256)
+  for (int i = threadIdx.x; i < 9 * CIN; i += 256)
     reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(wgt) + i);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)batch * h * w;
   const long long first = ((long long)blockIdx.x * 8 + warp) * pix_per_warp;
-  const int c4n = cin >> 2;
+  const int hw = h * w;
   for (int i = 0; i < pix_per_warp; ++i) {
     const long long pix = first + i;
     if (pix >= total) break;
-    const int hw = h * w;
     const int b = (int)(pix / hw), pl = (int)(pix - (long long)b * hw);
     const int py = pl / w, px = pl - py * w;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float4 v[9][CPL];                     // all taps in flight before the first FMA
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int iy = py + t / 3 - 1, ix = px + t % 3 - 1;
-      if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
-      const float4* src = reinterpret_cast<const float4*>(x + ((long long)(b * h + iy) * w + ix) * x_ld);
-      const float4* wt = reinterpret_cast<const float4*>(ws) + (long long)t * cin;
-      for (int c4 = lane; c4 < c4n; c4 += 32) {
-        const float4 v = __ldg(src + c4);
-        const float4 w0 = wt[4 * c4], w1 = wt[4 * c4 + 1], w2 = wt[4 * c4 + 2], w3 = wt[4 * c4 + 3];
-        a0 = fmaf(v.x, w0.x, a0); a1 = fmaf(v.x, w0.y, a1); a2 = fmaf(v.x, w0.z, a2); a3 = fmaf(v.x, w0.w, a3);
-        a0 = fmaf(v.y, w1.x, a0); a1 = fmaf(v.y, w1.y, a1); a2 = fmaf(v.y, w1.z, a2); a3 = fmaf(v.y, w1.w, a3);
-        a0 = fmaf(v.z, w2.x, a0); a1 = fmaf(v.z, w2.y, a1); a2 = fmaf(v.z, w2.z, a2); a3 = fmaf(v.z, w2.w, a3);
-        a0 = fmaf(v.w, w3.x, a0); a1 = fmaf(v.w, w3.y, a1); a2 = fmaf(v.w, w3.z, a2); a3 = fmaf(v.w, w3.w, a3);
+      const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < w;
+      const float4* src = reinterpret_cast<const float4*>(x + ((long long)(b * h + (ok ? iy : py)) * w + (ok ? ix : px)) * x_ld);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[t][j] = ok ? __ldg(src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4* wt = reinterpret_cast<const float4*>(ws) + t * CIN;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int c = 4 * (lane + 32 * j);
+        const float4 w0 = wt[c], w1 = wt[c + 1], w2 = wt[c + 2], w3 = wt[c + 3];
+        const float4 q = v[t][j];
+        a0 = fmaf(q.x, w0.x, a0); a1 = fmaf(q.x, w0.y, a1); a2 = fmaf(q.x, w0.z, a2); a3 = fmaf(q.x, w0.w, a3);
+        a0 = fmaf(q.y, w1.x, a0); a1 = fmaf(q.y, w1.y, a1); a2 = fmaf(q.y, w1.z, a2); a3 = fmaf(q.y, w1.w, a3);
+        a0 = fmaf(q.z, w2.x, a0); a1 = fmaf(q.z, w2.y, a1); a2 = fmaf(q.z, w2.z, a2); a3 = fmaf(q.z, w2.w, a3);
+        a0 = fmaf(q.w, w3.x, a0); a1 = fmaf(q.w, w3.y, a1); a2 = fmaf(q.w, w3.z, a2); a3 = fmaf(q.w, w3.w, a3);
       }
     }
 #pragma unroll
@@ -311,16 +323,17 @@ __global__ void __launch_bounds__(256) conv3x3_smallcout_kernel(const float* __r
       a3 += __shfl_xor_sync(0xffffffffu, a3, o);
     }
     if (lane < cout) {
-      float v = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : a3;
-      v = fmaf(v, scale ? __ldg(scale + lane) : 1.f, shift ? __ldg(shift + lane) : 0.f);
-      out[pix * out_ld + lane] = act_apply(v, act);
+      float r = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : a3;
+      r = fmaf(r, scale ? __ldg(scale + lane) : 1.f, shift ? __ldg(shift + lane) : 0.f);
+      out[pix * out_ld + lane] = act_apply(r, act);
     }
   }
 }
 
 template <int CIN, int KS, int STRIDE, int COUT, bool NCHW>
 static int launch_smallc(const float* in, int batch, int in_h, int in_w, const float* w, const float* scale,
-                         const float* shift, int act, float* out, int out_ld, cudaStream_t st) {
+                         const float* shift, int act, float* out, int out_ld, void* out_pl, int pl_pitch,
+                         long long pl_stride, int nplanes, cudaStream_t st) {
   constexpr int TILE = 8, PATCH = (TILE - 1) * STRIDE + KS, K = CIN * KS * KS, PAD = KS / 2;
   const int out_h = (in_h + 2 * PAD - KS) / STRIDE + 1, out_w = (in_w + 2 * PAD - KS) / STRIDE + 1;
   const size_t smem = (size_t)(K * COUT + CIN * PATCH * (PATCH + 1)) * sizeof(float);
@@ -334,7 +347,8 @@ static int launch_smallc(const float* in, int batch, int in_h, int in_w, const f
     configured_dev = dev;
   }
   dim3 grid(cdiv(out_w, TILE), cdiv(out_h, TILE), batch);
-  kern<<<grid, 256, smem, st>>>(in, in_h, in_w, w, scale, shift, act, out, out_ld, out_h, out_w);
+  kern<<<grid, 256, smem, st>>>(in, in_h, in_w, w, scale, shift, act, out, out_ld, out_h, out_w,
+                                reinterpret_cast<__nv_bfloat16*>(out_pl), pl_pitch, pl_stride, nplanes);
   return launched("conv_smallc");
 }
 
@@ -384,38 +398,48 @@ extern "C" int accflow_conv2d_f32(const accflow_conv_desc* dp, void* stream) {
 
 extern "C" int accflow_conv_smallc_f32(const float* in, int in_is_nchw, int batch, int cin, int in_h, int in_w,
                                        const float* weight, const float* scale, const float* shift, int ks,
-                                       int stride, int cout, int act, float* out, int out_ld, void* stream) {
+                                       int stride, int cout, int act, float* out, int out_ld, void* out_planes,
+                                       int pl_pitch, long long pl_stride, int nplanes, void* stream) {
   ACCFLOW_REQUIRE(in && weight && out && aligned16(weight), "conv_smallc: null/unaligned pointer");
   ACCFLOW_REQUIRE(batch > 0 && in_h > 0 && in_w > 0 && out_ld >= cout, "conv_smallc: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   if (cin == 3 && ks == 7 && stride == 2 && cout == 64 && in_is_nchw)
-    return launch_smallc<3, 7, 2, 64, true>(in, batch, in_h, in_w, weight, scale, shift, act, out, out_ld, st);
+    return launch_smallc<3, 7, 2, 64, true>(in, batch, in_h, in_w, weight, scale, shift, act, out, out_ld, out_planes,
+                                            pl_pitch, pl_stride, nplanes, st);
   if (cin == 2 && ks == 7 && stride == 1 && cout == 128 && !in_is_nchw)
-    return launch_smallc<2, 7, 1, 128, false>(in, batch, in_h, in_w, weight, scale, shift, act, out, out_ld, st);
+    return launch_smallc<2, 7, 1, 128, false>(in, batch, in_h, in_w, weight, scale, shift, act, out, out_ld, out_planes,
+                                              pl_pitch, pl_stride, nplanes, st);
   return fail(-1, "conv_smallc: unsupported configuration cin=%d ks=%d stride=%d cout=%d nchw=%d", cin, ks, stride,
               cout, in_is_nchw);
+}
+
+template <int CPL>
+static int launch_smallcout(const float* x, int x_ld, int batch, int h, int w, const float* weight, const float* scale,
+                            const float* shift, int cout, int act, float* out, int out_ld, cudaStream_t st) {
+  const size_t smem = (size_t)9 * CPL * 128 * 4 * sizeof(float);
+  auto kern = conv3x3_smallcout_kernel<CPL>;
+  static thread_local int cfg_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (cfg_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "conv3x3_smallcout: smem attribute: %s", cudaGetErrorString(e));
+    cfg_dev = dev;
+  }
+  const long long total = (long long)batch * h * w;
+  const int ppw = 4;
+  kern<<<cdiv(total, 8 * ppw), 256, smem, st>>>(x, x_ld, batch, h, w, weight, scale, shift, cout, act, out, out_ld, ppw);
+  return launched("conv3x3_smallcout");
 }
 
 extern "C" int accflow_conv3x3_smallcout_f32(const float* x, int x_ld, int batch, int h, int w, int cin,
                                              const float* weight, const float* scale, const float* shift, int cout,
                                              int act, float* out, int out_ld, void* stream) {
   ACCFLOW_REQUIRE(x && weight && out && aligned16(x) && aligned16(weight), "conv3x3_smallcout: null/unaligned pointer");
-  ACCFLOW_REQUIRE(batch > 0 && h > 0 && w > 0 && cin % 4 == 0 && x_ld % 4 == 0 && x_ld >= cin && cout >= 1 && cout <= 4 &&
-                      out_ld >= cout, "conv3x3_smallcout: bad shape (cin %% 4 == 0, cout <= 4)");
-  const size_t smem = (size_t)9 * cin * 4 * sizeof(float);
-  ACCFLOW_REQUIRE(smem <= 160 * 1024, "conv3x3_smallcout: cin=%d too large", cin);
-  static thread_local int cfg_dev = -1;
-  static thread_local size_t cfg_smem = 0;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (smem > 48 * 1024 && (cfg_dev != dev || cfg_smem < smem)) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_smallcout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail((int)e, "conv3x3_smallcout: smem attribute: %s", cudaGetErrorString(e));
-    cfg_dev = dev; cfg_smem = smem;
-  }
-  const long long total = (long long)batch * h * w;
-  const int ppw = 16;
-  conv3x3_smallcout_kernel<<<cdiv(total, 8 * ppw), 256, smem, (cudaStream_t)stream>>>(
-      x, x_ld, batch, h, w, cin, weight, scale, shift, cout, act, out, out_ld, ppw);
-  return launched("conv3x3_smallcout");
+  ACCFLOW_REQUIRE(batch > 0 && h > 0 && w > 0 && x_ld % 4 == 0 && x_ld >= cin && cout >= 1 && cout <= 4 && out_ld >= cout,
+                  "conv3x3_smallcout: bad shape (cout <= 4)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cin == 256) return launch_smallcout<2>(x, x_ld, batch, h, w, weight, scale, shift, cout, act, out, out_ld, st);
+  if (cin == 128) return launch_smallcout<1>(x, x_ld, batch, h, w, weight, scale, shift, cout, act, out, out_ld, st);
+  return fail(-1, "conv3x3_smallcout: cin must be 128 or 256 (got %d)", cin);
 }

@@ -1,6 +1,4 @@
 // Gather / resample / normalisation kernels of the flow path (all HBM- or latency-bound).
-#include <cuda_bf16.h>
-
 #include "common.cuh"
 
 namespace accflow {
@@ -164,6 +162,7 @@ struct LookupP {
   float* out; int out_ld;
   float* flow_out; float* mf_tail; int mf_ld;
   __nv_bfloat16* out_pl; int pl_pitch; long long pl_stride; int nplanes;
+  __nv_bfloat16* tail_pl; int tail_pitch; long long tail_stride;
 };
 
 __device__ __forceinline__ float bilinear_zeros(const float* __restrict__ img, int H, int W, float x, float y) {
@@ -183,19 +182,21 @@ __device__ __forceinline__ float bilinear_zeros(const float* __restrict__ img, i
   return r;
 }
 
-// One warp per source pixel.  Per level the warp stages the (2r+3)^2 patch of the pixel's target
+// One warp per source pixel.  Per level the warp stages the (2r+4)^2 patch of the pixel's target
 // map around floor(coords / 2^l) in shared memory (rows are contiguous in HBM, zero outside the
-// map), then every lane interpolates its taps from the patch.  The per-tap coordinate arithmetic
-// is the reference's (normalise / un-normalise round trip per tap), only the four corner reads
-// move from HBM to shared memory.  Output channels of a level are written as one coalesced run;
-// optional bf16 planes of the output feed the tensor-core 1x1 conv that follows (convc1).
+// map) and evaluates the reference's coordinate arithmetic (normalise / un-normalise round trip,
+// raft/utils/utils.py:70-74) once per window column and once per window row - the 81 taps of a
+// level only combine 9 x-terms with 9 y-terms.  Every lane then interpolates its taps from the
+// patch; a level's output channels are written as one coalesced run, optionally also as bf16
+// planes for the tensor-core 1x1 conv that follows (convc1).
 __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupP p) {
-  constexpr int MAXP = 19 * 19;                 // radius <= 8
+  constexpr int MAXP = 20 * 20, MAXK = 17;      // radius <= 8
   __shared__ float patch[8][MAXP];
+  __shared__ float4 axis[8][2][MAXK];           // (patch index, w0, w1, valid) per window column / row
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long pix = (long long)blockIdx.x * 8 + wib;
   if (pix >= (long long)p.batch * p.h * p.w) return;
-  const int r = p.radius, k1 = 2 * r + 1, k2 = k1 * k1, pd = k1 + 2;
+  const int r = p.radius, k1 = 2 * r + 1, k2 = k1 * k1, pd = k1 + 3;   // 1 texel of slack below, 2 above
   const float cx = __ldg(p.coords + pix * 2), cy = __ldg(p.coords + pix * 2 + 1);
   float* pt = patch[wib];
   float* orow = p.out + pix * p.out_ld;
@@ -213,45 +214,47 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupP p) {
       const int gx = x0 + xx, gy = y0 + yy;
       pt[i] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? __ldg(img + gy * W + gx) : 0.f;
     }
+    if (lane < k1) {
+#pragma unroll
+      for (int ax = 0; ax < 2; ++ax) {
+        const int size = ax ? H : W, org = ax ? y0 : x0;
+        const float c = grid_roundtrip(__fadd_rn(ax ? by : bx, (float)(lane - r)), size);
+        const float cf = floorf(c);
+        const bool in_range = c > -2.f && c < (float)size + 1.f;
+        const int idx = in_range ? (int)cf - org : -1;
+        // idx must address a 2-texel run inside the patch; otherwise the tap is outside the map
+        // for every finite coordinate (patch has a texel of slack), so it contributes zero
+        const bool ok = in_range && idx >= 0 && idx + 1 < pd;
+        axis[wib][ax][lane] = make_float4(__int_as_float(ok ? idx : 0), (cf + 1.f) - c, c - cf, ok ? 1.f : 0.f);
+      }
+    }
     __syncwarp();
     for (int t = lane; t < k2; t += 32) {
       const int a = t / k1, bb = t - a * k1;
-      const float x = grid_roundtrip(__fadd_rn(bx, (float)(a - r)), W);
-      const float y = grid_roundtrip(__fadd_rn(by, (float)(bb - r)), H);
+      const float4 ex = axis[wib][0][a], ey = axis[wib][1][bb];
       float v = 0.f;
-      if (x > -2.f && x < (float)W + 1.f && y > -2.f && y < (float)H + 1.f) {
-        const float xf = floorf(x), yf = floorf(y);
-        const int xi = (int)xf - x0, yi = (int)yf - y0;       // position inside the patch
-        const float wx1 = x - xf, wy1 = y - yf, wx0 = (xf + 1.f) - x, wy0 = (yf + 1.f) - y;
-        if (xi >= 0 && xi + 1 < pd && yi >= 0 && yi + 1 < pd) {
-          const float* q = pt + yi * pd + xi;
-          v = q[0] * (wx0 * wy0);
-          v += q[1] * (wx1 * wy0);
-          v += q[pd] * (wx0 * wy1);
-          v += q[pd + 1] * (wx1 * wy1);
-        } else {
-          v = bilinear_zeros(img, H, W, x, y);                 // never taken for finite coords; kept for safety
-        }
+      if (ex.w != 0.f && ey.w != 0.f) {
+        const float* q = pt + __float_as_int(ey.x) * pd + __float_as_int(ex.x);
+        v = q[0] * (ex.y * ey.y);
+        v += q[1] * (ex.z * ey.y);
+        v += q[pd] * (ex.y * ey.z);
+        v += q[pd + 1] * (ex.z * ey.z);
       }
       orow[lvl * k2 + t] = v;
-      if (p.out_pl) {
-        __nv_bfloat16* po = p.out_pl + pix * p.pl_pitch + lvl * k2 + t;
-        const __nv_bfloat16 p0 = __float2bfloat16_rn(v);
-        po[0] = p0;
-        if (p.nplanes > 1) {
-          const float r1 = v - __bfloat162float(p0);
-          const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
-          po[p.pl_stride] = p1;
-          po[2 * p.pl_stride] = __float2bfloat16_rn(r1 - __bfloat162float(p1));
-        }
-      }
+      if (p.out_pl) store_planes(p.out_pl + pix * p.pl_pitch + lvl * k2 + t, p.pl_stride, p.nplanes, v);
     }
   }
   if (lane == 0) {
     const int pl = (int)(pix % ((long long)p.h * p.w));
     const float fx = cx - (float)(pl % p.w), fy = cy - (float)(pl / p.w);
     if (p.flow_out) { p.flow_out[pix * 2] = fx; p.flow_out[pix * 2 + 1] = fy; }
-    if (p.mf_tail) { p.mf_tail[pix * p.mf_ld] = fx; p.mf_tail[pix * p.mf_ld + 1] = fy; }
+    if (p.mf_tail) {
+      p.mf_tail[pix * p.mf_ld] = fx; p.mf_tail[pix * p.mf_ld + 1] = fy;
+      if (p.tail_pl) {
+        store_planes(p.tail_pl + pix * p.tail_pitch, p.tail_stride, p.nplanes, fx);
+        store_planes(p.tail_pl + pix * p.tail_pitch + 1, p.tail_stride, p.nplanes, fy);
+      }
+    }
   }
 }
 
@@ -557,7 +560,8 @@ extern "C" int accflow_corr_pool_f32(const float* lvl0, long long n_rows, int h,
 extern "C" int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                        int batch, int h, int w, int radius, const float* coords, float* out,
                                        int out_ld, float* flow_out, float* mf_tail, int mf_ld, void* out_planes,
-                                       int pl_pitch, long long pl_stride, int nplanes, void* stream) {
+                                       int pl_pitch, long long pl_stride, void* tail_planes, int tail_pitch,
+                                       long long tail_stride, int nplanes, void* stream) {
   ACCFLOW_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && coords && out, "corr_lookup: null pointer");
   ACCFLOW_REQUIRE(batch > 0 && h >= 8 && w >= 8 && radius >= 0 && radius <= 8, "corr_lookup: bad shape");
   const int nch = 4 * (2 * radius + 1) * (2 * radius + 1);
@@ -568,8 +572,9 @@ extern "C" int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, con
   for (int l = 0; l < 4; ++l) { p.lh[l] = hh; p.lw[l] = ww; hh >>= 1; ww >>= 1; }
   p.batch = batch; p.h = h; p.w = w; p.radius = radius; p.coords = coords;
   p.out = out; p.out_ld = out_ld; p.flow_out = flow_out; p.mf_tail = mf_tail; p.mf_ld = mf_ld;
-  ACCFLOW_REQUIRE(!out_planes || (nplanes == 1 || nplanes == 3), "corr_lookup: nplanes must be 1 or 3");
+  ACCFLOW_REQUIRE((!out_planes && !tail_planes) || (nplanes == 1 || nplanes == 3), "corr_lookup: nplanes must be 1 or 3");
   p.out_pl = reinterpret_cast<__nv_bfloat16*>(out_planes); p.pl_pitch = pl_pitch; p.pl_stride = pl_stride; p.nplanes = nplanes;
+  p.tail_pl = reinterpret_cast<__nv_bfloat16*>(tail_planes); p.tail_pitch = tail_pitch; p.tail_stride = tail_stride;
   corr_lookup_kernel<<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(p);
   return launched("corr_lookup");
 }

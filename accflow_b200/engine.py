@@ -284,11 +284,23 @@ class Kernels:
         for tv in written:
             self._fresh(tv)
 
+    def _out_planes(self, v: View):
+        """Planes pointer triple for a kernel that can emit planes itself, or (None, 0, 0)."""
+        got = self.planes_ptr(v, create=False) if self.tc else None
+        return got if got is not None else (None, 0, 0)
+
+    def _done(self, v: View, emitted: bool):
+        if emitted:
+            self._fresh(v)
+        else:
+            self.wrote(v)
+
     def conv_smallc(self, x_ptr: int, nchw: bool, batch, cin, h, w, pc: PackedConv, act, out: View):
+        pl = self._out_planes(out)
         L.call("accflow_conv_smallc_f32", x_ptr, int(nchw), batch, cin, h, w, pc.w.data_ptr(),
                None if pc.scale is None else pc.scale.data_ptr(), pc.shift.data_ptr(), pc.kh, pc.stride, pc.cout,
-               act, out.ptr, out.ld, _stream())
-        self.wrote(out)
+               act, out.ptr, out.ld, pl[0], pl[1], pl[2], self.nplanes, _stream())
+        self._done(out, pl[0] is not None)
 
     def conv_smallcout(self, pc: PackedConv, x: View, out: View, act=L.ACT_NONE):
         """3x3 conv with <= 4 output channels on the bandwidth kernel (always fp32 arithmetic)."""
@@ -300,16 +312,12 @@ class Kernels:
 
     def corr_lookup(self, lv, radius: int, coords: torch.Tensor, out: View, flow: torch.Tensor, mf_tail: View):
         """CorrBlock.__call__ for all four levels; also emits flow = coords - grid."""
-        got = self.planes_ptr(out, create=False) if self.tc else None
-        pl_ptr, pl_pitch, pl_stride = got if got is not None else (None, 0, 0)
+        pl, tl = self._out_planes(out), self._out_planes(mf_tail)
         L.call("accflow_corr_lookup_f32", lv[0].data_ptr(), lv[1].data_ptr(), lv[2].data_ptr(), lv[3].data_ptr(),
                out.b, out.h, out.w, radius, coords.data_ptr(), out.ptr, out.ld, flow.data_ptr(), mf_tail.ptr, mf_tail.ld,
-               pl_ptr, pl_pitch, pl_stride, self.nplanes, _stream())
-        if got is not None:
-            self._fresh(out)
-        else:
-            self.wrote(out)
-        self.wrote(mf_tail)
+               pl[0], pl[1], pl[2], tl[0], tl[1], tl[2], self.nplanes, _stream())
+        self._done(out, pl[0] is not None)
+        self._done(mf_tail, tl[0] is not None)
 
     def instnorm(self, x: View, relu: bool, residual: Optional[View], post_relu: bool, out: View, eps=1e-5):
         assert x.c == x.ld and out.c == out.ld

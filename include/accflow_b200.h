@@ -135,7 +135,9 @@ ACCFLOW_API int accflow_split_bf16_planes(const float* x, long long rows, int k,
  * weight: packed [cin*ks*ks][cout] fp32 with k = (ky*ks + kx)*cin + c. */
 ACCFLOW_API int accflow_conv_smallc_f32(const float* in, int in_is_nchw, int batch, int cin, int in_h, int in_w,
                             const float* weight, const float* scale, const float* shift, int ks,
-                            int stride, int cout, int act, float* out, int out_ld, void* stream);
+                            int stride, int cout, int act, float* out, int out_ld,
+                            void* out_planes /* optional bf16 planes of `out` */, int pl_pitch,
+                            long long pl_plane_stride, int nplanes, void* stream);
 
 /* 3x3 / stride 1 / pad 1 convolution with cout <= 4 (FlowHead.conv2 raft/update.py:10,
  * FlowDecoder.flow[2] AccFlow_.py:19, Blending.mask[2] AccFlow_.py:118), fused affine + activation.
@@ -171,7 +173,9 @@ ACCFLOW_API int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, co
                             int batch, int h, int w, int radius, const float* coords, float* out,
                             int out_ld, float* flow_out, float* mf_tail, int mf_ld,
                             void* out_planes /* optional bf16 planes of `out` */, int pl_pitch,
-                            long long pl_plane_stride, int nplanes, void* stream);
+                            long long pl_plane_stride,
+                            void* tail_planes /* optional planes of the mf_tail slice */, int tail_pitch,
+                            long long tail_plane_stride, int nplanes, void* stream);
 
 /* coords1 = grid + flow_init (raft/raft.py:121-124); flow_init NULL -> zeros.  NCHW (B,2,h,w) in. */
 ACCFLOW_API int accflow_coords_init_f32(const float* flow_init_nchw, int batch, int h, int w, float* coords, void* stream);

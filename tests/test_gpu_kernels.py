@@ -190,7 +190,7 @@ def test_corr_pyramid_and_lookup(KP, golden):
     flow = torch.empty(B, h * w, 2, device="cuda")
     c = dev(coords.permute(0, 2, 3, 1).reshape(B, h * w, 2).contiguous())
     L.call("accflow_corr_lookup_f32", lv[0].data_ptr(), lv[1].data_ptr(), lv[2].data_ptr(), lv[3].data_ptr(), B, h, w, 4,
-           c.data_ptr(), out.data_ptr(), 324, flow.data_ptr(), None, 0, None, 0, 0, 1, None)
+           c.data_ptr(), out.data_ptr(), 324, flow.data_ptr(), None, 0, None, 0, 0, None, 0, 0, 1, None)
     torch.cuda.synchronize()
     assert maxdiff(out.permute(0, 3, 1, 2), g["corr.lookup"]) < tol
     from oracle import ops
