@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--clips", type=int, default=2, help="clips per GPU per step")
+    ap.add_argument("--clips", type=int, default=4, help="clips per GPU per step")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--ofe", default="raft", choices=["raft", "gma"])
@@ -166,8 +166,10 @@ def run_b200(args):
     model.iters = args.iters
     model.ofe.precision = args.precision
     b = args.clips
-    # clip-parallel sharding: rank r owns clips r*b .. r*b+b-1 of each step
-    batch = make_inputs([rank * b + i for i in range(b)], args.size)
+    # clip-parallel sharding: the step's world*b clips are dealt round-robin
+    from accflow_b200.sharding import gather_clip_metrics, shard_clip_ids
+    n_clips = world * b
+    batch = make_inputs(shard_clip_ids(n_clips, rank, world), args.size)
     host_imgs = [t.pin_memory() for t in batch["imgs"]]
     host_out = torch.empty(b, 2, args.size, args.size).pin_memory()
     dev_imgs = [t.to(dev) for t in batch["imgs"]]
@@ -177,11 +179,7 @@ def run_b200(args):
     def step_resident():
         flows = model(images=dev_imgs, test_mode=False)
         epe = torch.stack(metrics.cal_epe(flows[-1], bflow, occ_bw), 1)        # (b,3)
-        if world > 1:                                                         # the only collective: metric gather
-            gathered = torch.empty(world * b, 3, device=dev)
-            dist.all_gather_into_tensor(gathered, epe)
-            return gathered
-        return epe
+        return gather_clip_metrics(epe, n_clips, rank, world)                 # the only collective: metric gather
 
     def step_e2e():
         imgs = [t.to(dev, non_blocking=True) for t in host_imgs]
