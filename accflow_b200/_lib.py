@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libaccflow_b200.so")
+LIB_PATH = os.environ.get("ACCFLOW_LIB") or os.path.join(HERE, "libaccflow_b200.so")   # env override: A/B builds
 MAX_SRC = 4
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
 EPI_STORE, EPI_GRU_ZR, EPI_GRU_Q = 0, 1, 2

@@ -42,6 +42,7 @@ struct Params {
   int nsrc, batch, out_h, out_w;
   int kh, kw, stride, pad_h, pad_w;
   int tw, th, tw_shift, tiles_x, tiles_y;   // spatial tile of 128 output pixels (tw * th = 128)
+  int n_tiles;                              // cout tiles
   int per_sample;                           // weights' T coordinate = sample instead of tap
   int cout, bn, nplanes, nprod, stages;
   float alpha;
@@ -206,10 +207,13 @@ __device__ __forceinline__ void store_planes1(const PlaneOut& po, int nplanes, l
   }
 }
 
+// Persistent: grid = min(#tiles, #SMs); CTA c walks tiles c, c+grid, ... (tiles are N-major so that
+// neighbouring CTAs share one weight tile in L2).  Two TMEM accumulator slots let the epilogue of
+// tile i overlap the TMA/MMA main loop of tile i+1; the smem operand ring runs across tiles.
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPack maps) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
-  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_free[MAX_STAGES], bar_acc;
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_free[MAX_STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -217,32 +221,29 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   const int BN = p.bn, S = p.stages, NPL = p.nplanes;
   const int w_plane_bytes = BN * KC * 2;
   const int stage_bytes = NPL * (A_PLANE_BYTES + w_plane_bytes);
-  // 1024-byte aligned carve-up (SWIZZLE_128B atoms)
+  // 1024-byte aligned carve-up (SWIZZLE_128B atoms): [stages][A planes | W planes] then the epilogue panels
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  // tile -> (sample, tile_y, tile_x)
-  int t = blockIdx.x;
-  const int tile_x = t % p.tiles_x; t /= p.tiles_x;
-  const int tile_y = t % p.tiles_y;
-  const int sample = t / p.tiles_y;
-  const int ox0 = tile_x * p.tw, oy0 = tile_y * p.th;
-  const int n0 = blockIdx.y * BN;
+  constexpr int PITCH = 20;                                     // floats per staged row: 16 columns + 4 pad
+  float* stg_base = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);
 
   int nchunks = 0;
   for (int s = 0; s < p.nsrc; ++s) nchunks += (p.src_c[s] + KC - 1) / KC;
   nchunks *= taps;
-
+  const int acc_cols = (p.nprod > 1 ? 2 : 1) * BN;              // TMEM columns of one accumulator slot
   uint32_t tmem_cols = 32;
-  {
-    const int need = (p.nprod > 1 ? 2 : 1) * BN;
-    while ((int)tmem_cols < need) tmem_cols <<= 1;
-  }
+  while ((int)tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
+  const int total_tiles = m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_free[s], 1);
     }
-    mbar_init(&bar_acc, 1);
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(&bar_acc_full[j], 1);
+      mbar_init(&bar_acc_empty[j], 8);      // one arrival per epilogue warp
+    }
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
     for (int s = 0; s < p.nsrc; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
@@ -256,165 +257,192 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   if (warp == 0) {
     // ================================ TMA producer ============================================
     if (lane == 0) {
-      Chunk ck{0, 0, 0};
-      for (int i = 0; i < nchunks; ++i) {
-        const int s = i % S, round = i / S;
-        if (round > 0) mbar_wait(&bar_free[s], (round - 1) & 1);
-        uint8_t* adst = smem + (size_t)s * stage_bytes;
-        uint8_t* wdst = adst + NPL * A_PLANE_BYTES;
-        mbar_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
-        const int ky = ck.tap / p.kw, kx = ck.tap - ky * p.kw;
-        const int ix = ox0 * p.stride + kx - p.pad_w, iy = oy0 * p.stride + ky - p.pad_h;
-        const int kcoord = p.src_off[ck.s] + ck.c0;
-        const int tw_ = p.per_sample ? sample : ck.tap;
-        for (int pl = 0; pl < NPL; ++pl) {
-          tma_load_5d(adst + pl * A_PLANE_BYTES, &maps.a[ck.s], &bar_full[s], ck.c0, ix, iy, sample, pl);
-          tma_load_4d(wdst + pl * w_plane_bytes, &maps.w, &bar_full[s], kcoord, n0, tw_, pl);
+      int it = 0;                                            // global chunk counter (ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile / m_tiles;
+        int t = tile - n_tile * m_tiles;
+        const int tile_x = t % p.tiles_x; t /= p.tiles_x;
+        const int tile_y = t % p.tiles_y;
+        const int sample = t / p.tiles_y;
+        const int ox0 = tile_x * p.tw, oy0 = tile_y * p.th, n0 = n_tile * BN;
+        Chunk ck{0, 0, 0};
+        for (int i = 0; i < nchunks; ++i, ++it) {
+          const int s = it % S, round = it / S;
+          if (round > 0) mbar_wait(&bar_free[s], (round - 1) & 1);
+          uint8_t* adst = smem + (size_t)s * stage_bytes;
+          uint8_t* wdst = adst + NPL * A_PLANE_BYTES;
+          mbar_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
+          const int ky = ck.tap / p.kw, kx = ck.tap - ky * p.kw;
+          const int ix = ox0 * p.stride + kx - p.pad_w, iy = oy0 * p.stride + ky - p.pad_h;
+          const int kcoord = p.src_off[ck.s] + ck.c0;
+          const int tw_ = p.per_sample ? sample : ck.tap;
+          for (int pl = 0; pl < NPL; ++pl) {
+            tma_load_5d(adst + pl * A_PLANE_BYTES, &maps.a[ck.s], &bar_full[s], ck.c0, ix, iy, sample, pl);
+            tma_load_4d(wdst + pl * w_plane_bytes, &maps.w, &bar_full[s], kcoord, n0, tw_, pl);
+          }
+          ck.next(p, taps);
         }
-        ck.next(p, taps);
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==============================================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BM, BN);
-      const uint32_t acc_main = tmem_base, acc_corr = tmem_base + BN;
-      uint32_t first_main = 0, first_corr = 0;  // 0 -> overwrite accumulator
-      for (int i = 0; i < nchunks; ++i) {
-        const int s = i % S, round = i / S;
-        mbar_wait(&bar_full[s], round & 1);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int slot = lt & 1, use = lt >> 1;
+        mbar_wait(&bar_acc_empty[slot], (use & 1) ^ 1);     // epilogue has drained this slot (first use passes)
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t w_base = a_base + NPL * A_PLANE_BYTES;
+        const uint32_t acc_main = tmem_base + slot * acc_cols, acc_corr = acc_main + BN;
+        uint32_t first_main = 0, first_corr = 0;            // 0 -> overwrite accumulator
+        for (int i = 0; i < nchunks; ++i, ++it) {
+          const int s = it % S, round = it / S;
+          mbar_wait(&bar_full[s], round & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t w_base = a_base + NPL * A_PLANE_BYTES;
 #pragma unroll
-        for (int k4 = 0; k4 < KC / 16; ++k4) {
-          const uint32_t koff = k4 * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
-          const uint64_t a0 = make_desc(a_base + koff), w0 = make_desc(w_base + koff);
-          umma_bf16(acc_main, a0, w0, idesc, first_main);
-          first_main = 1;
-          if (p.nprod > 1) {
-            const uint64_t a1 = make_desc(a_base + A_PLANE_BYTES + koff), a2 = make_desc(a_base + 2 * A_PLANE_BYTES + koff);
-            const uint64_t w1 = make_desc(w_base + w_plane_bytes + koff), w2 = make_desc(w_base + 2 * w_plane_bytes + koff);
-            umma_bf16(acc_corr, a0, w1, idesc, first_corr);
-            first_corr = 1;
-            umma_bf16(acc_corr, a1, w0, idesc, 1);
-            umma_bf16(acc_corr, a1, w1, idesc, 1);
-            umma_bf16(acc_corr, a0, w2, idesc, 1);
-            umma_bf16(acc_corr, a2, w0, idesc, 1);
+          for (int k4 = 0; k4 < KC / 16; ++k4) {
+            const uint32_t koff = k4 * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
+            const uint64_t a0 = make_desc(a_base + koff), w0 = make_desc(w_base + koff);
+            umma_bf16(acc_main, a0, w0, idesc, first_main);
+            first_main = 1;
+            if (p.nprod > 1) {
+              const uint64_t a1 = make_desc(a_base + A_PLANE_BYTES + koff), a2 = make_desc(a_base + 2 * A_PLANE_BYTES + koff);
+              const uint64_t w1 = make_desc(w_base + w_plane_bytes + koff), w2 = make_desc(w_base + 2 * w_plane_bytes + koff);
+              umma_bf16(acc_corr, a0, w1, idesc, first_corr);
+              first_corr = 1;
+              umma_bf16(acc_corr, a1, w0, idesc, 1);
+              umma_bf16(acc_corr, a1, w1, idesc, 1);
+              umma_bf16(acc_corr, a0, w2, idesc, 1);
+              umma_bf16(acc_corr, a2, w0, idesc, 1);
+            }
           }
+          umma_commit(&bar_free[s]);  // smem of this stage is reusable once these MMAs retire
         }
-        umma_commit(&bar_free[s]);  // smem of this stage is reusable once these MMAs retire
+        umma_commit(&bar_acc_full[slot]);
       }
-      umma_commit(&bar_acc);
     }
   } else {
     // ================================ epilogue ================================================
-    // Phase 1: TMEM -> registers (MAIN + CORR) -> padded smem panel.  Phase 2: coalesced global
-    // traffic (4 pixels x 128 B per warp instruction) with the affine / activation / GRU math.
+    // Phase 1: TMEM -> registers (MAIN + CORR) -> padded smem panel (16 columns).  Phase 2: coalesced
+    // global traffic with the affine / activation / GRU math, fp32 stores + bf16 planes.
     const int half = (warp - 2) >> 2;
-    mbar_wait(&bar_acc, 0);
-    tc_fence_after();
-    constexpr int PITCH = 36;                                   // floats; conflict-free for both phases
-    float* stg = reinterpret_cast<float*>(smem + (size_t)half * stage_bytes);
+    float* stg = stg_base + half * (BM * PITCH);
     const int trow = 32 * (warp & 3) + lane;                    // TMEM lane owned by this thread
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     const int st = tid - 64 - 128 * half;                       // 0..127 inside this warp set
+    const int pc4 = st & 3;                                     // float4 group inside the 16-column panel
     const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
-    const int pc4 = st & 7;
-    for (int c = cbeg; c < cend; c += 32) {
-      const int pw = min(32, cend - c);
-      for (int g = 0; g < pw; g += 16) {
-        float acc[16];
-        tmem_ld16(lane_addr + c + g, acc);
-        if (p.nprod > 1) {
-          float corr[16];
-          tmem_ld16(lane_addr + BN + c + g, corr);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int n_tile = tile / m_tiles;
+      int t = tile - n_tile * m_tiles;
+      const int tile_x = t % p.tiles_x; t /= p.tiles_x;
+      const int tile_y = t % p.tiles_y;
+      const int sample = t / p.tiles_y;
+      const int ox0 = tile_x * p.tw, oy0 = tile_y * p.th, n0 = n_tile * BN;
+      const int slot = lt & 1, use = lt >> 1;
+      mbar_wait(&bar_acc_full[slot], use & 1);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + slot * acc_cols + ((uint32_t)(32 * (warp & 3)) << 16);
+      for (int c = cbeg; c < cend; c += 16) {
+        {
+          float acc[16];
+          tmem_ld16(lane_addr + c, acc);
+          if (p.nprod > 1) {
+            float corr[16];
+            tmem_ld16(lane_addr + BN + c, corr);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] += corr[j];
+            for (int j = 0; j < 16; ++j) acc[j] += corr[j];
+          }
+          float4* d4 = reinterpret_cast<float4*>(stg + trow * PITCH);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         }
-        float4* d4 = reinterpret_cast<float4*>(stg + trow * PITCH + g);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) d4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-      const int nb = n0 + c + pc4 * 4;
-      if (pc4 * 4 < pw && nb < p.cout) {
-        float sc[4], sh[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool ok = nb + j < p.cout;
-          sc[j] = p.alpha * ((p.scale && ok) ? __ldg(p.scale + nb + j) : 1.f);
-          sh[j] = (p.shift && ok) ? __ldg(p.shift + nb + j) : 0.f;
+        if (c + 16 >= cend) {                 // last TMEM read of this tile: hand the slot back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
         }
-        const bool vec4 = nb + 3 < p.cout;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        const int nb = n0 + c + pc4 * 4;
+        if (nb < p.cout) {
+          float sc[4], sh[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool ok = nb + j < p.cout;
+            sc[j] = p.alpha * ((p.scale && ok) ? __ldg(p.scale + nb + j) : 1.f);
+            sh[j] = (p.shift && ok) ? __ldg(p.shift + nb + j) : 0.f;
+          }
+          const bool vec4 = nb + 3 < p.cout;
 #pragma unroll 2
-        for (int it = 0; it < 8; ++it) {
-          const int row = it * 16 + (st >> 3);
-          const int oy = oy0 + (row >> p.tw_shift), ox = ox0 + (row & (p.tw - 1));
-          if (oy >= p.out_h || ox >= p.out_w) continue;
-          const long long pix = ((long long)sample * p.out_h + oy) * p.out_w + ox;
-          const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
-          float y[4] = {fmaf(a4.x, sc[0], sh[0]), fmaf(a4.y, sc[1], sh[1]), fmaf(a4.z, sc[2], sh[2]), fmaf(a4.w, sc[3], sh[3])};
-          if (p.epilogue == ACCFLOW_EPI_STORE) {
-            if (p.out_vec && vec4) {
+          for (int itr = 0; itr < 4; ++itr) {
+            const int row = itr * 32 + (st >> 2);
+            const int oy = oy0 + (row >> p.tw_shift), ox = ox0 + (row & (p.tw - 1));
+            if (oy >= p.out_h || ox >= p.out_w) continue;
+            const long long pix = ((long long)sample * p.out_h + oy) * p.out_w + ox;
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
+            float y[4] = {fmaf(a4.x, sc[0], sh[0]), fmaf(a4.y, sc[1], sh[1]), fmaf(a4.z, sc[2], sh[2]), fmaf(a4.w, sc[3], sh[3])};
+            if (p.epilogue == ACCFLOW_EPI_STORE) {
+              if (p.out_vec && vec4) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) y[j] = act_apply(y[j], p.act);
-              if (p.residual) {
-                const float4 r = *reinterpret_cast<const float4*>(p.residual + pix * p.res_ld + nb);
-                y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
-              }
-              if (p.post_relu) {
+                for (int j = 0; j < 4; ++j) y[j] = act_apply(y[j], p.act);
+                if (p.residual) {
+                  const float4 r = *reinterpret_cast<const float4*>(p.residual + pix * p.res_ld + nb);
+                  y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
+                }
+                if (p.post_relu) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
-              }
-              *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
-              if (p.out_pl.ptr) store_planes4(p.out_pl, NPL, pix, nb, y);
-            } else {
+                  for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
+                }
+                *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
+                if (p.out_pl.ptr) store_planes4(p.out_pl, NPL, pix, nb, y);
+              } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int n = nb + j;
-                if (n < p.cout) {
-                  const bool second = p.act_split > 0 && n >= p.act_split;
-                  float o = act_apply(y[j], second ? p.act2 : p.act);
-                  if (p.residual) o += p.residual[pix * p.res_ld + n];
-                  if (p.post_relu) o = fmaxf(o, 0.f);
-                  if (second && p.out2) {
-                    p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
-                    if (p.out2_pl.ptr) store_planes1(p.out2_pl, NPL, pix, n - p.act_split, o);
-                  } else {
-                    p.out[pix * p.out_ld + n] = o;
-                    if (p.out_pl.ptr) store_planes1(p.out_pl, NPL, pix, n, o);
+                for (int j = 0; j < 4; ++j) {
+                  const int n = nb + j;
+                  if (n < p.cout) {
+                    const bool second = p.act_split > 0 && n >= p.act_split;
+                    float o = act_apply(y[j], second ? p.act2 : p.act);
+                    if (p.residual) o += p.residual[pix * p.res_ld + n];
+                    if (p.post_relu) o = fmaxf(o, 0.f);
+                    if (second && p.out2) {
+                      p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
+                      if (p.out2_pl.ptr) store_planes1(p.out2_pl, NPL, pix, n - p.act_split, o);
+                    } else {
+                      p.out[pix * p.out_ld + n] = o;
+                      if (p.out_pl.ptr) store_planes1(p.out_pl, NPL, pix, n, o);
+                    }
                   }
                 }
               }
-            }
-          } else if (p.epilogue == ACCFLOW_EPI_GRU_ZR) {
-            const int hd = p.cout >> 1;   // multiple of 4 (checked on the host): a group never straddles z | r
-            float g4[4];
+            } else if (p.epilogue == ACCFLOW_EPI_GRU_ZR) {
+              const int hd = p.cout >> 1;   // multiple of 4 (checked on the host): a group never straddles z | r
+              float g4[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) g4[j] = 1.f / (1.f + expf(-y[j]));
-            if (nb < hd) {
-              *reinterpret_cast<float4*>(p.z + pix * p.z_ld + nb) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+              for (int j = 0; j < 4; ++j) g4[j] = 1.f / (1.f + expf(-y[j]));
+              if (nb < hd) {
+                *reinterpret_cast<float4*>(p.z + pix * p.z_ld + nb) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+              } else {
+                const int n = nb - hd;
+                const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + n);
+                float o[4] = {g4[0] * hh.x, g4[1] * hh.y, g4[2] * hh.z, g4[3] * hh.w};
+                *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
+                if (p.out2_pl.ptr) store_planes4(p.out2_pl, NPL, pix, n, o);
+              }
             } else {
-              const int n = nb - hd;
-              const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + n);
-              float o[4] = {g4[0] * hh.x, g4[1] * hh.y, g4[2] * hh.z, g4[3] * hh.w};
-              *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
-              if (p.out2_pl.ptr) store_planes4(p.out2_pl, NPL, pix, n, o);
+              const float4 zz = *reinterpret_cast<const float4*>(p.z + pix * p.z_ld + nb);
+              const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + nb);
+              float o[4] = {(1.f - zz.x) * hh.x + zz.x * tanhf(y[0]), (1.f - zz.y) * hh.y + zz.y * tanhf(y[1]),
+                            (1.f - zz.z) * hh.z + zz.z * tanhf(y[2]), (1.f - zz.w) * hh.w + zz.w * tanhf(y[3])};
+              *reinterpret_cast<float4*>(p.h + pix * p.h_ld + nb) = make_float4(o[0], o[1], o[2], o[3]);
+              if (p.h_pl.ptr) store_planes4(p.h_pl, NPL, pix, nb, o);
             }
-          } else {
-            const float4 zz = *reinterpret_cast<const float4*>(p.z + pix * p.z_ld + nb);
-            const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + nb);
-            float o[4] = {(1.f - zz.x) * hh.x + zz.x * tanhf(y[0]), (1.f - zz.y) * hh.y + zz.y * tanhf(y[1]),
-                          (1.f - zz.z) * hh.z + zz.z * tanhf(y[2]), (1.f - zz.w) * hh.w + zz.w * tanhf(y[3])};
-            *reinterpret_cast<float4*>(p.h + pix * p.h_ld + nb) = make_float4(o[0], o[1], o[2], o[3]);
-            if (p.h_pl.ptr) store_planes4(p.h_pl, NPL, pix, nb, o);
           }
         }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
     }
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
@@ -523,8 +551,10 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   int ntiles = cdiv(d.cout, bn_cap);
   int bn = cdiv(cdiv(d.cout, ntiles), 32) * 32;
   p.bn = bn;
+  p.n_tiles = cdiv(d.cout, bn);
   const int stage_bytes = nplanes * (tc::A_PLANE_BYTES + bn * tc::KC * 2);
-  int stages = (200 * 1024) / stage_bytes;
+  const int epi_bytes = 2 * tc::BM * 20 * 4;                 // two 128 x (16+4)-float epilogue panels
+  int stages = (222 * 1024 - 1024 - epi_bytes) / stage_bytes;
   if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
   ACCFLOW_REQUIRE(stages >= 2, "conv2d_tc: tile does not fit shared memory");
   p.stages = stages;
@@ -586,16 +616,19 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     ACCFLOW_REQUIRE(cr == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(source %d) failed (%d)", s, (int)cr);
   }
 
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + epi_bytes + 1024;
   static thread_local int cfg_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (cfg_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
     if (e != cudaSuccess) return fail((int)e, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
     cfg_dev = dev;
   }
-  dim3 grid(p.tiles_x * p.tiles_y * d.batch, cdiv(d.cout, bn), 1);
+  static thread_local int sm_count = 0;
+  if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
+  const int total_tiles = p.tiles_x * p.tiles_y * d.batch * p.n_tiles;
+  dim3 grid(total_tiles < sm_count ? total_tiles : sm_count, 1, 1);
   tc::conv_tc_kernel<<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
   return launched("conv2d_tc");
 }
