@@ -278,9 +278,14 @@ __global__ void __launch_bounds__(256) conv3x3_smallcout_kernel(const float* __r
                                                                 const float* __restrict__ shift, int cout, int act,
                                                                 float* __restrict__ out, int out_ld, int pix_per_warp) {
   constexpr int CIN = CPL * 128;
-  extern __shared__ __align__(16) float ws[];  // [9][cin][4]
-  for (int i = threadIdx.x; i < 9 * CIN; i += 256)
-    reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(wgt) + i);
+  // weights re-ordered to [tap][j][e][lane] (float4 = the 4 couts of channel 4*(lane+32j)+e) so that a
+  // warp-wide LDS.128 reads 32 consecutive float4: conflict-free (the natural [tap][cin] order is 4-way conflicted)
+  extern __shared__ __align__(16) float ws[];
+  for (int i = threadIdx.x; i < 9 * CIN; i += 256) {
+    const int t = i / CIN, c = i - t * CIN;
+    const int grp = c >> 2, e = c & 3, j = grp >> 5, ln = grp & 31;
+    reinterpret_cast<float4*>(ws)[((t * CPL + j) * 4 + e) * 32 + ln] = __ldg(reinterpret_cast<const float4*>(wgt) + i);
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)batch * h * w;
@@ -303,11 +308,10 @@ __global__ void __launch_bounds__(256) conv3x3_smallcout_kernel(const float* __r
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const float4* wt = reinterpret_cast<const float4*>(ws) + t * CIN;
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
-        const int c = 4 * (lane + 32 * j);
-        const float4 w0 = wt[c], w1 = wt[c + 1], w2 = wt[c + 2], w3 = wt[c + 3];
+        const float4* wt = reinterpret_cast<const float4*>(ws) + (t * CPL + j) * 128 + lane;
+        const float4 w0 = wt[0], w1 = wt[32], w2 = wt[64], w3 = wt[96];
         const float4 q = v[t][j];
         a0 = fmaf(q.x, w0.x, a0); a1 = fmaf(q.x, w0.y, a1); a2 = fmaf(q.x, w0.z, a2); a3 = fmaf(q.x, w0.w, a3);
         a0 = fmaf(q.y, w1.x, a0); a1 = fmaf(q.y, w1.y, a1); a2 = fmaf(q.y, w1.z, a2); a3 = fmaf(q.y, w1.w, a3);
@@ -328,6 +332,118 @@ __global__ void __launch_bounds__(256) conv3x3_smallcout_kernel(const float* __r
       out[pix * out_ld + lane] = act_apply(r, act);
     }
   }
+}
+
+// ---- encoder stem: 7x7 / stride 2 / 3 -> 64 on NCHW images -----------------------------------
+// 16x16 output pixels per tile, 2x2 (strided by 8) pixels x 16 couts per thread: 64 FMAs per
+// 4 patch + 4 weight shared loads.  Blocks loop over tiles so the 37 KB of weights are staged once.
+__global__ void __launch_bounds__(256) stem7x7_kernel(const float* __restrict__ in, int batch, int in_h, int in_w,
+                                                      const float* __restrict__ w, const float* __restrict__ scale,
+                                                      const float* __restrict__ shift, int act,
+                                                      float* __restrict__ out, int out_ld, int out_h, int out_w,
+                                                      __nv_bfloat16* __restrict__ out_pl, int pl_pitch,
+                                                      long long pl_stride, int nplanes) {
+  constexpr int CIN = 3, KS = 7, COUT = 64, TILE = 16, PATCH = (TILE - 1) * 2 + KS, PP = PATCH + 1, K = CIN * KS * KS;
+  extern __shared__ __align__(16) float sm[];
+  float* Ws = sm;                  // [K][COUT]
+  float* patch = sm + K * COUT;    // [CIN][PATCH][PP]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * COUT / 4; i += 256)
+    reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+  const int tiles_x = (out_w + TILE - 1) / TILE, tiles_y = (out_h + TILE - 1) / TILE;
+  const int ntiles = tiles_x * tiles_y * batch;
+  const int q = tid & 63, g = tid >> 6;           // pixel slot (8x8), cout group (16 channels)
+  const int qy = q >> 3, qx = q & 7;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int t = tile;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    const int oy0 = ty * TILE, ox0 = tx * TILE;
+    const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+    __syncthreads();                               // previous tile's readers are done (also covers the weight fill)
+    for (int i = tid; i < CIN * PATCH * PATCH; i += 256) {
+      const int c = i / (PATCH * PATCH), r = i - c * PATCH * PATCH;
+      const int py = r / PATCH, px = r - py * PATCH;
+      const int iy = iy0 + py, ix = ix0 + px;
+      float v = 0.f;
+      if (iy >= 0 && iy < in_h && ix >= 0 && ix < in_w) v = __ldg(in + ((long long)(b * CIN + c) * in_h + iy) * in_w + ix);
+      patch[(c * PATCH + py) * PP + px] = v;
+    }
+    __syncthreads();
+    float acc[4][16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+    // thread's pixels: (qy + 8*dy, qx + 8*dx)
+    for (int ky = 0; ky < KS; ++ky)
+      for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+          const float* pp = patch + (c * PATCH + 2 * qy + ky) * PP + 2 * qx + kx;
+          const float v0 = pp[0], v1 = pp[16], v2 = pp[16 * PP], v3 = pp[16 * PP + 16];
+          const float4* wr = reinterpret_cast<const float4*>(Ws + ((ky * KS + kx) * CIN + c) * COUT + g * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 ww = wr[j];
+            acc[0][4 * j] = fmaf(v0, ww.x, acc[0][4 * j]); acc[0][4 * j + 1] = fmaf(v0, ww.y, acc[0][4 * j + 1]);
+            acc[0][4 * j + 2] = fmaf(v0, ww.z, acc[0][4 * j + 2]); acc[0][4 * j + 3] = fmaf(v0, ww.w, acc[0][4 * j + 3]);
+            acc[1][4 * j] = fmaf(v1, ww.x, acc[1][4 * j]); acc[1][4 * j + 1] = fmaf(v1, ww.y, acc[1][4 * j + 1]);
+            acc[1][4 * j + 2] = fmaf(v1, ww.z, acc[1][4 * j + 2]); acc[1][4 * j + 3] = fmaf(v1, ww.w, acc[1][4 * j + 3]);
+            acc[2][4 * j] = fmaf(v2, ww.x, acc[2][4 * j]); acc[2][4 * j + 1] = fmaf(v2, ww.y, acc[2][4 * j + 1]);
+            acc[2][4 * j + 2] = fmaf(v2, ww.z, acc[2][4 * j + 2]); acc[2][4 * j + 3] = fmaf(v2, ww.w, acc[2][4 * j + 3]);
+            acc[3][4 * j] = fmaf(v3, ww.x, acc[3][4 * j]); acc[3][4 * j + 1] = fmaf(v3, ww.y, acc[3][4 * j + 1]);
+            acc[3][4 * j + 2] = fmaf(v3, ww.z, acc[3][4 * j + 2]); acc[3][4 * j + 3] = fmaf(v3, ww.w, acc[3][4 * j + 3]);
+          }
+        }
+    float sc[16], sh[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      sc[j] = scale ? __ldg(scale + g * 16 + j) : 1.f;
+      sh[j] = shift ? __ldg(shift + g * 16 + j) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int oy = oy0 + qy + 8 * (i >> 1), ox = ox0 + qx + 8 * (i & 1);
+      if (oy >= out_h || ox >= out_w) continue;
+      const long long pix = ((long long)b * out_h + oy) * out_w + ox;
+      float* op = out + pix * out_ld + g * 16;
+      float y[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) y[j] = act_apply(fmaf(acc[i][j], sc[j], sh[j]), act);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(op)[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+      if (out_pl) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) store_planes(out_pl + pix * pl_pitch + g * 16 + j, pl_stride, nplanes, y[j]);
+      }
+    }
+  }
+}
+
+// ---- 7x7 flow patches: flow [B,h,w,2] -> [B,h,w,ld] with channel (ky*7+kx)*2 + c = flow(y+ky-3, x+kx-3, c),
+// zero outside the map and for channels 98..ld-1.  Turns the 2-channel 7x7 convs (raft/update.py:85,
+// AccFlow_.py:51) into 1x1 convs with K = 98 for the tensor-core kernel.
+__global__ void __launch_bounds__(256) flow_patch_kernel(const float* __restrict__ flow, int batch, int h, int w,
+                                                         float* __restrict__ out, int out_ld,
+                                                         __nv_bfloat16* __restrict__ out_pl, int pl_pitch,
+                                                         long long pl_stride, int nplanes) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)batch * h * w * out_ld;
+  if (i >= total) return;
+  const long long pix = i / out_ld;
+  const int k = (int)(i - pix * out_ld);
+  float v = 0.f;
+  if (k < 98) {
+    const int tap = k >> 1, c = k & 1;
+    const int hw = h * w;
+    const int b = (int)(pix / hw), pl = (int)(pix - (long long)b * hw);
+    const int y = pl / w + tap / 7 - 3, x = pl % w + tap % 7 - 3;
+    if (y >= 0 && y < h && x >= 0 && x < w) v = __ldg(flow + ((long long)(b * h + y) * w + x) * 2 + c);
+  }
+  out[i] = v;
+  if (out_pl) store_planes(out_pl + pix * pl_pitch + k, pl_stride, nplanes, v);
 }
 
 template <int CIN, int KS, int STRIDE, int COUT, bool NCHW>
@@ -403,9 +519,27 @@ extern "C" int accflow_conv_smallc_f32(const float* in, int in_is_nchw, int batc
   ACCFLOW_REQUIRE(in && weight && out && aligned16(weight), "conv_smallc: null/unaligned pointer");
   ACCFLOW_REQUIRE(batch > 0 && in_h > 0 && in_w > 0 && out_ld >= cout, "conv_smallc: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  if (cin == 3 && ks == 7 && stride == 2 && cout == 64 && in_is_nchw)
-    return launch_smallc<3, 7, 2, 64, true>(in, batch, in_h, in_w, weight, scale, shift, act, out, out_ld, out_planes,
-                                            pl_pitch, pl_stride, nplanes, st);
+  if (cin == 3 && ks == 7 && stride == 2 && cout == 64 && in_is_nchw) {
+    ACCFLOW_REQUIRE(aligned16(out) && out_ld % 4 == 0, "conv_smallc: stem output must be 16B aligned");
+    constexpr int K = 147, PATCH = 37;
+    const size_t smem = (size_t)(K * 64 + 3 * PATCH * (PATCH + 1)) * sizeof(float);
+    static thread_local int cfg_dev = -1;
+    static thread_local int sms = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cfg_dev != dev) {
+      cudaError_t e = cudaFuncSetAttribute(stem7x7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail((int)e, "conv_smallc: smem attribute: %s", cudaGetErrorString(e));
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cfg_dev = dev;
+    }
+    const int out_h = (in_h + 6 - 7) / 2 + 1, out_w = (in_w + 6 - 7) / 2 + 1;
+    const int ntiles = cdiv(out_w, 16) * cdiv(out_h, 16) * batch;
+    const int grid = ntiles < sms * 4 ? ntiles : sms * 4;
+    stem7x7_kernel<<<grid, 256, smem, st>>>(in, batch, in_h, in_w, weight, scale, shift, act, out, out_ld, out_h, out_w,
+                                            reinterpret_cast<__nv_bfloat16*>(out_planes), pl_pitch, pl_stride, nplanes);
+    return launched("stem7x7");
+  }
   if (cin == 2 && ks == 7 && stride == 1 && cout == 128 && !in_is_nchw)
     return launch_smallc<2, 7, 1, 128, false>(in, batch, in_h, in_w, weight, scale, shift, act, out, out_ld, out_planes,
                                               pl_pitch, pl_stride, nplanes, st);
@@ -442,4 +576,15 @@ extern "C" int accflow_conv3x3_smallcout_f32(const float* x, int x_ld, int batch
   if (cin == 256) return launch_smallcout<2>(x, x_ld, batch, h, w, weight, scale, shift, cout, act, out, out_ld, st);
   if (cin == 128) return launch_smallcout<1>(x, x_ld, batch, h, w, weight, scale, shift, cout, act, out, out_ld, st);
   return fail(-1, "conv3x3_smallcout: cin must be 128 or 256 (got %d)", cin);
+}
+
+extern "C" int accflow_flow_patch_f32(const float* flow, int batch, int h, int w, float* out, int out_ld, void* out_planes,
+                                      int pl_pitch, long long pl_stride, int nplanes, void* stream) {
+  ACCFLOW_REQUIRE(flow && out && batch > 0 && h > 0 && w > 0 && out_ld >= 98, "flow_patch: bad arguments");
+  ACCFLOW_REQUIRE(!out_planes || nplanes == 1 || nplanes == 3, "flow_patch: nplanes must be 1 or 3");
+  const long long total = (long long)batch * h * w * out_ld;
+  flow_patch_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(flow, batch, h, w, out, out_ld,
+                                                                        reinterpret_cast<__nv_bfloat16*>(out_planes),
+                                                                        pl_pitch, pl_stride, nplanes);
+  return launched("flow_patch");
 }

@@ -87,6 +87,19 @@ class PackedConv:
         self.shift = shift.contiguous()
         self.has_bias = any(b is not None for b in biases) or bn is not None
 
+    def as_1x1(self) -> "PackedConv":
+        """The same filter as a 1x1 conv over im2col'd input with K ordered (ky, kx, cin)."""
+        if getattr(self, "_as1x1", None) is None:
+            w = self.w_oihw.permute(0, 2, 3, 1).reshape(self.cout, -1, 1, 1).contiguous()
+            pc = PackedConv.__new__(PackedConv)
+            pc.w_oihw, pc._tc, pc._as1x1 = w, None, None
+            pc.cout, pc.cin, pc.kh, pc.kw = w.shape
+            pc.stride, pc.pad_h, pc.pad_w, pc.cout_pad = 1, 0, 0, self.cout_pad
+            pc.w = None
+            pc.scale, pc.shift, pc.has_bias = self.scale, self.shift, self.has_bias
+            self._as1x1 = pc
+        return self._as1x1
+
     def tc_weights(self) -> "L.TcWeights":
         """bf16 planes [3][taps][cout][k_pitch] (w = p0 + p1 + p2) for accflow_conv2d_tc."""
         if self._tc is None:
@@ -301,6 +314,18 @@ class Kernels:
                None if pc.scale is None else pc.scale.data_ptr(), pc.shift.data_ptr(), pc.kh, pc.stride, pc.cout,
                act, out.ptr, out.ld, pl[0], pl[1], pl[2], self.nplanes, _stream())
         self._done(out, pl[0] is not None)
+
+    def flow_conv7(self, tag: str, flow: torch.Tensor, batch: int, h: int, w: int, pc: PackedConv, out: View):
+        """relu(conv7x7(flow)) for a 2-channel flow field [batch, h*w, 2] (raft/update.py:92, AccFlow_.py:62)."""
+        if not self.tc:
+            self.conv_smallc(flow.data_ptr(), False, batch, 2, h, w, pc, L.ACT_RELU, out)
+            return
+        patch = self.view(tag + ".fpatch", batch, h, w, 104)
+        pl = self.planes_ptr(patch, create=True)
+        L.call("accflow_flow_patch_f32", flow.data_ptr(), batch, h, w, patch.ptr, patch.ld, pl[0], pl[1], pl[2],
+               self.nplanes, _stream())
+        self._stale[patch.t.data_ptr()] = []
+        self.conv(pc.as_1x1(), [patch.ch(0, 98)], out, act=L.ACT_RELU)
 
     def conv_smallcout(self, pc: PackedConv, x: View, out: View, act=L.ACT_NONE):
         """3x3 conv with <= 4 output channels on the bandwidth kernel (always fp32 arithmetic)."""
@@ -648,7 +673,7 @@ class FlowEstimatorEngine:
             k.corr_lookup(lv, self.RADIUS, coords, corr, flow, mf.ch(126, 128))
             k.conv(self.convc1, [corr], cor1, act=L.ACT_RELU)
             k.conv(self.convc2, [cor1], cf.ch(0, 192), act=L.ACT_RELU)
-            k.conv_smallc(flow.data_ptr(), False, B, 2, h, w, self.convf1, L.ACT_RELU, flo1)
+            k.flow_conv7(tag, flow, B, h, w, self.convf1, flo1)
             k.conv(self.convf2, [flo1], cf.ch(192, 256), act=L.ACT_RELU)
             k.conv(self.convm, [cf], mf.ch(0, 126), act=L.ACT_RELU)
             if self.gma:
@@ -772,7 +797,7 @@ class AccFlowEngine:
             e1 = k.view("acc.e1", 3 * b, h, w, 128)
             e2 = k.view("acc.e2", 3 * b, h, w, 256)
             enc = k.view("acc.enc", 3 * b, h, w, 128)
-            k.conv_smallc(fin.data_ptr(), False, 3 * b, 2, h, w, self.fe1, L.ACT_RELU, e1)
+            k.flow_conv7("acc.fe", fin, 3 * b, h, w, self.fe1, e1)
             k.conv(self.fe2, [e1], e2, act=L.ACT_RELU)
             k.conv(self.fe3, [e2], enc)
             f_ini, df, f = enc.rows(0, b), enc.rows(b, 2 * b), enc.rows(2 * b, 3 * b)

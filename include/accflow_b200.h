@@ -139,6 +139,13 @@ ACCFLOW_API int accflow_conv_smallc_f32(const float* in, int in_is_nchw, int bat
                             void* out_planes /* optional bf16 planes of `out` */, int pl_pitch,
                             long long pl_plane_stride, int nplanes, void* stream);
 
+/* 7x7 neighbourhood gather of a 2-channel flow field: out[n,y,x,(ky*7+kx)*2+c] = flow[n,y+ky-3,x+kx-3,c]
+ * (zero outside; channels 98..out_ld-1 zero).  With it the 2->128 7x7 convs (raft/update.py:85,92;
+ * AccFlow_.py:51,62) run as K=98 1x1 convs on the tensor-core kernel. */
+ACCFLOW_API int accflow_flow_patch_f32(const float* flow, int batch, int h, int w, float* out, int out_ld,
+                                       void* out_planes, int pl_pitch, long long pl_plane_stride, int nplanes,
+                                       void* stream);
+
 /* 3x3 / stride 1 / pad 1 convolution with cout <= 4 (FlowHead.conv2 raft/update.py:10,
  * FlowDecoder.flow[2] AccFlow_.py:19, Blending.mask[2] AccFlow_.py:118), fused affine + activation.
  * weight: packed [9][cin][4] fp32 (the accflow_conv2d_f32 layout with cout_pad = 4). */
