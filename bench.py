@@ -228,8 +228,12 @@ def run_b200(args):
     eng = model.engine(dev)
     model.ofe.use_cuda_graph = False           # per-launch events need the eager path
     prof = eng.k.profile = []
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
     step_resident()
+    pe1.record()
     torch.cuda.synchronize()
+    prof_step_ms = pe0.elapsed_time(pe1)
     eng.k.profile = None
     model.ofe.use_cuda_graph = True
     conv_ms = sum(a.elapsed_time(z) for a, z, _ in prof)
@@ -240,10 +244,22 @@ def run_b200(args):
     kname = {"fp32": "conv_f32_kernel (implicit-GEMM conv, exact-fp32 FFMA path)",
              "bf16x3": "conv_tc_kernel (tcgen05 implicit-GEMM conv, bf16x3 split: 6 MMAs per algorithmic MAC)",
              "bf16": "conv_tc_kernel (tcgen05 implicit-GEMM conv, bf16 products)"}[args.precision]
-    roofline = {"bound": "tensor", "kernel": kname, "issued_mma_tflops": achieved * (6 if args.precision == "bf16x3" else 1),
+    issued = achieved * (6 if args.precision == "bf16x3" else 1)
+    traffic, traffic_note = None, None
+    tfile = os.path.join(ROOT, "profiles", f"r1_conv_tc_zr_{args.precision}_ncu_full.json")
+    if os.path.exists(tfile):
+        t = json.load(open(tfile))
+        scale_b = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        traffic = sum(float(t[k]["value"]) * scale_b[t[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        traffic_note = ("dram__bytes_read+write of one GRU z|r conv launch (1x5, 384->256, 8 pairs x 64x64) from "
+                        "profiles/" + os.path.basename(tfile) + "; algorithmic bytes of that launch ~154 MB")
+    roofline = {"bound": "tensor", "kernel": kname, "issued_mma_tflops": issued, "issued_frac": issued / pk["bf16_tflops_sustained"],
+                "traffic_note": traffic_note,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_kind": f"bf16 dense sustained, {pk_kind}", "launches": len(prof), "ms_in_step": conv_ms,
-                "share_of_step": conv_ms / (ms / args.steps), "traffic": None}
+                "share_of_step": conv_ms / prof_step_ms,
+                "share_note": "conv launches / whole step, both CUDA-event timed in one eager (non-graph) step",
+                "traffic": traffic}
 
     line = None
     if rank == 0:
