@@ -115,7 +115,7 @@ def flow_estimator(sd: SD, image1, image2, iters: int = 12, flow_init=None, pfx:
     inp = torch.relu(cnet[:, 128:])
     attn = gma_attention(sd, pfx + "att.", inp) if gma else None
     h, w = image1.shape[-2] // 8, image1.shape[-1] // 8
-    coords0 = ops.coords_grid(b, h, w)
+    coords0 = ops.coords_grid(b, h, w, image1.device)
     coords1 = coords0.clone()
     if flow_init is not None:
         coords1 = coords1 + flow_init

@@ -86,7 +86,7 @@ def _sample_zeros(img: torch.Tensor, x: torch.Tensor, y: torch.Tensor) -> torch.
     fy = iy - y0
     out_shape = x.shape[1:]
     flat = img.reshape(n, c, h * w)
-    res = torch.zeros((n, c) + tuple(out_shape), dtype=img.dtype)
+    res = torch.zeros((n, c) + tuple(out_shape), dtype=img.dtype, device=img.device)
     for dy, dx, wgt in ((0, 0, (1 - fx) * (1 - fy)), (0, 1, fx * (1 - fy)),
                         (1, 0, (1 - fx) * fy), (1, 1, fx * fy)):
         xi = x0 + dx
@@ -108,7 +108,7 @@ def corr_lookup(pyramid, coords: torch.Tensor, radius: int = 4) -> torch.Tensor:
     b, _, h, w = coords.shape
     n = b * h * w
     k = 2 * radius + 1
-    d = torch.arange(-radius, radius + 1, dtype=coords.dtype)
+    d = torch.arange(-radius, radius + 1, dtype=coords.dtype, device=coords.device)
     cx = coords[:, 0].reshape(n, 1, 1)
     cy = coords[:, 1].reshape(n, 1, 1)
     outs = []
@@ -122,9 +122,9 @@ def corr_lookup(pyramid, coords: torch.Tensor, radius: int = 4) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- flow helpers
-def coords_grid(b: int, h: int, w: int) -> torch.Tensor:
+def coords_grid(b: int, h: int, w: int, device=None) -> torch.Tensor:
     """raft/utils/utils.py:83-87: channel 0 = x (column index), channel 1 = y."""
-    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    ys, xs = torch.meshgrid(torch.arange(h, device=device), torch.arange(w, device=device), indexing="ij")
     return torch.stack([xs, ys], dim=0).float()[None].repeat(b, 1, 1, 1)
 
 
@@ -138,7 +138,7 @@ def convex_upsample(flow: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     m = mask.reshape(n, 9, 8, 8, h, w)
     m = torch.softmax(m, dim=1)
     fp = F.pad(8 * flow, (1, 1, 1, 1))
-    out = torch.zeros(n, 2, 8, 8, h, w, dtype=flow.dtype)
+    out = torch.zeros(n, 2, 8, 8, h, w, dtype=flow.dtype, device=flow.device)
     for ky in range(3):
         for kx in range(3):
             nb = fp[:, :, ky:ky + h, kx:kx + w]                  # (n,2,h,w)
@@ -149,7 +149,7 @@ def convex_upsample(flow: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
 def backwarp(img: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
     """networks/utils.py:96-124: sample img at (x+flow_x, y+flow_y), zeros, align_corners."""
     n, _, h, w = img.shape
-    g = coords_grid(n, h, w)
+    g = coords_grid(n, h, w, img.device)
     x = g[:, 0] + flow[:, 0]
     y = g[:, 1] + flow[:, 1]
     # reference normalises with max(size-1, 1) — identical for size >= 2
@@ -161,8 +161,8 @@ def resize_bilinear_ac(x: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
     n, c, h, w = x.shape
     sy = (h - 1) / (oh - 1) if oh > 1 else 0.0
     sx = (w - 1) / (ow - 1) if ow > 1 else 0.0
-    ys = torch.arange(oh, dtype=torch.float32) * torch.tensor(sy, dtype=torch.float32)
-    xs = torch.arange(ow, dtype=torch.float32) * torch.tensor(sx, dtype=torch.float32)
+    ys = torch.arange(oh, dtype=torch.float32, device=x.device) * torch.tensor(sy, dtype=torch.float32, device=x.device)
+    xs = torch.arange(ow, dtype=torch.float32, device=x.device) * torch.tensor(sx, dtype=torch.float32, device=x.device)
     y0 = ys.floor().long().clamp(max=h - 1)
     x0 = xs.floor().long().clamp(max=w - 1)
     y1 = (y0 + 1).clamp(max=h - 1)
@@ -201,7 +201,7 @@ def deform_conv2d(x, offset, mask, weight, bias):
     ordinary weight contraction over (cin, tap) and + bias  (SURVEY.md §4 table).
     """
     n, c, h, w = x.shape
-    g = coords_grid(n, h, w)
+    g = coords_grid(n, h, w, x.device)
     cols = []
     flat = x.reshape(n, c, h * w)
     for k in range(9):
@@ -213,7 +213,7 @@ def deform_conv2d(x, offset, mask, weight, bias):
         x0 = torch.floor(px)
         fy = py - y0
         fx = px - x0
-        acc = torch.zeros(n, c, h, w, dtype=x.dtype)
+        acc = torch.zeros(n, c, h, w, dtype=x.dtype, device=x.device)
         for dy, dx, wgt in ((0, 0, (1 - fy) * (1 - fx)), (0, 1, (1 - fy) * fx),
                             (1, 0, fy * (1 - fx)), (1, 1, fy * fx)):
             yi = y0 + dy
