@@ -1,6 +1,7 @@
 // Shared helpers for the accflow_b200 kernels (sm_100a).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
@@ -65,8 +66,21 @@ __device__ __forceinline__ float grid_roundtrip(float x, int size) {
   return __fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.f), 2.f), s);
 }
 
-// bf16 planes (x = p0 + p1 + p2) written next to an fp32 value for the tensor-core convolutions.
+// 16-bit operand planes written next to an fp32 value for the tensor-core convolutions.
+//   nplanes = 1 : bf16(x)                                   ("bf16" mode)
+//   nplanes = 3 : bf16 p0 + p1 + p2 = x (24 mantissa bits)   ("bf16x3" mode, 6 products)
+//   nplanes = 2 : fp16 hi = fp16(x), lo = fp16((x - hi) * 2^11)  ("fp16x2" mode, 3 products);
+//                 the lo plane is pre-scaled so it never underflows; the kernel multiplies the
+//                 cross-term accumulator by 2^-11.
+#define ACCFLOW_FP16X2_SCALE 2048.0f
 __device__ __forceinline__ void store_planes(__nv_bfloat16* dst, long long plane_stride, int nplanes, float v) {
+  if (nplanes == 2) {
+    __half* d = reinterpret_cast<__half*>(dst);
+    const __half hi = __float2half_rn(v);
+    d[0] = hi;
+    d[plane_stride] = __float2half_rn((v - __half2float(hi)) * ACCFLOW_FP16X2_SCALE);
+    return;
+  }
   const __nv_bfloat16 p0 = __float2bfloat16_rn(v);
   dst[0] = p0;
   if (nplanes > 1) {

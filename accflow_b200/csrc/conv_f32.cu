@@ -581,7 +581,7 @@ extern "C" int accflow_conv3x3_smallcout_f32(const float* x, int x_ld, int batch
 extern "C" int accflow_flow_patch_f32(const float* flow, int batch, int h, int w, float* out, int out_ld, void* out_planes,
                                       int pl_pitch, long long pl_stride, int nplanes, void* stream) {
   ACCFLOW_REQUIRE(flow && out && batch > 0 && h > 0 && w > 0 && out_ld >= 98, "flow_patch: bad arguments");
-  ACCFLOW_REQUIRE(!out_planes || nplanes == 1 || nplanes == 3, "flow_patch: nplanes must be 1 or 3");
+  ACCFLOW_REQUIRE(!out_planes || (nplanes >= 1 && nplanes <= 3), "flow_patch: nplanes must be 1, 2 or 3");
   const long long total = (long long)batch * h * w * out_ld;
   flow_patch_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(flow, batch, h, w, out, out_ld,
                                                                         reinterpret_cast<__nv_bfloat16*>(out_planes),

@@ -572,7 +572,7 @@ extern "C" int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, con
   for (int l = 0; l < 4; ++l) { p.lh[l] = hh; p.lw[l] = ww; hh >>= 1; ww >>= 1; }
   p.batch = batch; p.h = h; p.w = w; p.radius = radius; p.coords = coords;
   p.out = out; p.out_ld = out_ld; p.flow_out = flow_out; p.mf_tail = mf_tail; p.mf_ld = mf_ld;
-  ACCFLOW_REQUIRE((!out_planes && !tail_planes) || (nplanes == 1 || nplanes == 3), "corr_lookup: nplanes must be 1 or 3");
+  ACCFLOW_REQUIRE((!out_planes && !tail_planes) || (nplanes >= 1 && nplanes <= 3), "corr_lookup: nplanes must be 1, 2 or 3");
   p.out_pl = reinterpret_cast<__nv_bfloat16*>(out_planes); p.pl_pitch = pl_pitch; p.pl_stride = pl_stride; p.nplanes = nplanes;
   p.tail_pl = reinterpret_cast<__nv_bfloat16*>(tail_planes); p.tail_pitch = tail_pitch; p.tail_stride = tail_stride;
   corr_lookup_kernel<<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(p);

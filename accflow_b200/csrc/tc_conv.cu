@@ -155,8 +155,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
 // A/B K-major, N>>3 at [17,23), M>>4 at [24,29).
-__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, bool fp16) {
+  const uint32_t fmt = fp16 ? 0u : 1u;   // F32F16Format: 0 = F16, 1 = BF16
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -182,6 +183,16 @@ struct Chunk {  // iterator over (tap, source, 64-channel block)
 // Writes 4 consecutive channels of one pixel into the bf16 planes of an output.
 __device__ __forceinline__ void store_planes4(const PlaneOut& po, int nplanes, long long pix, int n, const float* y) {
   __nv_bfloat16* base = po.ptr + pix * po.pitch + n;
+  if (nplanes == 2) {   // fp16 hi + pre-scaled fp16 lo
+    const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn((y[0] - f01.x) * ACCFLOW_FP16X2_SCALE, (y[1] - f01.y) * ACCFLOW_FP16X2_SCALE);
+    const __half2 l23 = __floats2half2_rn((y[2] - f23.x) * ACCFLOW_FP16X2_SCALE, (y[3] - f23.y) * ACCFLOW_FP16X2_SCALE);
+    *reinterpret_cast<uint2*>(base) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    *reinterpret_cast<uint2*>(base + po.plane_stride) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    return;
+  }
   const __nv_bfloat162 a01 = __floats2bfloat162_rn(y[0], y[1]), a23 = __floats2bfloat162_rn(y[2], y[3]);
   *reinterpret_cast<uint2*>(base) = make_uint2(*reinterpret_cast<const uint32_t*>(&a01), *reinterpret_cast<const uint32_t*>(&a23));
   if (nplanes > 1) {
@@ -196,15 +207,7 @@ __device__ __forceinline__ void store_planes4(const PlaneOut& po, int nplanes, l
   }
 }
 __device__ __forceinline__ void store_planes1(const PlaneOut& po, int nplanes, long long pix, int n, float y) {
-  __nv_bfloat16* base = po.ptr + pix * po.pitch + n;
-  const __nv_bfloat16 a = __float2bfloat16_rn(y);
-  base[0] = a;
-  if (nplanes > 1) {
-    const float r = y - __bfloat162float(a);
-    const __nv_bfloat16 b = __float2bfloat16_rn(r);
-    base[po.plane_stride] = b;
-    base[2 * po.plane_stride] = __float2bfloat16_rn(r - __bfloat162float(b));
-  }
+  store_planes(po.ptr + pix * po.pitch + n, po.plane_stride, nplanes, y);
 }
 
 // Persistent: grid = min(#tiles, #SMs); CTA c walks tiles c, c+grid, ... (tiles are N-major so that
@@ -287,7 +290,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   } else if (warp == 1) {
     // ================================ MMA issuer ==============================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, BN);
+      const uint32_t idesc = make_idesc(BM, BN, p.nprod == 3);
       int it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
         const int slot = lt & 1, use = lt >> 1;
@@ -308,14 +311,16 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             umma_bf16(acc_main, a0, w0, idesc, first_main);
             first_main = 1;
             if (p.nprod > 1) {
-              const uint64_t a1 = make_desc(a_base + A_PLANE_BYTES + koff), a2 = make_desc(a_base + 2 * A_PLANE_BYTES + koff);
-              const uint64_t w1 = make_desc(w_base + w_plane_bytes + koff), w2 = make_desc(w_base + 2 * w_plane_bytes + koff);
+              const uint64_t a1 = make_desc(a_base + A_PLANE_BYTES + koff), w1 = make_desc(w_base + w_plane_bytes + koff);
               umma_bf16(acc_corr, a0, w1, idesc, first_corr);
               first_corr = 1;
               umma_bf16(acc_corr, a1, w0, idesc, 1);
-              umma_bf16(acc_corr, a1, w1, idesc, 1);
-              umma_bf16(acc_corr, a0, w2, idesc, 1);
-              umma_bf16(acc_corr, a2, w0, idesc, 1);
+              if (p.nprod == 6) {
+                const uint64_t a2 = make_desc(a_base + 2 * A_PLANE_BYTES + koff), w2 = make_desc(w_base + 2 * w_plane_bytes + koff);
+                umma_bf16(acc_corr, a1, w1, idesc, 1);
+                umma_bf16(acc_corr, a0, w2, idesc, 1);
+                umma_bf16(acc_corr, a2, w0, idesc, 1);
+              }
             }
           }
           umma_commit(&bar_free[s]);  // smem of this stage is reusable once these MMAs retire
@@ -352,8 +357,9 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           if (p.nprod > 1) {
             float corr[16];
             tmem_ld16(lane_addr + BN + c, corr);
+            const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;   // fp16x2: lo planes carry 2^11
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] += corr[j];
+            for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
           }
           float4* d4 = reinterpret_cast<float4*>(stg + trow * PITCH);
 #pragma unroll
@@ -461,15 +467,7 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long rows,
   const long long r = i / k_fill;
   const int c = (int)(i - r * k_fill);
   const float v = c < k ? __ldg(x + r * ld + c) : 0.f;
-  const long long o = r * pitch + c;
-  const __nv_bfloat16 p0 = __float2bfloat16_rn(v);
-  out[o] = p0;
-  if (nplanes > 1) {
-    const float r1 = v - __bfloat162float(p0);
-    const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
-    out[plane_stride + o] = p1;
-    out[2 * plane_stride + o] = __float2bfloat16_rn(r1 - __bfloat162float(p1));
-  }
+  store_planes(out + r * pitch + c, plane_stride, nplanes, v);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -499,7 +497,7 @@ extern "C" int accflow_split_bf16_planes(const float* x, long long rows, int k, 
                                          long long plane_stride, int nplanes, void* out_planes, void* stream) {
   ACCFLOW_REQUIRE(x && out_planes && rows > 0 && k > 0 && ld >= k && k_fill >= k && pitch >= k_fill,
                   "split_bf16_planes: bad arguments");
-  ACCFLOW_REQUIRE(nplanes == 1 || nplanes == 3, "split_bf16_planes: nplanes must be 1 or 3");
+  ACCFLOW_REQUIRE(nplanes >= 1 && nplanes <= 3, "split_bf16_planes: nplanes must be 1 (bf16), 2 (fp16x2) or 3 (bf16x3)");
   tc::split_planes_kernel<<<cdiv(rows * k_fill, 256), 256, 0, (cudaStream_t)stream>>>(
       x, rows, k, ld, k_fill, pitch, plane_stride, nplanes, reinterpret_cast<__nv_bfloat16*>(out_planes));
   return launched("split_bf16_planes");
@@ -511,8 +509,8 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   const accflow_conv_desc& d = *dp;
   const accflow_tc_weights& w = *wp;
   const accflow_tc_io& io = *iop;
-  ACCFLOW_REQUIRE(nprod == 1 || nprod == 6, "conv2d_tc: nprod must be 1 (bf16) or 6 (bf16x3 split)");
-  ACCFLOW_REQUIRE(w.planes && aligned16(w.planes) && w.nplanes >= (nprod == 1 ? 1 : 3), "conv2d_tc: weight planes missing");
+  ACCFLOW_REQUIRE(nprod == 1 || nprod == 3 || nprod == 6, "conv2d_tc: nprod must be 1 (bf16), 3 (fp16x2 split) or 6 (bf16x3 split)");
+  ACCFLOW_REQUIRE(w.planes && aligned16(w.planes) && w.nplanes >= (nprod == 1 ? 1 : nprod == 3 ? 2 : 3), "conv2d_tc: weight planes missing");
   ACCFLOW_REQUIRE(w.k_pitch % 8 == 0 && w.k_pitch >= w.k && w.rows > 0 && w.t > 0, "conv2d_tc: bad weight geometry");
   ACCFLOW_REQUIRE(d.nsrc >= 1 && d.nsrc <= ACCFLOW_MAX_SRC, "conv2d_tc: nsrc=%d out of range", d.nsrc);
   ACCFLOW_REQUIRE(d.batch > 0 && d.in_h > 0 && d.in_w > 0 && d.kh > 0 && d.kw > 0 && d.stride > 0 && d.stride <= 2,
@@ -520,7 +518,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   ACCFLOW_REQUIRE(d.cout > 0 && d.cout <= w.rows, "conv2d_tc: cout=%d exceeds packed rows %d", d.cout, w.rows);
   tc::Params p;
   memset(&p, 0, sizeof(p));
-  const int nplanes = nprod == 1 ? 1 : 3;
+  const int nplanes = nprod == 1 ? 1 : nprod == 3 ? 2 : 3;
   int cin = 0;
   for (int s = 0; s < d.nsrc; ++s) {
     ACCFLOW_REQUIRE(d.src_c[s] > 0, "conv2d_tc: bad source %d", s);
@@ -597,7 +595,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
                                 (cuuint64_t)w.k_pitch * 2 * w.rows * w.t};
     const cuuint32_t box[4] = {(cuuint32_t)tc::KC, (cuuint32_t)bn, 1, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult cr = enc(&maps.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w.planes), gdim, gstr, box, estr,
+    CUresult cr = enc(&maps.w, nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w.planes), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ACCFLOW_REQUIRE(cr == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(weights) failed (%d)", (int)cr);
@@ -610,7 +608,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     const cuuint64_t gstr[4] = {pitchb, pitchb * d.in_w, pitchb * d.in_w * d.in_h, (cuuint64_t)io.src_plane_stride[s] * 2};
     const cuuint32_t box[5] = {(cuuint32_t)tc::KC, (cuuint32_t)(p.tw * d.stride), (cuuint32_t)(p.th * d.stride), 1, 1};
     const cuuint32_t estr[5] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1, 1};
-    CUresult cr = enc(&maps.a[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(io.src_planes[s]), gdim, gstr, box,
+    CUresult cr = enc(&maps.a[s], nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(io.src_planes[s]), gdim, gstr, box,
                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ACCFLOW_REQUIRE(cr == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(source %d) failed (%d)", s, (int)cr);

@@ -100,21 +100,28 @@ class PackedConv:
             self._as1x1 = pc
         return self._as1x1
 
-    def tc_weights(self) -> "L.TcWeights":
-        """bf16 planes [3][taps][cout][k_pitch] (w = p0 + p1 + p2) for accflow_conv2d_tc."""
+    def tc_weights(self, fp16x2: bool = False) -> "L.TcWeights":
+        """16-bit operand planes [planes][taps][cout][k_pitch] for accflow_conv2d_tc."""
         if self._tc is None:
+            self._tc = {}
+        if fp16x2 not in self._tc:
             taps = self.kh * self.kw
             pitch = (self.cin + 7) // 8 * 8
             wt = torch.zeros(taps, self.cout, pitch, device=self.w_oihw.device, dtype=F32)
             wt[:, :, : self.cin] = self.w_oihw.permute(2, 3, 0, 1).reshape(taps, self.cout, self.cin)
-            planes = split_planes_torch(wt)
-            tw = L.TcWeights(planes.data_ptr(), 3, self.cout, self.cin, pitch, taps)
-            self._tc = (tw, planes)
-        return self._tc[0]
+            planes = split_planes_torch(wt, fp16x2)
+            tw = L.TcWeights(planes.data_ptr(), planes.shape[0], self.cout, self.cin, pitch, taps)
+            self._tc[fp16x2] = (tw, planes)
+        return self._tc[fp16x2][0]
 
 
-def split_planes_torch(x: torch.Tensor) -> torch.Tensor:
-    """x (fp32) -> stacked bf16 planes p0, p1, p2 with x ~= p0 + p1 + p2 (one-off weight packing)."""
+def split_planes_torch(x: torch.Tensor, fp16x2: bool = False) -> torch.Tensor:
+    """x (fp32) -> stacked 16-bit planes (one-off weight packing): bf16 p0, p1, p2 with x ~= p0 + p1 + p2,
+    or fp16 (hi, lo * 2^11) when ``fp16x2``."""
+    if fp16x2:
+        hi = x.to(torch.float16)
+        lo = ((x - hi.float()) * 2048.0).to(torch.float16)
+        return torch.stack([hi, lo]).contiguous()
     p0 = x.to(torch.bfloat16)
     r1 = x - p0.float()
     p1 = r1.to(torch.bfloat16)
@@ -125,7 +132,9 @@ def split_planes_torch(x: torch.Tensor) -> torch.Tensor:
 class Kernels:
     """Thin typed wrappers over the C ABI.  One instance per device."""
 
-    MODES = ("fp32", "bf16x3", "bf16")
+    MODES = ("fp32", "bf16x3", "fp16x2", "bf16")
+    NPROD = {"bf16x3": 6, "fp16x2": 3, "bf16": 1}
+    NPLANES = {"bf16x3": 3, "fp16x2": 2, "bf16": 1, "fp32": 0}
 
     def __init__(self, device: torch.device, precision: str = "fp32"):
         assert precision in self.MODES, precision
@@ -159,7 +168,7 @@ class Kernels:
 
     @property
     def nplanes(self) -> int:
-        return 3 if self.precision == "bf16x3" else 1
+        return self.NPLANES[self.precision]
 
     def wrote(self, v: Optional[View]):
         """A non-tensor-core kernel wrote ``v``: its planes (if any exist) are stale."""
@@ -278,9 +287,8 @@ class Kernels:
                     written.append(tv)
                 else:
                     self.wrote(tv)
-            tw = tc_b if tc_b is not None else pc.tc_weights()
-            args = ("accflow_conv2d_tc", C.byref(d), C.byref(io), C.byref(tw), 6 if self.precision == "bf16x3" else 1,
-                    _stream())
+            tw = tc_b if tc_b is not None else pc.tc_weights(self.precision == "fp16x2")
+            args = ("accflow_conv2d_tc", C.byref(d), C.byref(io), C.byref(tw), self.NPROD[self.precision], _stream())
         else:
             args = ("accflow_conv2d_f32", C.byref(d), _stream())
             written = []
@@ -367,7 +375,7 @@ class Kernels:
             self.conv(_Gemm(K, N, Np), [a], out, alpha=alpha, weight_ptr=bt.data_ptr(), weight_batch_stride=K * Np,
                       use_affine=False)
             return
-        npl = 3 if self.precision == "bf16x3" else 1
+        npl = self.nplanes
         pitch = (K + 7) // 8 * 8
         planes = self.buf16(tag + ".bpl", npl, B, N, pitch)
         L.call("accflow_split_bf16_planes", b.ptr, B * N, K, b.ld, K, pitch, B * N * pitch, npl, planes.data_ptr(),
@@ -385,7 +393,7 @@ class Kernels:
             self.conv(_Gemm(K, N, N), [a], out, alpha=alpha, weight_ptr=b.ptr, weight_batch_stride=K * N,
                       residual=residual, use_affine=False)
             return
-        npl = 3 if self.precision == "bf16x3" else 1
+        npl = self.nplanes
         Kp = (K + 7) // 8 * 8
         bt = self.buf(tag + ".bt", B, N, Kp, zero=True)
         self.transpose(b, bt, Kp)

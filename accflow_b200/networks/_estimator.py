@@ -24,9 +24,12 @@ class FlowEstimatorBase(nn.Module):
             args.dropout = 0
         _tree.populate(self, S.gma_entries() if self._GMA else S.raft_entries())
         self._engines = {}
-        # arithmetic of the conv/GEMM kernels: "fp32" (FFMA, exact), "bf16x3" (tcgen05, bf16x3 split
-        # products = fp32-class), "bf16" (tcgen05, bf16 products = the reference's autocast class)
-        self.precision = os.environ.get("ACCFLOW_PRECISION", "bf16x3")
+        # arithmetic of the conv/GEMM kernels (activations are fp32 in HBM in every mode):
+        #   "fp16x2" tcgen05, every operand split into fp16 hi + scaled fp16 lo, 3 products: fp32-class
+        #            precision inside the fp16 range (the range of the reference's own autocast default)
+        #   "bf16x3" tcgen05, three bf16 planes, 6 products: fp32-class precision, fp32 range
+        #   "fp32"   FFMA kernels, exact;   "bf16" tcgen05, plain bf16 products (autocast class)
+        self.precision = os.environ.get("ACCFLOW_PRECISION", "fp16x2")
         # replay whole forwards as CUDA graphs (captured on the third call per input shape)
         self.use_cuda_graph = os.environ.get("ACCFLOW_GRAPH", "1") != "0"
 

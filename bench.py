@@ -41,8 +41,8 @@ def parse():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--ofe", default="raft", choices=["raft", "gma"])
-    ap.add_argument("--precision", default=os.environ.get("ACCFLOW_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
-                    help="conv/GEMM arithmetic: bf16x3 = tcgen05 split products (fp32-class, parity-gated at 1e-3 px)")
+    ap.add_argument("--precision", default=os.environ.get("ACCFLOW_PRECISION", "fp16x2"), choices=["fp32", "bf16x3", "fp16x2", "bf16"],
+                    help="conv/GEMM arithmetic: fp16x2 / bf16x3 = tcgen05 split products (fp32-class, parity-gated at 1e-3 px)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -243,8 +243,9 @@ def run_b200(args):
     peak = pk["bf16_tflops_sustained"]
     kname = {"fp32": "conv_f32_kernel (implicit-GEMM conv, exact-fp32 FFMA path)",
              "bf16x3": "conv_tc_kernel (tcgen05 implicit-GEMM conv, bf16x3 split: 6 MMAs per algorithmic MAC)",
+             "fp16x2": "conv_tc_kernel (tcgen05 implicit-GEMM conv, fp16x2 split: 3 MMAs per algorithmic MAC)",
              "bf16": "conv_tc_kernel (tcgen05 implicit-GEMM conv, bf16 products)"}[args.precision]
-    issued = achieved * (6 if args.precision == "bf16x3" else 1)
+    issued = achieved * {"bf16x3": 6, "fp16x2": 3}.get(args.precision, 1)
     traffic, traffic_note = None, None
     tfile = os.path.join(ROOT, "profiles", f"r1_conv_tc_zr_{args.precision}_ncu_full.json")
     if os.path.exists(tfile):
@@ -266,7 +267,7 @@ def run_b200(args):
         line = {"metric": "long-range flow pairs/sec", "value": value, "unit": "flows/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
-                "dtype": {"fp32": "f32", "bf16x3": "bf16x3", "bf16": "bf16"}[args.precision], "data": "synthetic",
+                "dtype": {"fp32": "f32", "bf16x3": "bf16x3", "fp16x2": "fp16x2", "bf16": "bf16"}[args.precision], "data": "synthetic",
                 "config": workload_config(args, b), "clips_per_s": value / FLOWS_PER_CLIP,
                 "pair_evals_per_s": value / FLOWS_PER_CLIP * 11, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "flows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

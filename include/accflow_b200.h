@@ -119,7 +119,9 @@ typedef struct accflow_tc_io {
 /* Same contract as accflow_conv2d_f32 (the descriptor's fp32 `src` pointers, `weight` and
  * `cout_pad` are ignored) on the 5th-gen tensor cores: tcgen05.mma with TMEM accumulators, both
  * operands by TMA (im2col boxes with zero fill for the activations).
- * nprod = 1: bf16 products; nprod = 6: bf16x3 split products (fp32-class accuracy). */
+ * nprod = 1: bf16 products (1 plane); nprod = 6: bf16x3 split products (3 bf16 planes, fp32-class);
+ * nprod = 3: fp16x2 split products (2 fp16 planes: hi, and lo pre-scaled by 2^11; fp32-class for
+ * operands inside the fp16 range). */
 ACCFLOW_API int accflow_conv2d_tc(const accflow_conv_desc* d, const accflow_tc_io* io, const accflow_tc_weights* w,
                                   int nprod, void* stream);
 

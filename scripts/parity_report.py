@@ -31,7 +31,7 @@ def md(a, b):
 
 
 oracle_cache = {}
-for precision in ("fp32", "bf16x3", "bf16"):
+for precision in ("fp32", "bf16x3", "fp16x2", "bf16"):
     for kind in ("raft", "gma"):
         m = build(kind, precision)
         i1, i2, finit = cases.pair_case()

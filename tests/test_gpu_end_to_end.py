@@ -101,7 +101,7 @@ def test_clip_vs_oracle_and_epe():
         assert float((a - b).abs().max()) < EPE_TOL_PX
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "fp16x2"])
 def test_cuda_graph_replay_matches_eager_and_oracle(golden, precision):
     """Third and later calls replay a captured CUDA graph; results must not change."""
     g, _ = golden
@@ -125,6 +125,17 @@ def test_cuda_graph_replay_matches_eager_and_oracle(golden, precision):
         assert maxdiff(a, b.cpu()) == 0.0
     for i, f in enumerate(outs[-1]):
         assert maxdiff(f, g[f"acc+raft.flow{i}"]) < FLOW_TOL_PX
+
+
+@pytest.mark.parametrize("precision", ["fp16x2", "bf16x3"])
+@pytest.mark.parametrize("kind", ["raft", "gma"])
+def test_split_precision_modes_meet_fp32_bar(golden, kind, precision):
+    """Both tensor-core split modes are fp32-class: same 1e-3 px bar as the exact mode."""
+    g, _ = golden
+    m = build(kind)
+    m.precision = precision
+    i1, i2, finit = cases.pair_case()
+    assert maxdiff(m(i1.cuda(), i2.cuda(), iters=12, flow_init=finit.cuda()), g[f"{kind}.flow_up"]) < FLOW_TOL_PX
 
 
 def test_exact_fp32_mode_matches_reference(golden):

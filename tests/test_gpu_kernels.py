@@ -20,7 +20,7 @@ def K():
 
 
 # tolerance (relative to the output scale ~1) per arithmetic mode of the conv/GEMM kernels
-PRECISIONS = {"fp32": 2e-5, "bf16x3": 2e-5, "bf16": 6e-2}
+PRECISIONS = {"fp32": 2e-5, "bf16x3": 2e-5, "fp16x2": 2e-5, "bf16": 6e-2}
 
 
 @pytest.fixture(scope="module", params=list(PRECISIONS))
