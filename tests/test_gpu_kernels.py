@@ -138,6 +138,28 @@ def test_gru_epilogues(KP):
     assert maxdiff(hv.t.permute(0, 3, 1, 2), ref) < tol
 
 
+@pytest.mark.parametrize("precision", ["fp16x2", "bf16x3", "bf16"])
+def test_cta_pair_kernel_matches_torch(precision, monkeypatch):
+    """The opt-in cta_group::2 variant (ACCFLOW_TC_2CTA): M=256 MMAs over a 2-CTA cluster, odd tile
+    counts (phantom tile), multi-source K, GRU epilogue."""
+    from accflow_b200 import _lib as L
+    from accflow_b200.engine import Kernels, PackedConv, View
+    monkeypatch.setenv("ACCFLOW_TC_2CTA", "2")
+    Kp = Kernels(torch.device("cuda:0"), precision)
+    tol = PRECISIONS[precision]
+    g = torch.Generator().manual_seed(21)
+    for (B, cins, H, W, cout, kh, kw) in ((3, [128, 128, 128], 24, 16, 256, 1, 5), (1, [256], 17, 19, 192, 3, 3)):
+        xs = [torch.randn(B, c, H, W, generator=g) for c in cins]
+        w = torch.randn(cout, sum(cins), kh, kw, generator=g) / math.sqrt(sum(cins) * kh * kw)
+        b = torch.randn(cout, generator=g)
+        ref = torch.relu(F.conv2d(torch.cat(xs, 1), w, b, padding=(kh // 2, kw // 2)))
+        out = torch.empty(B, H, W, cout, device="cuda")
+        Kp.conv(PackedConv([dev(w)], [dev(b)], 1, (kh // 2, kw // 2)), [View(dev(nhwc(x))) for x in xs], View(out),
+                act=L.ACT_RELU)
+        torch.cuda.synchronize()
+        assert maxdiff(out.permute(0, 3, 1, 2), ref) < tol
+
+
 @pytest.mark.parametrize("cfg", [(3, 2, 64, True, 40, 56), (2, 1, 128, False, 18, 21)])
 def test_conv_smallc(K, cfg):
     from accflow_b200 import _lib as L
