@@ -61,6 +61,7 @@ SIGNATURES = {
     "accflow_nhwc_transpose_f32": [fp, i, i, i, i, fp, i, fp],
     "accflow_corr_pool_f32": [fp, ll, i, i, fp, fp, fp, fp],
     "accflow_corr_lookup_f32": [fp, fp, fp, fp, i, i, i, i, fp, fp, i, fp, fp, i, fp, i, ll, fp, i, ll, i, fp],
+    "accflow_stem_patch_planes": [fp, i, i, i, fp, i, ll, i, fp],
     "accflow_flow_patch_f32": [fp, i, i, i, fp, i, fp, i, ll, i, fp],
     "accflow_conv3x3_smallcout_f32": [fp, i, i, i, i, i, fp, fp, fp, i, i, fp, i, fp],
     "accflow_coords_init_f32": [fp, i, i, i, fp, fp],

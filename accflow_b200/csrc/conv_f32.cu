@@ -422,6 +422,54 @@ __global__ void __launch_bounds__(256) stem7x7_kernel(const float* __restrict__ 
   }
 }
 
+// ---- 7x7 / stride-2 stem patches: NCHW image [N,3,H,W] -> operand planes [planes][N][H/2][W/2][pitch] with
+// channel k = (ky*7+kx)*3 + c = image(c, 2y-3+ky, 2x-3+kx) (zero outside, zero for k >= 147).  The stem conv
+// (raft/extractor.py:163-167) then runs as a K=147 1x1 conv on the tensor-core kernel.  Planes only (no fp32
+// copy): one thread writes two consecutive channels (32-bit stores).
+__global__ void __launch_bounds__(256) stem_patch_kernel(const float* __restrict__ img, int batch, int H, int W,
+                                                         __nv_bfloat16* __restrict__ out_pl, int pitch,
+                                                         long long pl_stride, int nplanes) {
+  const int oh = (H + 1) / 2, ow = (W + 1) / 2;
+  const int kp = pitch >> 1;                                    // channel pairs per pixel
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)batch * oh * ow * kp;
+  if (i >= total) return;
+  const long long pix = i / kp;
+  const int k0 = (int)(i - pix * kp) * 2;
+  const int b = (int)(pix / ((long long)oh * ow));
+  const int r = (int)(pix - (long long)b * oh * ow);
+  const int oy = r / ow, ox = r - oy * ow;
+  float v[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = k0 + e;
+    v[e] = 0.f;
+    if (k < 147) {
+      const int tap = k / 3, c = k - tap * 3;
+      const int iy = 2 * oy - 3 + tap / 7, ix = 2 * ox - 3 + tap % 7;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[e] = __ldg(img + ((long long)(b * 3 + c) * H + iy) * W + ix);
+    }
+  }
+  __nv_bfloat16* dst = out_pl + pix * pitch + k0;
+  if (nplanes == 2) {
+    const __half2 hi = __floats2half2_rn(v[0], v[1]);
+    const float2 hf = __half22float2(hi);
+    const __half2 lo = __floats2half2_rn((v[0] - hf.x) * ACCFLOW_FP16X2_SCALE, (v[1] - hf.y) * ACCFLOW_FP16X2_SCALE);
+    *reinterpret_cast<__half2*>(dst) = hi;
+    *reinterpret_cast<__half2*>(dst + pl_stride) = lo;
+  } else {
+    const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]);
+    *reinterpret_cast<__nv_bfloat162*>(dst) = p0;
+    if (nplanes > 1) {
+      const float r0 = v[0] - __bfloat162float(p0.x), r1 = v[1] - __bfloat162float(p0.y);
+      const __nv_bfloat162 p1 = __floats2bfloat162_rn(r0, r1);
+      *reinterpret_cast<__nv_bfloat162*>(dst + pl_stride) = p1;
+      *reinterpret_cast<__nv_bfloat162*>(dst + 2 * pl_stride) =
+          __floats2bfloat162_rn(r0 - __bfloat162float(p1.x), r1 - __bfloat162float(p1.y));
+    }
+  }
+}
+
 // ---- 7x7 flow patches: flow [B,h,w,2] -> [B,h,w,ld] with channel (ky*7+kx)*2 + c = flow(y+ky-3, x+kx-3, c),
 // zero outside the map and for channels 98..ld-1.  Turns the 2-channel 7x7 convs (raft/update.py:85,
 // AccFlow_.py:51) into 1x1 convs with K = 98 for the tensor-core kernel.
@@ -587,4 +635,16 @@ extern "C" int accflow_flow_patch_f32(const float* flow, int batch, int h, int w
                                                                         reinterpret_cast<__nv_bfloat16*>(out_planes),
                                                                         pl_pitch, pl_stride, nplanes);
   return launched("flow_patch");
+}
+
+extern "C" int accflow_stem_patch_planes(const float* img_nchw, int batch, int H, int W, void* out_planes, int pitch,
+                                         long long pl_stride, int nplanes, void* stream) {
+  ACCFLOW_REQUIRE(img_nchw && out_planes && batch > 0 && H > 0 && W > 0, "stem_patch: bad arguments");
+  ACCFLOW_REQUIRE(pitch >= 148 && pitch % 8 == 0 && pl_stride % 2 == 0 && nplanes >= 1 && nplanes <= 3 &&
+                      (reinterpret_cast<uintptr_t>(out_planes) & 3u) == 0, "stem_patch: pitch must be >= 148 and a multiple of 8");
+  const long long total = (long long)batch * ((H + 1) / 2) * ((W + 1) / 2) * (pitch / 2);
+  stem_patch_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(img_nchw, batch, H, W,
+                                                                        reinterpret_cast<__nv_bfloat16*>(out_planes), pitch,
+                                                                        pl_stride, nplanes);
+  return launched("stem_patch");
 }

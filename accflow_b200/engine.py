@@ -53,6 +53,14 @@ class View:
         return self.b * self.h * self.w
 
 
+class PlanesOnly:
+    """Shape carrier for a conv source that exists only as operand planes (no fp32 tensor)."""
+    __slots__ = ("b", "h", "w", "c", "ld", "ptr")
+
+    def __init__(self, b, h, w, c, ld):
+        self.b, self.h, self.w, self.c, self.ld, self.ptr = b, h, w, c, ld, 0
+
+
 class PackedConv:
     """Weights of one conv in the kernel layout [kh*kw][cin][cout_pad] + epilogue vectors."""
 
@@ -233,7 +241,7 @@ class Kernels:
              act_split=0, act2=L.ACT_NONE, out2: Optional[View] = None, residual: Optional[View] = None,
              post_relu=False, epilogue=L.EPI_STORE, h: Optional[View] = None, z: Optional[View] = None,
              weight_ptr: Optional[int] = None, weight_batch_stride=0, cout=None, cout_pad=None,
-             use_affine=True, tc_b: Optional["L.TcWeights"] = None):
+             use_affine=True, tc_b: Optional["L.TcWeights"] = None, tc_src_planes=None):
         d = L.ConvDesc()
         cin = 0
         for k, s in enumerate(srcs):
@@ -268,7 +276,8 @@ class Kernels:
         if tc:
             io = L.TcIO()
             for k, sv in enumerate(srcs):
-                io.src_planes[k], io.src_pitch[k], io.src_plane_stride[k] = self.ensure_planes(sv)
+                io.src_planes[k], io.src_pitch[k], io.src_plane_stride[k] = (
+                    tc_src_planes[k] if tc_src_planes is not None else self.ensure_planes(sv))
             written = []
             if epilogue == L.EPI_STORE:
                 targets = (("out", out), ("out2", out2 if act_split else None))
@@ -504,11 +513,25 @@ class EncoderPlan:
         h2, w2 = (H + 1) // 2, (W + 1) // 2
         x = k.view(tag + ".stem", n, h2, w2, 64)
         b0 = 0
-        for im in images:
-            assert im.dtype == F32 and im.is_contiguous() and im.shape[1] == 3
-            nb = int(im.shape[0])
-            k.conv_smallc(im.data_ptr(), True, nb, 3, H, W, self.stem, relu, x.rows(b0, b0 + nb))
-            b0 += nb
+        if k.tc:
+            # im2col (7x7/s2, K=147) straight into operand planes, then a 1x1 conv on the tensor cores
+            pitch = 152
+            patches = k.buf16("stem.patches", 3, n, h2, w2, pitch)      # shared by the encoders (used back to back)
+            stride_pl = n * h2 * w2 * pitch
+            for im in images:
+                assert im.dtype == F32 and im.is_contiguous() and im.shape[1] == 3
+                nb = int(im.shape[0])
+                L.call("accflow_stem_patch_planes", im.data_ptr(), nb, H, W,
+                       patches.data_ptr() + 2 * b0 * h2 * w2 * pitch, pitch, stride_pl, k.nplanes, _stream())
+                b0 += nb
+            k.conv(self.stem.as_1x1(), [PlanesOnly(n, h2, w2, 147, pitch)], x, act=relu,
+                   tc_src_planes=[(patches.data_ptr(), pitch, stride_pl)])
+        else:
+            for im in images:
+                assert im.dtype == F32 and im.is_contiguous() and im.shape[1] == 3
+                nb = int(im.shape[0])
+                k.conv_smallc(im.data_ptr(), True, nb, 3, H, W, self.stem, relu, x.rows(b0, b0 + nb))
+                b0 += nb
         if inst:
             k.instnorm(x, True, None, False, x)
         for bi, blk in enumerate(self.blocks):

@@ -148,6 +148,12 @@ ACCFLOW_API int accflow_flow_patch_f32(const float* flow, int batch, int h, int 
                                        void* out_planes, int pl_pitch, long long pl_plane_stride, int nplanes,
                                        void* stream);
 
+/* 7x7 / stride-2 im2col of NCHW (N,3,H,W) images straight into operand planes
+ * [nplanes][N][H/2][W/2][pitch], channel (ky*7+kx)*3 + c: the BasicEncoder stem (raft/extractor.py:163-167,
+ * 209) then runs as a K=147 1x1 conv on the tensor-core kernel. */
+ACCFLOW_API int accflow_stem_patch_planes(const float* img_nchw, int batch, int H, int W, void* out_planes, int pitch,
+                                          long long pl_plane_stride, int nplanes, void* stream);
+
 /* 3x3 / stride 1 / pad 1 convolution with cout <= 4 (FlowHead.conv2 raft/update.py:10,
  * FlowDecoder.flow[2] AccFlow_.py:19, Blending.mask[2] AccFlow_.py:118), fused affine + activation.
  * weight: packed [9][cin][4] fp32 (the accflow_conv2d_f32 layout with cout_pad = 4). */
