@@ -289,11 +289,9 @@ __global__ void __launch_bounds__(256) conv3x3_smallcout_kernel(const float* __r
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)batch * h * w;
-  const long long first = ((long long)blockIdx.x * 8 + warp) * pix_per_warp;
   const int hw = h * w;
-  for (int i = 0; i < pix_per_warp; ++i) {
-    const long long pix = first + i;
-    if (pix >= total) break;
+  // blocks are persistent (weights staged once); warps stride over the pixels
+  for (long long pix = (long long)blockIdx.x * 8 + warp; pix < total; pix += (long long)gridDim.x * 8) {
     const int b = (int)(pix / hw), pl = (int)(pix - (long long)b * hw);
     const int py = pl / w, px = pl - py * w;
     float4 v[9][CPL];                     // all taps in flight before the first FMA
@@ -609,8 +607,12 @@ static int launch_smallcout(const float* x, int x_ld, int batch, int h, int w, c
     cfg_dev = dev;
   }
   const long long total = (long long)batch * h * w;
-  const int ppw = 4;
-  kern<<<cdiv(total, 8 * ppw), 256, smem, st>>>(x, x_ld, batch, h, w, weight, scale, shift, cout, act, out, out_ld, ppw);
+  static thread_local int sms = 0;
+  if (sms == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  const int blocks_per_sm = smem > 40 * 1024 ? 5 : 8;
+  const long long want = cdiv(total, 8);
+  const int grid = (int)(want < (long long)sms * blocks_per_sm ? want : (long long)sms * blocks_per_sm);
+  kern<<<grid, 256, smem, st>>>(x, x_ld, batch, h, w, weight, scale, shift, cout, act, out, out_ld, 0);
   return launched("conv3x3_smallcout");
 }
 
