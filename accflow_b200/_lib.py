@@ -70,6 +70,7 @@ SIGNATURES = {
     "accflow_downflow8_f32": [fp, i, i, i, fp, fp],
     "accflow_warp_occ_f32": [fp, i, fp, i, fp, i, i, i, i, fp, i, fp, i, fp],
     "accflow_backwarp_nchw_f32": [fp, fp, i, i, i, i, fp, fp],
+    "accflow_epe_metrics_f32": [fp, fp, fp, i, i, i, fp, fp, fp],
     "accflow_deform_gather_f32": [fp, i, fp, i, i, i, i, i, fp, fp],
     "accflow_blend_f32": [fp, fp, fp, i, ll, i, fp, fp],
     "accflow_softmax_rows_f32": [fp, ll, i, fp],

@@ -400,6 +400,59 @@ __global__ void backwarp_nchw_kernel(const float* __restrict__ img, const float*
     out[((long long)b * c + ch) * hw + pl] = bilinear_zeros(img + ((long long)b * c + ch) * hw, h, w, x, y);
 }
 
+// =============================== fused evaluation metric ====================================
+// test_cvo.py:53-101 in one pass: occ_bw = |bflow + warp(fflow, bflow)| > 0.01 (|fflow| + |bflow|) + 0.5,
+// diff = |pred - bflow|; per clip: sum(diff), sum(diff * occ), sum(occ).  Deterministic: per-block
+// partials, then one block per clip adds them in a fixed order.
+__global__ void __launch_bounds__(256) epe_partial_kernel(const float* __restrict__ pred, const float* __restrict__ bflow,
+                                                          const float* __restrict__ fflow, int h, int w,
+                                                          float* __restrict__ partial) {
+  __shared__ float red[3][8];
+  const int b = blockIdx.y, hw = h * w;
+  const int pl = blockIdx.x * 256 + threadIdx.x;
+  float d = 0.f, docc = 0.f, occ = 0.f;
+  if (pl < hw) {
+    const float* bf = bflow + (long long)b * 2 * hw;
+    const float* ff = fflow + (long long)b * 2 * hw;
+    const float* pr = pred + (long long)b * 2 * hw;
+    const float bx = __ldg(bf + pl), by = __ldg(bf + hw + pl);
+    const float fx = __ldg(ff + pl), fy = __ldg(ff + hw + pl);
+    const float mag = sqrtf(fx * fx + fy * fy) + sqrtf(bx * bx + by * by);
+    const int py = pl / w, px = pl - py * w;
+    const float sx = grid_roundtrip(__fadd_rn((float)px, bx), w), sy = grid_roundtrip(__fadd_rn((float)py, by), h);
+    const float wx = bx + bilinear_zeros(ff, h, w, sx, sy), wy = by + bilinear_zeros(ff + hw, h, w, sx, sy);
+    occ = sqrtf(wx * wx + wy * wy) > 0.01f * mag + 0.5f ? 1.f : 0.f;
+    const float ex = __ldg(pr + pl) - bx, ey = __ldg(pr + hw + pl) - by;
+    d = sqrtf(ex * ex + ey * ey);
+    docc = d * occ;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    d += __shfl_xor_sync(0xffffffffu, d, o);
+    docc += __shfl_xor_sync(0xffffffffu, docc, o);
+    occ += __shfl_xor_sync(0xffffffffu, occ, o);
+  }
+  const int wid = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[0][wid] = d; red[1][wid] = docc; red[2][wid] = occ; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[threadIdx.x][k];
+    partial[((long long)b * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;
+  }
+}
+
+__global__ void epe_finalize_kernel(const float* __restrict__ partial, int nblocks, int hw, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  double s[3] = {0.0, 0.0, 0.0};
+  for (int k = 0; k < nblocks; ++k)
+    for (int j = 0; j < 3; ++j) s[j] += (double)partial[((long long)b * nblocks + k) * 3 + j];
+  out[b * 3 + 0] = (float)(s[0] / hw);                       // epe_all
+  out[b * 3 + 1] = (float)(s[1] / s[2]);                     // epe_occ  (0/0 -> NaN, as the reference)
+  out[b * 3 + 2] = (float)((s[0] - s[1]) / (hw - s[2]));     // epe_vis
+}
+
 // =============================== deformable gather ==========================================
 // One warp per pixel; 9 modulated bilinear taps -> col[pix][tap*c + ch].
 __global__ void __launch_bounds__(256) deform_gather_kernel(const float* __restrict__ x, int x_ld,
@@ -623,6 +676,16 @@ extern "C" int accflow_backwarp_nchw_f32(const float* img, const float* flow, in
   ACCFLOW_REQUIRE(img && flow && out && batch > 0 && c > 0 && h > 1 && w > 1, "backwarp: bad arguments");
   backwarp_nchw_kernel<<<cdiv((long long)batch * h * w, 256), 256, 0, ST>>>(img, flow, batch, c, h, w, out);
   return launched("backwarp_nchw");
+}
+
+extern "C" int accflow_epe_metrics_f32(const float* pred, const float* bflow, const float* fflow, int batch, int h, int w,
+                                       float* partial, float* out, void* stream) {
+  ACCFLOW_REQUIRE(pred && bflow && fflow && partial && out && batch > 0 && h > 1 && w > 1, "epe_metrics: bad arguments");
+  const int nblocks = cdiv((long long)h * w, 256);
+  epe_partial_kernel<<<dim3(nblocks, batch), 256, 0, ST>>>(pred, bflow, fflow, h, w, partial);
+  if (int e = launched("epe_partial")) return e;
+  epe_finalize_kernel<<<batch, 32, 0, ST>>>(partial, nblocks, h * w, out);
+  return launched("epe_finalize");
 }
 
 extern "C" int accflow_deform_gather_f32(const float* x, int x_ld, const float* offmask, int om_ld, int batch,

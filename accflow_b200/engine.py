@@ -813,72 +813,71 @@ class AccFlowEngine:
         h, w = H // 8, W // 8
         P = h * w
         npair = int(flows.shape[0]) // b
-        if True:
-            lr = k.buf("acc.lr", npair * b, P, 2)                       # [dflow | flow_ini | (F2n)]
-            L.call("accflow_downflow8_f32", flows.data_ptr(), npair * b, H, W, lr.data_ptr(), s())
-            fin = k.buf("acc.fin", 3 * b, P, 2)                          # encoder order: flow_ini, dflow, F2n
-            fin[0:b].copy_(lr[b:2 * b])
-            fin[b:2 * b].copy_(lr[0:b])
-            if F2n is None:
-                fin[2 * b:].copy_(lr[2 * b:])
-            else:
-                fin[2 * b:].copy_(F2n.to(device=dev, dtype=F32).permute(0, 2, 3, 1).reshape(b, P, 2))
-            dflow, flow_ini = fin[b:2 * b], fin[0:b]
-            # FlowEncoder (AccFlow_.py:56-65)
-            e1 = k.view("acc.e1", 3 * b, h, w, 128)
-            e2 = k.view("acc.e2", 3 * b, h, w, 256)
-            enc = k.view("acc.enc", 3 * b, h, w, 128)
-            k.flow_conv7("acc.fe", fin, 3 * b, h, w, self.fe1, e1)
-            k.conv(self.fe2, [e1], e2, act=L.ACT_RELU)
-            k.conv(self.fe3, [e2], enc)
-            f_ini, df, f = enc.rows(0, b), enc.rows(b, 2 * b), enc.rows(2 * b, 3 * b)
-            # occlusion + error maps (getOcc, AccFlow_.py:127-135,194,197)
-            occ = k.view("acc.occ", b, h, w, 1)
-            emap = k.view("acc.emap", b, h, w, 128)
-            L.call("accflow_warp_occ_f32", c1.ptr, c1.ld, c2.ptr, c2.ld, dflow.data_ptr(), b, h, w, 128, occ.ptr, 1,
-                   None, 0, s())
-            L.call("accflow_warp_occ_f32", c1.ptr, c1.ld, cn.ptr, cn.ld, flow_ini.data_ptr(), b, h, w, 128, None, 0,
-                   emap.ptr, emap.ld, s())
-            k.wrote(occ)
-            k.wrote(emap)
-            # AccPlus (AccFlow_.py:97-109)
-            t256 = k.view("acc.t256", b, h, w, 256)
-            x1 = k.view("acc.x1", b, h, w, 128)
-            x2 = k.view("acc.x2", b, h, w, 128)
-            om = k.view("acc.om", b, h, w, 28)
-            col = k.buf("acc.col", b, P, 9 * 128)
-            fdc = k.view("acc.fdc", b, h, w, 128)
-            k.conv(self.a10, [df, f, occ], t256, act=L.ACT_RELU)
-            k.conv(self.a12, [t256], x1)
-            k.conv(self.a20, [x1, c1], t256, act=L.ACT_RELU)
-            k.conv(self.a22, [t256], x2, act=L.ACT_RELU)
-            k.conv(self.a24, [x2], om.ch(0, 27))
-            L.call("accflow_deform_gather_f32", f.ptr, f.ld, om.ptr, om.ld, b, h, w, 128, col.data_ptr(), s())
-            colv = View(col.view(b, h, w, 9 * 128))
-            k.wrote(colv)
-            k.conv(self.dcn, [colv], fdc)
-            k.conv(self.a30, [fdc, df, occ], t256, act=L.ACT_RELU)
-            k.conv(self.a32, [t256], x1)
-            k.conv(self.a40, [x1, c1, fdc, df], t256, act=L.ACT_RELU)
-            k.conv(self.a42, [t256], x2, act=L.ACT_RELU)
-            f_acc = k.view("acc.facc", b, h, w, 128)
-            k.conv(self.a44, [x2], f_acc)
-            # Blending (AccFlow_.py:122-124)
-            m = k.view("acc.m", b, h, w, 1)
-            k.conv(self.bl0, [emap], t256, act=L.ACT_RELU)
-            k.conv_smallcout(self.bl2, t256, m, act=L.ACT_SIGMOID)
-            fuse = k.view("acc.fuse", b, h, w, 128)
-            L.call("accflow_blend_f32", f_ini.ptr, f_acc.ptr, m.ptr, 1, b * P, 128, fuse.ptr, s())
-            k.wrote(fuse)
-            # FlowDecoder (AccFlow_.py:40-45)
-            small = torch.empty(b, h, w, 2, device=dev, dtype=F32)
-            k.conv(self.df0, [fuse], t256, act=L.ACT_RELU)
-            k.conv_smallcout(self.df2, t256, View(small))
-            mask = k.view("acc.mask", b, h, w, 576)
-            k.conv(self.dm0, [fuse], t256, act=L.ACT_RELU)
-            k.conv(self.dm2, [t256], mask)
-            out = torch.empty(b, 2, H, W, device=dev, dtype=F32)
-            L.call("accflow_convex_upsample_f32", small.data_ptr(), 2, 0, mask.ptr, mask.ld, b, h, w, out.data_ptr(), s())
+        lr = k.buf("acc.lr", npair * b, P, 2)                       # [dflow | flow_ini | (F2n)]
+        L.call("accflow_downflow8_f32", flows.data_ptr(), npair * b, H, W, lr.data_ptr(), s())
+        fin = k.buf("acc.fin", 3 * b, P, 2)                          # encoder order: flow_ini, dflow, F2n
+        fin[0:b].copy_(lr[b:2 * b])
+        fin[b:2 * b].copy_(lr[0:b])
+        if F2n is None:
+            fin[2 * b:].copy_(lr[2 * b:])
+        else:
+            fin[2 * b:].copy_(F2n.to(device=dev, dtype=F32).permute(0, 2, 3, 1).reshape(b, P, 2))
+        dflow, flow_ini = fin[b:2 * b], fin[0:b]
+        # FlowEncoder (AccFlow_.py:56-65)
+        e1 = k.view("acc.e1", 3 * b, h, w, 128)
+        e2 = k.view("acc.e2", 3 * b, h, w, 256)
+        enc = k.view("acc.enc", 3 * b, h, w, 128)
+        k.flow_conv7("acc.fe", fin, 3 * b, h, w, self.fe1, e1)
+        k.conv(self.fe2, [e1], e2, act=L.ACT_RELU)
+        k.conv(self.fe3, [e2], enc)
+        f_ini, df, f = enc.rows(0, b), enc.rows(b, 2 * b), enc.rows(2 * b, 3 * b)
+        # occlusion + error maps (getOcc, AccFlow_.py:127-135,194,197)
+        occ = k.view("acc.occ", b, h, w, 1)
+        emap = k.view("acc.emap", b, h, w, 128)
+        L.call("accflow_warp_occ_f32", c1.ptr, c1.ld, c2.ptr, c2.ld, dflow.data_ptr(), b, h, w, 128, occ.ptr, 1,
+               None, 0, s())
+        L.call("accflow_warp_occ_f32", c1.ptr, c1.ld, cn.ptr, cn.ld, flow_ini.data_ptr(), b, h, w, 128, None, 0,
+               emap.ptr, emap.ld, s())
+        k.wrote(occ)
+        k.wrote(emap)
+        # AccPlus (AccFlow_.py:97-109)
+        t256 = k.view("acc.t256", b, h, w, 256)
+        x1 = k.view("acc.x1", b, h, w, 128)
+        x2 = k.view("acc.x2", b, h, w, 128)
+        om = k.view("acc.om", b, h, w, 28)
+        col = k.buf("acc.col", b, P, 9 * 128)
+        fdc = k.view("acc.fdc", b, h, w, 128)
+        k.conv(self.a10, [df, f, occ], t256, act=L.ACT_RELU)
+        k.conv(self.a12, [t256], x1)
+        k.conv(self.a20, [x1, c1], t256, act=L.ACT_RELU)
+        k.conv(self.a22, [t256], x2, act=L.ACT_RELU)
+        k.conv(self.a24, [x2], om.ch(0, 27))
+        L.call("accflow_deform_gather_f32", f.ptr, f.ld, om.ptr, om.ld, b, h, w, 128, col.data_ptr(), s())
+        colv = View(col.view(b, h, w, 9 * 128))
+        k.wrote(colv)
+        k.conv(self.dcn, [colv], fdc)
+        k.conv(self.a30, [fdc, df, occ], t256, act=L.ACT_RELU)
+        k.conv(self.a32, [t256], x1)
+        k.conv(self.a40, [x1, c1, fdc, df], t256, act=L.ACT_RELU)
+        k.conv(self.a42, [t256], x2, act=L.ACT_RELU)
+        f_acc = k.view("acc.facc", b, h, w, 128)
+        k.conv(self.a44, [x2], f_acc)
+        # Blending (AccFlow_.py:122-124)
+        m = k.view("acc.m", b, h, w, 1)
+        k.conv(self.bl0, [emap], t256, act=L.ACT_RELU)
+        k.conv_smallcout(self.bl2, t256, m, act=L.ACT_SIGMOID)
+        fuse = k.view("acc.fuse", b, h, w, 128)
+        L.call("accflow_blend_f32", f_ini.ptr, f_acc.ptr, m.ptr, 1, b * P, 128, fuse.ptr, s())
+        k.wrote(fuse)
+        # FlowDecoder (AccFlow_.py:40-45)
+        small = torch.empty(b, h, w, 2, device=dev, dtype=F32)
+        k.conv(self.df0, [fuse], t256, act=L.ACT_RELU)
+        k.conv_smallcout(self.df2, t256, View(small))
+        mask = k.view("acc.mask", b, h, w, 576)
+        k.conv(self.dm0, [fuse], t256, act=L.ACT_RELU)
+        k.conv(self.dm2, [t256], mask)
+        out = torch.empty(b, 2, H, W, device=dev, dtype=F32)
+        L.call("accflow_convex_upsample_f32", small.data_ptr(), 2, 0, mask.ptr, mask.ld, b, h, w, out.data_ptr(), s())
         return small.permute(0, 3, 1, 2).contiguous(), out
 
     def forward(self, images: List[torch.Tensor], iters=12, graph=False) -> List[torch.Tensor]:

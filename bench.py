@@ -174,11 +174,10 @@ def run_b200(args):
     host_out = torch.empty(b, 2, args.size, args.size).pin_memory()
     dev_imgs = [t.to(dev) for t in batch["imgs"]]
     bflow, fflow = batch["bflows"][-1].to(dev), batch["fflows"][-1].to(dev)
-    occ_bw, _ = metrics.calc_occ_mask(bflow, fflow)
 
     def step_resident():
         flows = model(images=dev_imgs, test_mode=False)
-        epe = torch.stack(metrics.cal_epe(flows[-1], bflow, occ_bw), 1)        # (b,3)
+        epe = metrics.clip_epe(flows[-1], bflow, fflow)                       # (b,3): fused occlusion mask + EPE kernel
         return gather_clip_metrics(epe, n_clips, rank, world)                 # the only collective: metric gather
 
     def step_e2e():
@@ -262,6 +261,36 @@ def run_b200(args):
                 "share_note": "conv launches / whole step, both CUDA-event timed in one eager (non-graph) step",
                 "traffic": traffic}
 
+    # ---- second metric of BASELINE.json: ms per GRU iteration (lookup + update block), graph-replayed ----
+    def gru_iter_ms(pairs):
+        from accflow_b200.engine import View
+        ofe = eng.ofe
+        hh = args.size // 8
+        g = torch.Generator(device="cpu").manual_seed(7)
+        mk = lambda c, f: View(f(torch.randn(pairs, hh, hh, c, generator=g)).to(dev).contiguous())
+        st = ofe.prepare(mk(256, lambda t: t), mk(256, lambda t: t), mk(128, torch.tanh), mk(128, torch.relu),
+                         args.size, args.size, f"gi{pairs}")
+        took = {}
+        for iters in (4, 16):
+            run = lambda: ofe.iterate(st, iters, None, f"gi{pairs}")
+            run(); run()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                run()
+            graph.replay()
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                graph.replay()
+            z.record()
+            torch.cuda.synchronize()
+            took[iters] = a.elapsed_time(z) / 5
+        return (took[16] - took[4]) / 12.0
+
+    ms_iter = {"pairs_3 (one clip, first accumulation step)": gru_iter_ms(3),
+               f"pairs_{3 * b} (this bench's batch)": gru_iter_ms(3 * b)} if rank == 0 else None
+
     line = None
     if rank == 0:
         line = {"metric": "long-range flow pairs/sec", "value": value, "unit": "flows/s", "n_gpus": world,
@@ -269,7 +298,7 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": {"fp32": "f32", "bf16x3": "bf16x3", "fp16x2": "fp16x2", "bf16": "bf16"}[args.precision], "data": "synthetic",
                 "config": workload_config(args, b), "clips_per_s": value / FLOWS_PER_CLIP,
-                "pair_evals_per_s": value / FLOWS_PER_CLIP * 11, "clocks": clocks,
+                "pair_evals_per_s": value / FLOWS_PER_CLIP * 11, "ms_per_gru_iter": ms_iter, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "flows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "roofline": roofline,

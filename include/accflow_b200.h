@@ -218,6 +218,12 @@ ACCFLOW_API int accflow_warp_occ_f32(const float* c1, int c1_ld, const float* c2
 ACCFLOW_API int accflow_backwarp_nchw_f32(const float* img, const float* flow, int batch, int c, int h, int w,
                               float* out, void* stream);
 
+/* Evaluation metric of test_cvo.py:53-101 fused: bidirectional occlusion mask of (bflow, fflow) and the
+ * per-clip EPE all / occ / vis of `pred` against `bflow`.  All NCHW (N,2,H,W) fp32.
+ * partial: workspace >= N * ceil(H*W/256) * 3 floats; out: N x (epe_all, epe_occ, epe_vis). */
+ACCFLOW_API int accflow_epe_metrics_f32(const float* pred, const float* bflow, const float* fflow, int batch, int h,
+                                        int w, float* partial, float* out, void* stream);
+
 /* Modulated deformable 3x3 gather (torchvision deform_conv2d sampling, AccFlow_.py:83,104):
  * offmask NHWC slice with 27 channels (18 offsets dy,dx interleaved per tap, then 9 mask
  * logits -> sigmoid applied here).  col: [B,h*w,9*c] (tap-major) for the following GEMM. */

@@ -160,6 +160,40 @@ def test_bf16_mode_stated_tolerance(golden):
         assert float((out.cpu() - ref).norm(dim=1).mean()) < 0.1
 
 
+def test_fused_metric_kernel_matches_reference(golden):
+    """accflow_epe_metrics_f32 == cal_epe(pred, bflow, calc_occ_mask(bflow, fflow)[0]) of test_cvo.py."""
+    from accflow_b200 import metrics
+    g, _ = golden
+    bflow, fflow, pred = cases.metric_case()
+    out = metrics.clip_epe(pred.cuda(), bflow.cuda(), fflow.cuda()).cpu()
+    for j, name in enumerate(("all", "occ", "vis")):
+        assert float((out[:, j] - torch.as_tensor(g[f"metric.epe_{name}"])).abs().max()) < 1e-5, name
+    occ_bw, occ_fw = metrics.calc_occ_mask(bflow.cuda(), fflow.cuda())
+    assert maxdiff(occ_bw, g["metric.occ_bw"]) == 0 and maxdiff(occ_fw, g["metric.occ_fw"]) == 0
+
+
+def test_shape_contract_errors():
+    """H, W must be multiples of 8 and >= 128 (the reference asserts / crashes, AccFlow_.py:140)."""
+    m = build("raft")
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 3, 132, 128).cuda(), torch.zeros(1, 3, 132, 128).cuda())
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 3, 64, 64).cuda(), torch.zeros(1, 3, 64, 64).cuda())
+
+
+def test_pair_1024_vs_oracle():
+    """BASELINE configs[4] resolution (1024x1024; 4 iterations keep the CPU oracle to seconds)."""
+    from accflow_b200.data import make_clip
+    from oracle import flow_oracle as fo
+    clip = make_clip(9, size=1024)
+    i1, i2 = clip["imgs"][2], clip["imgs"][0]
+    sd = cases.weights("raft")
+    ref = fo.flow_estimator(sd, i1, i2, 4)
+    out = build("raft")(i1.cuda(), i2.cuda(), iters=4)
+    assert out.shape == (1, 2, 1024, 1024)
+    assert maxdiff(out, ref) < FLOW_TOL_PX
+
+
 def test_no_cpu_fallback():
     from accflow_b200.networks import build_flow_estimator
     m = build_flow_estimator("raft")
