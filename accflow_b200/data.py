@@ -57,3 +57,33 @@ def make_batch(clip_ids, size: int = 512, frames: int = 7, seed: int = 1234):
     bflows = [torch.cat([c["bflows"][k] for c in clips], 0) for k in range(frames - 2)]
     fflows = [torch.cat([c["fflows"][k] for c in clips], 0) for k in range(frames - 2)]
     return {"imgs": imgs, "bflows": bflows, "fflows": fflows}
+
+
+def decode_cvo_flow_u16(raw: torch.Tensor) -> torch.Tensor:
+    """CVO stores flows as uint16 fixed point (data/dataset.py:65-67): flow = (v - 2**15) / 128.
+    ``raw``: integer tensor (..., H, W, C) or (..., C, H, W) as read from the LMDB record; returns fp32."""
+    return (raw.to(torch.float32) - 32768.0) / 128.0
+
+
+def encode_cvo_flow_u16(flow: torch.Tensor) -> torch.Tensor:
+    """Inverse of :func:`decode_cvo_flow_u16` (round to nearest, clamp to the uint16 range); int32 container."""
+    return torch.clamp(torch.round(flow * 128.0 + 32768.0), 0, 65535).to(torch.int32)
+
+
+def preprocess(batch: Dict[str, torch.Tensor], device=None) -> Dict[str, List[torch.Tensor]]:
+    """test_cvo.py:32-50: 'imgs' (B,21,H,W) uint8-valued -> 7 x (B,3,H,W) in [-1,1]; '*flows' (B,10,H,W) ->
+    5 x (B,2,H,W).  Same assertions as the reference."""
+    out = {}
+    for key, value in batch.items():
+        if device is not None:
+            value = value.to(device)
+        if "flow" in key:
+            value = list(value.split(2, dim=1))
+            assert len(value) in (5, 6), len(value)
+        elif "imgs" in key:
+            value = list((2 * (value / 255.0) - 1).split(3, dim=1))
+            assert len(value) == 7, len(value)
+        else:
+            raise ValueError(key)
+        out[key] = value
+    return out

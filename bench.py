@@ -37,7 +37,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--clips", type=int, default=4, help="clips per GPU per step")
+    ap.add_argument("--clips", type=int, default=9,
+                    help="clips per GPU per step (9 clips = 18/27 pairs fill the 148 SMs with 7.8/11.7 tile rounds)")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--ofe", default="raft", choices=["raft", "gma"])

@@ -99,3 +99,20 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_cvo_record_helpers():
+    """uint16 fixed-point flows (data/dataset.py:65-67) and the preprocess split (test_cvo.py:32-50)."""
+    from accflow_b200.data import decode_cvo_flow_u16, encode_cvo_flow_u16, make_batch, preprocess
+    raw = torch.tensor([0, 32768, 32768 + 128, 65535], dtype=torch.int32)
+    assert decode_cvo_flow_u16(raw).tolist() == [-256.0, 0.0, 1.0, (65535 - 32768) / 128.0]
+    f = torch.randn(2, 10, 8, 8) * 20
+    assert float((decode_cvo_flow_u16(encode_cvo_flow_u16(f)) - f).abs().max()) <= 0.5 / 128 + 1e-4
+    b = make_batch([0, 1], size=128)
+    rec = {"imgs": torch.cat([(t + 1) * 127.5 for t in b["imgs"]], 1), "bflows": torch.cat(b["bflows"], 1),
+           "fflows": torch.cat(b["fflows"], 1)}
+    out = preprocess(rec)
+    assert len(out["imgs"]) == 7 and len(out["bflows"]) == 5 and out["imgs"][0].shape == (2, 3, 128, 128)
+    assert float((out["imgs"][3] - b["imgs"][3]).abs().max()) < 1e-6
+    with pytest.raises(ValueError):
+        preprocess({"other": torch.zeros(1, 3, 8, 8)})
