@@ -271,20 +271,24 @@ __global__ void __launch_bounds__(256) conv_smallc_kernel(const float* __restric
 // A GEMM tile would be >90 % padding; this is a bandwidth kernel instead: one warp per output
 // pixel, lanes stride over 4-channel groups of the 9 taps, weights (9*cin*4 floats) in shared
 // memory, warp-shuffle reduction, fused affine + activation.
-template <int CPL>  // float4 groups per lane per tap = cin / 128
+template <int CPL, int COUT>  // CPL: float4 groups per lane per tap = cin / 128;  COUT: 1, 2 or 4 accumulators
 __global__ void __launch_bounds__(256) conv3x3_smallcout_kernel(const float* __restrict__ x, int x_ld, int batch, int h,
                                                                 int w, const float* __restrict__ wgt,
                                                                 const float* __restrict__ scale,
                                                                 const float* __restrict__ shift, int cout, int act,
-                                                                float* __restrict__ out, int out_ld, int pix_per_warp) {
+                                                                float* __restrict__ out, int out_ld) {
   constexpr int CIN = CPL * 128;
-  // weights re-ordered to [tap][j][e][lane] (float4 = the 4 couts of channel 4*(lane+32j)+e) so that a
-  // warp-wide LDS.128 reads 32 consecutive float4: conflict-free (the natural [tap][cin] order is 4-way conflicted)
+  // weights re-ordered to [tap][j][e][lane][COUT] (the COUT filters of channel 4*(lane+32j)+e): warp-wide shared
+  // loads read consecutive addresses (the natural [tap][cin][4] order is 4-way bank conflicted)
   extern __shared__ __align__(16) float ws[];
   for (int i = threadIdx.x; i < 9 * CIN; i += 256) {
     const int t = i / CIN, c = i - t * CIN;
     const int grp = c >> 2, e = c & 3, j = grp >> 5, ln = grp & 31;
-    reinterpret_cast<float4*>(ws)[((t * CPL + j) * 4 + e) * 32 + ln] = __ldg(reinterpret_cast<const float4*>(wgt) + i);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(wgt) + i);
+    float* d = ws + ((((t * CPL + j) * 4 + e) * 32 + ln) * COUT);
+    d[0] = v.x;
+    if (COUT > 1) d[1] = v.y;
+    if (COUT > 2) { d[2] = v.z; d[3] = v.w; }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -303,31 +307,43 @@ __global__ void __launch_bounds__(256) conv3x3_smallcout_kernel(const float* __r
 #pragma unroll
       for (int j = 0; j < CPL; ++j) v[t][j] = ok ? __ldg(src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
-        const float4* wt = reinterpret_cast<const float4*>(ws) + (t * CPL + j) * 128 + lane;
-        const float4 w0 = wt[0], w1 = wt[32], w2 = wt[64], w3 = wt[96];
-        const float4 q = v[t][j];
-        a0 = fmaf(q.x, w0.x, a0); a1 = fmaf(q.x, w0.y, a1); a2 = fmaf(q.x, w0.z, a2); a3 = fmaf(q.x, w0.w, a3);
-        a0 = fmaf(q.y, w1.x, a0); a1 = fmaf(q.y, w1.y, a1); a2 = fmaf(q.y, w1.z, a2); a3 = fmaf(q.y, w1.w, a3);
-        a0 = fmaf(q.z, w2.x, a0); a1 = fmaf(q.z, w2.y, a1); a2 = fmaf(q.z, w2.z, a2); a3 = fmaf(q.z, w2.w, a3);
-        a0 = fmaf(q.w, w3.x, a0); a1 = fmaf(q.w, w3.y, a1); a2 = fmaf(q.w, w3.z, a2); a3 = fmaf(q.w, w3.w, a3);
+        const float* wt = ws + ((t * CPL + j) * 128 + lane) * COUT;
+        const float q[4] = {v[t][j].x, v[t][j].y, v[t][j].z, v[t][j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float* we = wt + e * 32 * COUT;
+          if (COUT == 1) {
+            acc[0] = fmaf(q[e], we[0], acc[0]);
+          } else if (COUT == 2) {
+            const float2 w2 = *reinterpret_cast<const float2*>(we);
+            acc[0] = fmaf(q[e], w2.x, acc[0]); acc[1] = fmaf(q[e], w2.y, acc[1]);
+          } else {
+            const float4 w4 = *reinterpret_cast<const float4*>(we);
+            acc[0] = fmaf(q[e], w4.x, acc[0]); acc[1] = fmaf(q[e], w4.y, acc[1]);
+            acc[2] = fmaf(q[e], w4.z, acc[2]); acc[3] = fmaf(q[e], w4.w, acc[3]);
+          }
+        }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-      a3 += __shfl_xor_sync(0xffffffffu, a3, o);
-    }
-    if (lane < cout) {
-      float r = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : a3;
-      r = fmaf(r, scale ? __ldg(scale + lane) : 1.f, shift ? __ldg(shift + lane) : 0.f);
-      out[pix * out_ld + lane] = act_apply(r, act);
+    for (int sft = 16; sft > 0; sft >>= 1)
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sft);
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        if (o < cout) {
+          const float r = fmaf(acc[o], scale ? __ldg(scale + o) : 1.f, shift ? __ldg(shift + o) : 0.f);
+          out[pix * out_ld + o] = act_apply(r, act);
+        }
+      }
     }
   }
 }
@@ -428,42 +444,56 @@ __global__ void __launch_bounds__(256) stem_patch_kernel(const float* __restrict
                                                          __nv_bfloat16* __restrict__ out_pl, int pitch,
                                                          long long pl_stride, int nplanes) {
   const int oh = (H + 1) / 2, ow = (W + 1) / 2;
-  const int kp = pitch >> 1;                                    // channel pairs per pixel
+  const int kg = pitch >> 3;                                    // 8-channel groups per pixel (19 for pitch 152)
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long total = (long long)batch * oh * ow * kp;
+  const long long total = (long long)batch * oh * ow * kg;
   if (i >= total) return;
-  const long long pix = i / kp;
-  const int k0 = (int)(i - pix * kp) * 2;
+  const long long pix = i / kg;
+  const int k0 = (int)(i - pix * kg) * 8;
   const int b = (int)(pix / ((long long)oh * ow));
   const int r = (int)(pix - (long long)b * oh * ow);
   const int oy = r / ow, ox = r - oy * ow;
-  float v[2];
+  const float* ib = img + (long long)b * 3 * H * W;
+  float v[8];
 #pragma unroll
-  for (int e = 0; e < 2; ++e) {
+  for (int e = 0; e < 8; ++e) {
     const int k = k0 + e;
     v[e] = 0.f;
     if (k < 147) {
       const int tap = k / 3, c = k - tap * 3;
-      const int iy = 2 * oy - 3 + tap / 7, ix = 2 * ox - 3 + tap % 7;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[e] = __ldg(img + ((long long)(b * 3 + c) * H + iy) * W + ix);
+      const int ky = tap / 7, kx = tap - ky * 7;
+      const int iy = 2 * oy - 3 + ky, ix = 2 * ox - 3 + kx;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[e] = __ldg(ib + ((long long)c * H + iy) * W + ix);
     }
   }
   __nv_bfloat16* dst = out_pl + pix * pitch + k0;
+  uint32_t p0[4], p1[4], p2[4];
   if (nplanes == 2) {
-    const __half2 hi = __floats2half2_rn(v[0], v[1]);
-    const float2 hf = __half22float2(hi);
-    const __half2 lo = __floats2half2_rn((v[0] - hf.x) * ACCFLOW_FP16X2_SCALE, (v[1] - hf.y) * ACCFLOW_FP16X2_SCALE);
-    *reinterpret_cast<__half2*>(dst) = hi;
-    *reinterpret_cast<__half2*>(dst + pl_stride) = lo;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 hi = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+      const float2 hf = __half22float2(hi);
+      const __half2 lo = __floats2half2_rn((v[2 * e] - hf.x) * ACCFLOW_FP16X2_SCALE, (v[2 * e + 1] - hf.y) * ACCFLOW_FP16X2_SCALE);
+      p0[e] = *reinterpret_cast<const uint32_t*>(&hi);
+      p1[e] = *reinterpret_cast<const uint32_t*>(&lo);
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+    *reinterpret_cast<uint4*>(dst + pl_stride) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
   } else {
-    const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]);
-    *reinterpret_cast<__nv_bfloat162*>(dst) = p0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 a = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      const float r0 = v[2 * e] - __bfloat162float(a.x), r1 = v[2 * e + 1] - __bfloat162float(a.y);
+      const __nv_bfloat162 bq = __floats2bfloat162_rn(r0, r1);
+      const __nv_bfloat162 cq = __floats2bfloat162_rn(r0 - __bfloat162float(bq.x), r1 - __bfloat162float(bq.y));
+      p0[e] = *reinterpret_cast<const uint32_t*>(&a);
+      p1[e] = *reinterpret_cast<const uint32_t*>(&bq);
+      p2[e] = *reinterpret_cast<const uint32_t*>(&cq);
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
     if (nplanes > 1) {
-      const float r0 = v[0] - __bfloat162float(p0.x), r1 = v[1] - __bfloat162float(p0.y);
-      const __nv_bfloat162 p1 = __floats2bfloat162_rn(r0, r1);
-      *reinterpret_cast<__nv_bfloat162*>(dst + pl_stride) = p1;
-      *reinterpret_cast<__nv_bfloat162*>(dst + 2 * pl_stride) =
-          __floats2bfloat162_rn(r0 - __bfloat162float(p1.x), r1 - __bfloat162float(p1.y));
+      *reinterpret_cast<uint4*>(dst + pl_stride) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+      *reinterpret_cast<uint4*>(dst + 2 * pl_stride) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
     }
   }
 }
@@ -593,26 +623,25 @@ extern "C" int accflow_conv_smallc_f32(const float* in, int in_is_nchw, int batc
               cout, in_is_nchw);
 }
 
-template <int CPL>
+template <int CPL, int COUT>
 static int launch_smallcout(const float* x, int x_ld, int batch, int h, int w, const float* weight, const float* scale,
                             const float* shift, int cout, int act, float* out, int out_ld, cudaStream_t st) {
-  const size_t smem = (size_t)9 * CPL * 128 * 4 * sizeof(float);
-  auto kern = conv3x3_smallcout_kernel<CPL>;
+  const size_t smem = (size_t)9 * CPL * 128 * COUT * sizeof(float);
+  auto kern = conv3x3_smallcout_kernel<CPL, COUT>;
   static thread_local int cfg_dev = -1;
+  static thread_local int sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);
   if (cfg_dev != dev) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "conv3x3_smallcout: smem attribute: %s", cudaGetErrorString(e));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cfg_dev = dev;
   }
   const long long total = (long long)batch * h * w;
-  static thread_local int sms = 0;
-  if (sms == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-  const int blocks_per_sm = smem > 40 * 1024 ? 5 : 8;
   const long long want = cdiv(total, 8);
-  const int grid = (int)(want < (long long)sms * blocks_per_sm ? want : (long long)sms * blocks_per_sm);
-  kern<<<grid, 256, smem, st>>>(x, x_ld, batch, h, w, weight, scale, shift, cout, act, out, out_ld, 0);
+  const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+  kern<<<grid, 256, smem, st>>>(x, x_ld, batch, h, w, weight, scale, shift, cout, act, out, out_ld);
   return launched("conv3x3_smallcout");
 }
 
@@ -623,8 +652,10 @@ extern "C" int accflow_conv3x3_smallcout_f32(const float* x, int x_ld, int batch
   ACCFLOW_REQUIRE(batch > 0 && h > 0 && w > 0 && x_ld % 4 == 0 && x_ld >= cin && cout >= 1 && cout <= 4 && out_ld >= cout,
                   "conv3x3_smallcout: bad shape (cout <= 4)");
   cudaStream_t st = (cudaStream_t)stream;
-  if (cin == 256) return launch_smallcout<2>(x, x_ld, batch, h, w, weight, scale, shift, cout, act, out, out_ld, st);
-  if (cin == 128) return launch_smallcout<1>(x, x_ld, batch, h, w, weight, scale, shift, cout, act, out, out_ld, st);
+#define ACCFLOW_SC(CPL_, COUT_) return launch_smallcout<CPL_, COUT_>(x, x_ld, batch, h, w, weight, scale, shift, cout, act, out, out_ld, st)
+  if (cin == 256) { if (cout == 1) ACCFLOW_SC(2, 1); if (cout == 2) ACCFLOW_SC(2, 2); ACCFLOW_SC(2, 4); }
+  if (cin == 128) { if (cout == 1) ACCFLOW_SC(1, 1); if (cout == 2) ACCFLOW_SC(1, 2); ACCFLOW_SC(1, 4); }
+#undef ACCFLOW_SC
   return fail(-1, "conv3x3_smallcout: cin must be 128 or 256 (got %d)", cin);
 }
 
@@ -642,9 +673,9 @@ extern "C" int accflow_flow_patch_f32(const float* flow, int batch, int h, int w
 extern "C" int accflow_stem_patch_planes(const float* img_nchw, int batch, int H, int W, void* out_planes, int pitch,
                                          long long pl_stride, int nplanes, void* stream) {
   ACCFLOW_REQUIRE(img_nchw && out_planes && batch > 0 && H > 0 && W > 0, "stem_patch: bad arguments");
-  ACCFLOW_REQUIRE(pitch >= 148 && pitch % 8 == 0 && pl_stride % 2 == 0 && nplanes >= 1 && nplanes <= 3 &&
-                      (reinterpret_cast<uintptr_t>(out_planes) & 3u) == 0, "stem_patch: pitch must be >= 148 and a multiple of 8");
-  const long long total = (long long)batch * ((H + 1) / 2) * ((W + 1) / 2) * (pitch / 2);
+  ACCFLOW_REQUIRE(pitch >= 148 && pitch % 8 == 0 && pl_stride % 8 == 0 && nplanes >= 1 && nplanes <= 3 &&
+                      aligned16(out_planes), "stem_patch: pitch must be >= 148 and a multiple of 8, planes 16B aligned");
+  const long long total = (long long)batch * ((H + 1) / 2) * ((W + 1) / 2) * (pitch / 8);
   stem_patch_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(img_nchw, batch, H, W,
                                                                         reinterpret_cast<__nv_bfloat16*>(out_planes), pitch,
                                                                         pl_stride, nplanes);

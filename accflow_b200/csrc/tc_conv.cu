@@ -778,8 +778,8 @@ conv_tc2_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPa
   }
 }
 
-// fp32 [rows][k] (row stride ld) -> bf16 planes: out[pl*plane_stride + row*pitch + c], c < k_fill
-// (columns k..k_fill-1 are zero-filled so TMA never reads uninitialised padding).
+// fp32 [rows][k] (row stride ld) -> 16-bit operand planes: out[pl*plane_stride + row*pitch + c], c < k_fill
+// (columns k..k_fill-1 are zero-filled).  Scalar version + a vector version (8 channels per thread, 16-byte stores).
 __global__ void split_planes_kernel(const float* __restrict__ x, long long rows, int k, int ld, int k_fill, int pitch,
                                     long long plane_stride, int nplanes, __nv_bfloat16* __restrict__ out) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -788,6 +788,47 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long rows,
   const int c = (int)(i - r * k_fill);
   const float v = c < k ? __ldg(x + r * ld + c) : 0.f;
   store_planes(out + r * pitch + c, plane_stride, nplanes, v);
+}
+
+__global__ void split_planes_vec8_kernel(const float* __restrict__ x, long long rows, int k8, int ld, int pitch,
+                                         long long plane_stride, int nplanes, __nv_bfloat16* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= rows * k8) return;
+  const long long r = i / k8;
+  const int c = (int)(i - r * k8) * 8;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(x + r * ld + c) + 1);
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  __nv_bfloat16* dst = out + r * pitch + c;
+  uint32_t p0[4], p1[4], p2[4];
+  if (nplanes == 2) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 hi = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+      const float2 hf = __half22float2(hi);
+      const __half2 lo = __floats2half2_rn((v[2 * e] - hf.x) * ACCFLOW_FP16X2_SCALE, (v[2 * e + 1] - hf.y) * ACCFLOW_FP16X2_SCALE);
+      p0[e] = *reinterpret_cast<const uint32_t*>(&hi);
+      p1[e] = *reinterpret_cast<const uint32_t*>(&lo);
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+    *reinterpret_cast<uint4*>(dst + plane_stride) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    return;
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 q0 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    const float r0 = v[2 * e] - __bfloat162float(q0.x), r1 = v[2 * e + 1] - __bfloat162float(q0.y);
+    const __nv_bfloat162 q1 = __floats2bfloat162_rn(r0, r1);
+    const __nv_bfloat162 q2 = __floats2bfloat162_rn(r0 - __bfloat162float(q1.x), r1 - __bfloat162float(q1.y));
+    p0[e] = *reinterpret_cast<const uint32_t*>(&q0);
+    p1[e] = *reinterpret_cast<const uint32_t*>(&q1);
+    p2[e] = *reinterpret_cast<const uint32_t*>(&q2);
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+  if (nplanes > 1) {
+    *reinterpret_cast<uint4*>(dst + plane_stride) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    *reinterpret_cast<uint4*>(dst + 2 * plane_stride) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -818,6 +859,12 @@ extern "C" int accflow_split_bf16_planes(const float* x, long long rows, int k, 
   ACCFLOW_REQUIRE(x && out_planes && rows > 0 && k > 0 && ld >= k && k_fill >= k && pitch >= k_fill,
                   "split_bf16_planes: bad arguments");
   ACCFLOW_REQUIRE(nplanes >= 1 && nplanes <= 3, "split_bf16_planes: nplanes must be 1 (bf16), 2 (fp16x2) or 3 (bf16x3)");
+  if (k == k_fill && k % 8 == 0 && ld % 4 == 0 && pitch % 8 == 0 && plane_stride % 8 == 0 && aligned16(x) &&
+      aligned16(out_planes)) {
+    tc::split_planes_vec8_kernel<<<cdiv(rows * (k / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        x, rows, k / 8, ld, pitch, plane_stride, nplanes, reinterpret_cast<__nv_bfloat16*>(out_planes));
+    return launched("split_bf16_planes");
+  }
   tc::split_planes_kernel<<<cdiv(rows * k_fill, 256), 256, 0, (cudaStream_t)stream>>>(
       x, rows, k, ld, k_fill, pitch, plane_stride, nplanes, reinterpret_cast<__nv_bfloat16*>(out_planes));
   return launched("split_bf16_planes");
