@@ -220,6 +220,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_free[MAX_STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
+  // per-tile epilogue affine (alpha folded in), staged once per tile; two copies: a warp set may run one tile ahead
+  __shared__ __align__(16) float s_scale[2][256], s_shift[2][256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int taps = p.kh * p.kw;
@@ -349,8 +351,18 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       const int sample = t / p.tiles_y;
       const int ox0 = tile_x * p.tw, oy0 = tile_y * p.th, n0 = n_tile * BN;
       const int slot = lt & 1, use = lt >> 1;
+      {  // stage this tile's scale / shift (global-load latency off the per-panel critical path)
+        const int et = tid - 64;                                  // 0..255
+        if (et < BN) {
+          const int n = n0 + et;
+          const bool ok = n < p.cout;
+          s_scale[lt & 1][et] = p.alpha * ((p.scale && ok) ? __ldg(p.scale + n) : 1.f);
+          s_shift[lt & 1][et] = (p.shift && ok) ? __ldg(p.shift + n) : 0.f;
+        }
+      }
       mbar_wait(&bar_acc_full[slot], use & 1);
       tc_fence_after();
+      asm volatile("bar.sync 3, 256;" ::: "memory");             // staged affine visible to both warp sets
       const uint32_t lane_addr = tmem_base + slot * acc_cols + ((uint32_t)(32 * (warp & 3)) << 16);
       for (int c = cbeg; c < cend; c += 16) {
         {
@@ -375,13 +387,9 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
         const int nb = n0 + c + pc4 * 4;
         if (nb < p.cout) {
-          float sc[4], sh[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const bool ok = nb + j < p.cout;
-            sc[j] = p.alpha * ((p.scale && ok) ? __ldg(p.scale + nb + j) : 1.f);
-            sh[j] = (p.shift && ok) ? __ldg(p.shift + nb + j) : 0.f;
-          }
+          const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
+          const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[lt & 1][c + pc4 * 4]);
+          const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
           const bool vec4 = nb + 3 < p.cout;
 #pragma unroll 2
           for (int itr = 0; itr < 4; ++itr) {
@@ -528,6 +536,8 @@ conv_tc2_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPa
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_free[MAX_STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
+  // per-tile epilogue affine (alpha folded in), staged once per tile; two copies: a warp set may run one tile ahead
+  __shared__ __align__(16) float s_scale[2][256], s_shift[2][256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int taps = p.kh * p.kw;
@@ -666,8 +676,18 @@ conv_tc2_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPa
       const int sample = t / p.tiles_y;
       const int ox0 = tile_x * p.tw, oy0 = tile_y * p.th, n0 = n_tile * BN;
       const int slot = slots == 2 ? (lt & 1) : 0, use = slots == 2 ? (lt >> 1) : lt;
+      {  // stage this tile's scale / shift (global-load latency off the per-panel critical path)
+        const int et = tid - 64;                                  // 0..255
+        if (et < BN) {
+          const int n = n0 + et;
+          const bool ok = n < p.cout;
+          s_scale[lt & 1][et] = p.alpha * ((p.scale && ok) ? __ldg(p.scale + n) : 1.f);
+          s_shift[lt & 1][et] = (p.shift && ok) ? __ldg(p.shift + n) : 0.f;
+        }
+      }
       mbar_wait(&bar_acc_full[slot], use & 1);
       tc_fence_after();
+      asm volatile("bar.sync 3, 256;" ::: "memory");             // staged affine visible to both warp sets
       const uint32_t lane_addr = tmem_base + slot * acc_cols + ((uint32_t)(32 * (warp & 3)) << 16);
       for (int c = cbeg; c < cend; c += 16) {
         {
@@ -692,13 +712,9 @@ conv_tc2_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPa
         asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
         const int nb = n0 + c + pc4 * 4;
         if (nb < p.cout) {
-          float sc[4], sh[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const bool ok = nb + j < p.cout;
-            sc[j] = p.alpha * ((p.scale && ok) ? __ldg(p.scale + nb + j) : 1.f);
-            sh[j] = (p.shift && ok) ? __ldg(p.shift + nb + j) : 0.f;
-          }
+          const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
+          const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[lt & 1][c + pc4 * 4]);
+          const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
           const bool vec4 = nb + 3 < p.cout;
 #pragma unroll 2
           for (int itr = 0; itr < 4; ++itr) {
