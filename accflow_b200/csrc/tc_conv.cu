@@ -31,6 +31,7 @@ constexpr int BM = 128;       // pixels per CTA (TMEM lanes)
 constexpr int KC = 64;        // K elements per pipeline stage (one 128-byte swizzle atom of bf16)
 constexpr int A_PLANE_BYTES = BM * KC * 2;  // 16 KB
 constexpr int MAX_STAGES = 6;
+constexpr int MAX_B_STAGES = 8;
 constexpr int NTHREADS = 320;
 
 struct PlaneOut {  // optional bf16 planes written next to an fp32 output
@@ -47,6 +48,15 @@ struct Params {
   int n_tiles;                              // cout tiles
   int per_sample;                           // weights' T coordinate = sample instead of tap
   int cout, bn, nplanes, nprod, stages;
+  // Operand rings of conv_tc_kernel.  A (activations) and W (weights) are staged independently so one
+  // activation box can serve several filter taps ("shift" modes):
+  //   mode 0: one box per tap (strided convs, 1x1, per-sample GEMMs), pixels row-major in the tile.
+  //   mode 1: slow axis = y.  Box = 8 x-pixels x (16 + kh - 1) y-pixels loaded once per (kx, K block);
+  //           the tap ky is the same box read 1024*ky bytes further (8 pixel rows of 128 B).
+  //   mode 2: slow axis = x (tensor map dims permuted to C,H,W): box = 8 y-pixels x (16 + kw - 1)
+  //           x-pixels per (ky, K block); tap kx is 1024*kx bytes further.  Tile = 16 wide x 8 tall.
+  int mode, n_outer, n_inner, tile_w, tile_h, a_plane_bytes, stages_b;
+  int debug;   // perf experiments only (ACCFLOW_TC_DEBUG): bit 0 = no TMA loads, bit 1 = no MMAs (results are garbage)
   float alpha;
   const float* scale;
   const float* shift;
@@ -212,30 +222,110 @@ __device__ __forceinline__ void store_planes1(const PlaneOut& po, int nplanes, l
   store_planes(po.ptr + pix * po.pitch + n, po.plane_stride, nplanes, y);
 }
 
+// ---------------------------------------------------------------------------------- MMA issue loop
+// One thread issues every tcgen05.mma of the CTA, so its instruction count per weight tile is on the
+// critical path (measured: with TMA and epilogue disabled the old loop still ran at 2.2x the tensor time).
+// Descriptors are therefore built from a constant high word and a low word advanced by adds, ring
+// positions and parities are carried instead of divided out, and in the split modes the first two
+// products share one instruction: the weight planes w0 | w1 are contiguous in shared memory and the
+// MAIN | CORR accumulators are contiguous in TMEM, so  a0 x [w0; w1]  is a single N = 2*BN MMA.
+struct MmaCtx {
+  int total_tiles, stride_tiles, first_tile, nchunks, n_inner, SA, SB, BN, a_stage, b_stage, debug;
+  uint32_t a_plane16, w_plane16, smem_a, smem_b, tmem_base, acc_cols;
+  uint64_t *afull, *afree, *bfull, *bfree, *acc_full, *acc_empty;
+};
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) {
+  // high word: SBO = 1024 B (>>4) at [32,46), version 1 at [46,48), SWIZZLE_128B (2) at [61,64)
+  constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(HI));
+  return d;
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+
+template <int NPROD>
+__device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
+  const uint32_t idesc1 = make_idesc(BM, c.BN, NPROD == 3);
+  const uint32_t idesc2 = make_idesc(BM, 2 * c.BN, NPROD == 3);      // a0 x [w0; w1] -> MAIN | CORR
+  int sa = 0, sb = 0;
+  uint32_t pa = 0, pb = 0;                                           // ring parities
+  uint32_t a_slot = c.smem_a, w_slot = c.smem_b;
+  int lt = 0;
+  for (int tile = c.first_tile; tile < c.total_tiles; tile += c.stride_tiles, ++lt) {
+    const int slot = lt & 1, use = lt >> 1;
+    mbar_wait(&c.acc_empty[slot], (use & 1) ^ 1);                    // epilogue has drained this slot (first use passes)
+    tc_fence_after();
+    const uint32_t acc_main = c.tmem_base + slot * c.acc_cols, acc_corr = acc_main + c.BN;
+    uint32_t first = 0;                                              // 0 -> overwrite the accumulators
+    for (int i = 0; i < c.nchunks; ++i) {
+      mbar_wait(&c.afull[sa], pa);
+      uint32_t a_lo = desc_lo(a_slot);
+      for (int j = 0; j < c.n_inner; ++j) {
+        mbar_wait(&c.bfull[sb], pb);
+        tc_fence_after();
+        const uint32_t w_lo = desc_lo(w_slot);
+        if (!(c.debug & 2)) {
+#pragma unroll
+          for (int k4 = 0; k4 < KC / 16; ++k4) {                     // 16 elements = 32 B = 2 descriptor units
+            const uint64_t a0 = desc_from_lo(a_lo + 2 * k4), w0 = desc_from_lo(w_lo + 2 * k4);
+            if (NPROD == 1) {
+              umma_bf16(acc_main, a0, w0, idesc1, first);
+            } else {
+              const uint64_t a1 = desc_from_lo(a_lo + c.a_plane16 + 2 * k4);
+              umma_bf16(acc_main, a0, w0, idesc2, first);            // MAIN += a0 w0 ; CORR += a0 w1
+              umma_bf16(acc_corr, a1, w0, idesc1, 1);                // CORR += a1 w0
+              if (NPROD == 6) {
+                const uint64_t w1 = desc_from_lo(w_lo + c.w_plane16 + 2 * k4);
+                const uint64_t a2 = desc_from_lo(a_lo + 2 * c.a_plane16 + 2 * k4);
+                const uint64_t w2 = desc_from_lo(w_lo + 2 * c.w_plane16 + 2 * k4);
+                umma_bf16(acc_corr, a1, w1, idesc1, 1);
+                umma_bf16(acc_corr, a0, w2, idesc1, 1);
+                umma_bf16(acc_corr, a2, w0, idesc1, 1);
+              }
+            }
+            first = 1;
+          }
+        }
+        umma_commit(&c.bfree[sb]);                                   // weight tile reusable once these MMAs retire
+        a_lo += 1024 >> 4;                                           // shift modes: next tap = 8 pixel rows further
+        w_slot += c.b_stage;
+        if (++sb == c.SB) { sb = 0; pb ^= 1; w_slot = c.smem_b; }
+      }
+      umma_commit(&c.afree[sa]);                                     // ... and so is the activation box
+      a_slot += c.a_stage;
+      if (++sa == c.SA) { sa = 0; pa ^= 1; a_slot = c.smem_a; }
+    }
+    umma_commit(&c.acc_full[slot]);
+  }
+}
+
 // Persistent: grid = min(#tiles, #SMs); CTA c walks tiles c, c+grid, ... (tiles are N-major so that
 // neighbouring CTAs share one weight tile in L2).  Two TMEM accumulator slots let the epilogue of
 // tile i overlap the TMA/MMA main loop of tile i+1; the smem operand ring runs across tiles.
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPack maps) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
-  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_free[MAX_STAGES], bar_acc_full[2], bar_acc_empty[2];
+  __shared__ __align__(8) uint64_t bar_afull[MAX_STAGES], bar_afree[MAX_STAGES], bar_bfull[MAX_B_STAGES],
+      bar_bfree[MAX_B_STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
   // per-tile epilogue affine (alpha folded in), staged once per tile; two copies: a warp set may run one tile ahead
   __shared__ __align__(16) float s_scale[2][256], s_shift[2][256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int taps = p.kh * p.kw;
-  const int BN = p.bn, S = p.stages, NPL = p.nplanes;
+  const int BN = p.bn, SA = p.stages, SB = p.stages_b, NPL = p.nplanes;
+  const int n_outer = p.n_outer, n_inner = p.n_inner;          // A boxes per K block / taps served by one box
   const int w_plane_bytes = BN * KC * 2;
-  const int stage_bytes = NPL * (A_PLANE_BYTES + w_plane_bytes);
-  // 1024-byte aligned carve-up (SWIZZLE_128B atoms): [stages][A planes | W planes] then the epilogue panels
+  const int a_plane_bytes = p.a_plane_bytes;                    // (128 + 8 * halo rows) pixels x 128 B
+  const int a_stage = NPL * a_plane_bytes, b_stage = NPL * w_plane_bytes;
+  // 1024-byte aligned carve-up (SWIZZLE_128B atoms): [A ring][W ring] then the epilogue panels
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem + (size_t)SA * a_stage;
   constexpr int PITCH = 20;                                     // floats per staged row: 16 columns + 4 pad
-  float* stg_base = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);
+  float* stg_base = reinterpret_cast<float*>(smem_b + (size_t)SB * b_stage);
 
   int nchunks = 0;
   for (int s = 0; s < p.nsrc; ++s) nchunks += (p.src_c[s] + KC - 1) / KC;
-  nchunks *= taps;
+  nchunks *= n_outer;
   const int acc_cols = (p.nprod > 1 ? 2 : 1) * BN;              // TMEM columns of one accumulator slot
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
@@ -243,9 +333,13 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   const int total_tiles = m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_free[s], 1);
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(&bar_afull[s], 1);
+      mbar_init(&bar_afree[s], 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(&bar_bfull[s], 1);
+      mbar_init(&bar_bfree[s], 1);
     }
     for (int j = 0; j < 2; ++j) {
       mbar_init(&bar_acc_full[j], 1);
@@ -264,73 +358,60 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   if (warp == 0) {
     // ================================ TMA producer ============================================
     if (lane == 0) {
-      int it = 0;                                            // global chunk counter (ring position)
+      int sa = 0, sb = 0;                                    // ring positions (A boxes, weight tiles)
+      uint32_t pa = 1, pb = 1;                               // parity of the "free" phase to wait for (first lap passes)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile / m_tiles;
         int t = tile - n_tile * m_tiles;
         const int tile_x = t % p.tiles_x; t /= p.tiles_x;
         const int tile_y = t % p.tiles_y;
         const int sample = t / p.tiles_y;
-        const int ox0 = tile_x * p.tw, oy0 = tile_y * p.th, n0 = n_tile * BN;
-        Chunk ck{0, 0, 0};
-        for (int i = 0; i < nchunks; ++i, ++it) {
-          const int s = it % S, round = it / S;
-          if (round > 0) mbar_wait(&bar_free[s], (round - 1) & 1);
-          uint8_t* adst = smem + (size_t)s * stage_bytes;
-          uint8_t* wdst = adst + NPL * A_PLANE_BYTES;
-          mbar_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
-          const int ky = ck.tap / p.kw, kx = ck.tap - ky * p.kw;
-          const int ix = ox0 * p.stride + kx - p.pad_w, iy = oy0 * p.stride + ky - p.pad_h;
-          const int kcoord = p.src_off[ck.s] + ck.c0;
-          const int tw_ = p.per_sample ? sample : ck.tap;
-          for (int pl = 0; pl < NPL; ++pl) {
-            tma_load_5d(adst + pl * A_PLANE_BYTES, &maps.a[ck.s], &bar_full[s], ck.c0, ix, iy, sample, pl);
-            tma_load_4d(wdst + pl * w_plane_bytes, &maps.w, &bar_full[s], kcoord, n0, tw_, pl);
+        const int ox0 = tile_x * p.tile_w, oy0 = tile_y * p.tile_h, n0 = n_tile * BN;
+        Chunk ck{0, 0, 0};                                   // ck.tap = outer tap index
+        for (int i = 0; i < nchunks; ++i) {
+          mbar_wait(&bar_afree[sa], pa);
+          uint8_t* adst = smem + (size_t)sa * a_stage;
+          mbar_expect_tx(&bar_afull[sa], (p.debug & 1) ? 0u : (uint32_t)a_stage);
+          int c1, c2;                                        // box origin along tensor-map dims 1, 2
+          if (p.mode == 0) {
+            const int ky = ck.tap / p.kw, kx = ck.tap - ky * p.kw;
+            c1 = ox0 * p.stride + kx - p.pad_w; c2 = oy0 * p.stride + ky - p.pad_h;
+          } else if (p.mode == 1) {                          // dims (C, W, H): outer tap = kx, halo along y
+            c1 = ox0 + ck.tap - p.pad_w; c2 = oy0 - p.pad_h;
+          } else {                                           // dims (C, H, W): outer tap = ky, halo along x
+            c1 = oy0 + ck.tap - p.pad_h; c2 = ox0 - p.pad_w;
           }
-          ck.next(p, taps);
+          for (int pl = 0; pl < NPL && !(p.debug & 1); ++pl)
+            tma_load_5d(adst + pl * a_plane_bytes, &maps.a[ck.s], &bar_afull[sa], ck.c0, c1, c2, sample, pl);
+          const int kcoord = p.src_off[ck.s] + ck.c0;
+          for (int j = 0; j < n_inner; ++j) {
+            mbar_wait(&bar_bfree[sb], pb);
+            uint8_t* wdst = smem_b + (size_t)sb * b_stage;
+            mbar_expect_tx(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)b_stage);
+            const int tap = p.per_sample ? sample : p.mode == 0 ? ck.tap : p.mode == 1 ? j * p.kw + ck.tap : ck.tap * p.kw + j;
+            for (int pl = 0; pl < NPL && !(p.debug & 1); ++pl)
+              tma_load_4d(wdst + pl * w_plane_bytes, &maps.w, &bar_bfull[sb], kcoord, n0, tap, pl);
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+          ck.next(p, n_outer);
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==============================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, BN, p.nprod == 3);
-      int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-        const int slot = lt & 1, use = lt >> 1;
-        mbar_wait(&bar_acc_empty[slot], (use & 1) ^ 1);     // epilogue has drained this slot (first use passes)
-        tc_fence_after();
-        const uint32_t acc_main = tmem_base + slot * acc_cols, acc_corr = acc_main + BN;
-        uint32_t first_main = 0, first_corr = 0;            // 0 -> overwrite accumulator
-        for (int i = 0; i < nchunks; ++i, ++it) {
-          const int s = it % S, round = it / S;
-          mbar_wait(&bar_full[s], round & 1);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t w_base = a_base + NPL * A_PLANE_BYTES;
-#pragma unroll
-          for (int k4 = 0; k4 < KC / 16; ++k4) {
-            const uint32_t koff = k4 * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
-            const uint64_t a0 = make_desc(a_base + koff), w0 = make_desc(w_base + koff);
-            umma_bf16(acc_main, a0, w0, idesc, first_main);
-            first_main = 1;
-            if (p.nprod > 1) {
-              const uint64_t a1 = make_desc(a_base + A_PLANE_BYTES + koff), w1 = make_desc(w_base + w_plane_bytes + koff);
-              umma_bf16(acc_corr, a0, w1, idesc, first_corr);
-              first_corr = 1;
-              umma_bf16(acc_corr, a1, w0, idesc, 1);
-              if (p.nprod == 6) {
-                const uint64_t a2 = make_desc(a_base + 2 * A_PLANE_BYTES + koff), w2 = make_desc(w_base + 2 * w_plane_bytes + koff);
-                umma_bf16(acc_corr, a1, w1, idesc, 1);
-                umma_bf16(acc_corr, a0, w2, idesc, 1);
-                umma_bf16(acc_corr, a2, w0, idesc, 1);
-              }
-            }
-          }
-          umma_commit(&bar_free[s]);  // smem of this stage is reusable once these MMAs retire
-        }
-        umma_commit(&bar_acc_full[slot]);
-      }
+      MmaCtx c;
+      c.total_tiles = total_tiles; c.stride_tiles = gridDim.x; c.first_tile = blockIdx.x;
+      c.nchunks = nchunks; c.n_inner = n_inner; c.SA = SA; c.SB = SB; c.BN = BN;
+      c.a_stage = a_stage; c.b_stage = b_stage; c.a_plane16 = a_plane_bytes >> 4; c.w_plane16 = w_plane_bytes >> 4;
+      c.smem_a = smem_u32(smem); c.smem_b = smem_u32(smem_b);
+      c.tmem_base = tmem_base; c.acc_cols = acc_cols; c.debug = p.debug;
+      c.afull = bar_afull; c.afree = bar_afree; c.bfull = bar_bfull; c.bfree = bar_bfree;
+      c.acc_full = bar_acc_full; c.acc_empty = bar_acc_empty;
+      if (p.nprod == 3) mma_issue_loop<3>(c);
+      else if (p.nprod == 1) mma_issue_loop<1>(c);
+      else mma_issue_loop<6>(c);
     }
   } else {
     // ================================ epilogue ================================================
@@ -349,7 +430,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       const int tile_x = t % p.tiles_x; t /= p.tiles_x;
       const int tile_y = t % p.tiles_y;
       const int sample = t / p.tiles_y;
-      const int ox0 = tile_x * p.tw, oy0 = tile_y * p.th, n0 = n_tile * BN;
+      const int ox0 = tile_x * p.tile_w, oy0 = tile_y * p.tile_h, n0 = n_tile * BN;
       const int slot = lt & 1, use = lt >> 1;
       {  // stage this tile's scale / shift (global-load latency off the per-panel critical path)
         const int et = tid - 64;                                  // 0..255
@@ -367,8 +448,11 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       for (int c = cbeg; c < cend; c += 16) {
         {
           float acc[16];
-          tmem_ld16(lane_addr + c, acc);
-          if (p.nprod > 1) {
+          if (p.debug & 8) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+          } else tmem_ld16(lane_addr + c, acc);
+          if (p.nprod > 1 && !(p.debug & 8)) {
             float corr[16];
             tmem_ld16(lane_addr + BN + c, corr);
             const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;   // fp16x2: lo planes carry 2^11
@@ -386,7 +470,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
         const int nb = n0 + c + pc4 * 4;
-        if (nb < p.cout) {
+        if (nb < p.cout && !(p.debug & 4)) {
           const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
           const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[lt & 1][c + pc4 * 4]);
           const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
@@ -394,7 +478,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
 #pragma unroll 2
           for (int itr = 0; itr < 4; ++itr) {
             const int row = itr * 32 + (st >> 2);
-            const int oy = oy0 + (row >> p.tw_shift), ox = ox0 + (row & (p.tw - 1));
+            const int r_slow = row >> p.tw_shift, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
+            const int oy = oy0 + (p.mode == 2 ? r_fast : r_slow), ox = ox0 + (p.mode == 2 ? r_slow : r_fast);
             if (oy >= p.out_h || ox >= p.out_w) continue;
             const long long pix = ((long long)sample * p.out_h + oy) * p.out_w + ox;
             const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
@@ -851,6 +936,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static bool mode2_rejected = false;   // set if cuTensorMapEncodeTiled refuses the (C, H, W) stride order of shift mode 2
+
 static EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
@@ -922,6 +1009,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   int tw = 8, sh = 3;
   while (tw < p.out_w && tw < 128) { tw <<= 1; ++sh; }
   p.tw = tw; p.tw_shift = sh; p.th = tc::BM / tw;
+  p.tile_w = p.tw; p.tile_h = p.th;
   p.tiles_x = cdiv(p.out_w, p.tw); p.tiles_y = cdiv(p.out_h, p.th);
   p.per_sample = per_sample;
   p.cout = d.cout;
@@ -941,6 +1029,24 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     const bool allowed = m_tiles_all >= 2 && (!per_sample || (p.tiles_x * p.tiles_y) % 2 == 0);
     pair = mode == 2 ? allowed : (mode == 1 && allowed && m_tiles_all >= 8 && nprod > 1 && k_steps >= 9);
   }
+  // Shift modes (see Params): stride-1 multi-tap convs load each activation box once per K block and
+  // serve kh (mode 1) or kw (mode 2) taps from it.  ACCFLOW_TC_SHIFT=0 forces one box per tap.
+  static bool shift_env_read = false, shift_enabled = true;
+  if (!shift_env_read) {
+    if (const char* e = getenv("ACCFLOW_TC_SHIFT")) shift_enabled = atoi(e) != 0;
+    shift_env_read = true;
+  }
+  p.mode = 0; p.n_outer = per_sample ? 1 : d.kh * d.kw; p.n_inner = 1;
+  if (shift_enabled && !pair && !per_sample && d.stride == 1 && d.kh * d.kw > 1 && nplanes <= 2 && d.kh <= 7 && d.kw <= 7) {
+    if (d.kh > 1) { p.mode = 1; p.n_outer = d.kw; p.n_inner = d.kh; p.tile_w = 8; p.tile_h = 16; }
+    else if (!tc::mode2_rejected) { p.mode = 2; p.n_outer = d.kh; p.n_inner = d.kw; p.tile_w = 16; p.tile_h = 8; }
+    if (p.mode) {
+      p.tw = 8; p.tw_shift = 3; p.th = 16;
+      p.tiles_x = cdiv(p.out_w, p.tile_w); p.tiles_y = cdiv(p.out_h, p.tile_h);
+    }
+  }
+  p.a_plane_bytes = (tc::BM + 8 * (p.n_inner - 1)) * tc::KC * 2;
+  if (const char* e = getenv("ACCFLOW_TC_DEBUG")) p.debug = atoi(e);
   // N tile: multiple of 32.  Single CTA: the split modes keep two accumulators x two TMEM slots (BN <= 128);
   // CTA pair: each CTA holds half of the weight tile, BN up to 256 (one TMEM slot in the split modes).
   const int bn_cap = pair ? 256 : (nprod == 1 ? 256 : 128);
@@ -950,12 +1056,21 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   if (pair && bn % 64 != 0) bn = cdiv(bn, 64) * 64;      // each CTA's half must be a multiple of 32 rows
   p.bn = bn;
   p.n_tiles = cdiv(d.cout, bn);
-  const int stage_bytes = nplanes * (tc::A_PLANE_BYTES + (pair ? bn / 2 : bn) * tc::KC * 2);
+  const int a_stage = nplanes * p.a_plane_bytes, b_stage = nplanes * (pair ? bn / 2 : bn) * tc::KC * 2;
+  const int stage_bytes = a_stage + b_stage;
   const int epi_bytes = 2 * tc::BM * 20 * 4;                 // two 128 x (16+4)-float epilogue panels
-  int stages = (222 * 1024 - 1024 - epi_bytes) / stage_bytes;
+  const int ring_bytes = 222 * 1024 - 1024 - epi_bytes;
+  int stages = ring_bytes / stage_bytes, stages_b;
   if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
-  ACCFLOW_REQUIRE(stages >= 2, "conv2d_tc: tile does not fit shared memory");
-  p.stages = stages;
+  stages_b = stages;
+  if (p.n_inner > 1) {       // shift modes: two activation boxes in flight, the rest of the ring holds weight tiles
+    stages = 2;
+    stages_b = (ring_bytes - stages * a_stage) / b_stage;
+    if (stages_b > tc::MAX_B_STAGES) stages_b = tc::MAX_B_STAGES;
+    if (ring_bytes - 3 * a_stage - stages_b * b_stage >= 0) stages = 3;
+  }
+  ACCFLOW_REQUIRE(stages >= 2 && stages_b >= 2, "conv2d_tc: tile does not fit shared memory");
+  p.stages = stages; p.stages_b = stages_b;
   p.alpha = d.alpha; p.scale = d.scale; p.shift = d.shift;
   p.act = d.act; p.act_split = d.act_split; p.act2 = d.act2;
   p.residual = d.residual; p.res_ld = d.res_ld; p.post_relu = d.post_relu; p.epilogue = d.epilogue;
@@ -1009,18 +1124,27 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   for (int s = 0; s < d.nsrc; ++s) {
     // activation planes [plane][batch][in_h][in_w][pitch]; box = 64 channels x (tw x th) pixels, strided
     const cuuint64_t pitchb = (cuuint64_t)io.src_pitch[s] * 2;
-    const cuuint64_t gdim[5] = {(cuuint64_t)d.src_c[s], (cuuint64_t)d.in_w, (cuuint64_t)d.in_h, (cuuint64_t)d.batch,
-                                (cuuint64_t)nplanes};
-    const cuuint64_t gstr[4] = {pitchb, pitchb * d.in_w, pitchb * d.in_w * d.in_h, (cuuint64_t)io.src_plane_stride[s] * 2};
-    const cuuint32_t box[5] = {(cuuint32_t)tc::KC, (cuuint32_t)(p.tw * d.stride), (cuuint32_t)(p.th * d.stride), 1, 1};
+    cuuint64_t gdim[5] = {(cuuint64_t)d.src_c[s], (cuuint64_t)d.in_w, (cuuint64_t)d.in_h, (cuuint64_t)d.batch,
+                          (cuuint64_t)nplanes};
+    cuuint64_t gstr[4] = {pitchb, pitchb * d.in_w, pitchb * d.in_w * d.in_h, (cuuint64_t)io.src_plane_stride[s] * 2};
+    cuuint32_t box[5] = {(cuuint32_t)tc::KC, (cuuint32_t)(p.tw * d.stride), (cuuint32_t)(p.th * d.stride), 1, 1};
+    if (p.mode) box[2] = (cuuint32_t)(16 + p.n_inner - 1);           // 8 fast-axis pixels x (16 + halo) slow-axis pixels
+    if (p.mode == 2) {                                               // dims (C, H, W, B, plane): x is the slow axis
+      gdim[1] = (cuuint64_t)d.in_h; gdim[2] = (cuuint64_t)d.in_w;
+      gstr[0] = pitchb * d.in_w; gstr[1] = pitchb;
+    }
     const cuuint32_t estr[5] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1, 1};
     CUresult cr = enc(&maps.a[s], nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(io.src_planes[s]), gdim, gstr, box,
                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS && p.mode == 2) {   // driver refuses the permuted strides: horizontal convs go one box per tap
+      tc::mode2_rejected = true;
+      return accflow_conv2d_tc(dp, iop, wp, nprod, stream);
+    }
     ACCFLOW_REQUIRE(cr == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(source %d) failed (%d)", s, (int)cr);
   }
 
-  const size_t smem = (size_t)stages * stage_bytes + epi_bytes + 1024;
+  const size_t smem = (size_t)stages * a_stage + (size_t)stages_b * b_stage + epi_bytes + 1024;
   static thread_local int cfg_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);

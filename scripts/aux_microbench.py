@@ -11,7 +11,11 @@ B, h, w = int(os.environ.get("MB_PAIRS", "8")), 64, 64
 P = h * w
 dev = "cuda"
 
+ONCE = os.environ.get("MB_ONCE") == "1"   # under ncu: one launch per kernel, no timing loop
+
 def timeit(name, fn, bytes_moved, n=20):
+    if ONCE:
+        fn(); torch.cuda.synchronize(); print(json.dumps({"kernel": name, "MB": round(bytes_moved / 1e6, 1)})); return
     for _ in range(3): fn()
     torch.cuda.synchronize()
     a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -51,3 +55,20 @@ timeit("instnorm 12x256x256x64 (3 kernels)", lambda: K.instnorm(t, True, None, F
 # corr pool
 l1, l2, l3 = (torch.empty(B * P, (h >> l) * (w >> l), device=dev) for l in (1, 2, 3))
 timeit("corr_pool", lambda: L.call("accflow_corr_pool_f32", lv[0].data_ptr(), B * P, h, w, l1.data_ptr(), l2.data_ptr(), l3.data_ptr(), None), B * P * P * 4 * 1.33)
+
+# convex upsample (flow + 576-channel mask -> 8x flow), once per pair
+cflow = torch.randn(B, P, 2, device=dev); mask = torch.randn(B, h, w, 576, device=dev); up = torch.empty(B, 2, 8 * h, 8 * w, device=dev)
+timeit("convex_upsample", lambda: L.call("accflow_convex_upsample_f32", cflow.data_ptr(), 2, 1, mask.data_ptr(), 576, B, h, w, up.data_ptr(), None),
+       B * P * (576 * 4 + 8 + 128 * 4))
+# warp + occlusion (getOcc): binary mask and error map
+c1 = torch.randn(B, h, w, 128, device=dev); c2 = torch.randn(B, h, w, 128, device=dev); wf = torch.randn(B, h, w, 2, device=dev) * 3
+occ = torch.empty(B, h, w, 1, device=dev); emap = torch.empty(B, h, w, 128, device=dev)
+timeit("warp_occ (binary)", lambda: L.call("accflow_warp_occ_f32", c1.data_ptr(), 128, c2.data_ptr(), 128, wf.data_ptr(), B, h, w, 128, occ.data_ptr(), 1, None, 0, None),
+       B * P * (128 * 4 * 2 + 8 + 4))
+timeit("warp_occ (emap)", lambda: L.call("accflow_warp_occ_f32", c1.data_ptr(), 128, c2.data_ptr(), 128, wf.data_ptr(), B, h, w, 128, None, 0, emap.data_ptr(), 128, None),
+       B * P * (128 * 4 * 3 + 8))
+# correlation volume GEMM (fmap1 . fmap2^T / sqrt(D)), level 0 of the pyramid
+f1 = View(torch.randn(B, h, w, 256, device=dev)); f2 = View(torch.randn(B, h, w, 256, device=dev))
+vol = View(lv[0].view(B, h, w, P))
+K.ensure_planes(f1); K.ensure_planes(f2)
+timeit("corr_gemm (fp16x2) [GFLOP in MB field]", lambda: K.gemm_nt("mb.corr", f1, f2, vol, alpha=1.0 / 16), B * 2.0 * P * P * 256 / 1e3)

@@ -65,6 +65,11 @@ CONV_CASES = [
     (2, [64], 32, 32, 96, 1, 1, 2, 0, 0),                # encoder downsample
     (1, [128], 9, 7, 27, 3, 3, 1, 1, 1),                 # ZeroConv2d
     (1, [130], 8, 8, 126, 3, 3, 1, 1, 1),                # cin not a multiple of 4 (scalar loader)
+    (1, [64], 40, 36, 64, 3, 3, 1, 1, 1),                # encoder layer1 shape, several ragged 8x16 tiles
+    (2, [96], 17, 33, 96, 3, 3, 1, 1, 1),                # odd map, cout 96
+    (1, [128, 128, 128, 128], 24, 40, 256, 5, 1, 1, 2, 0),   # GMA GRU (4 sources), vertical taps
+    (1, [128, 128, 128, 128], 24, 40, 128, 1, 5, 1, 0, 2),   # GMA GRU q conv, horizontal taps (x-major tiles)
+    (1, [256], 33, 47, 192, 3, 3, 1, 1, 1),              # convc2: two 96-wide N tiles
 ]
 
 
