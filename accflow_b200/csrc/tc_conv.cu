@@ -247,6 +247,7 @@ template <int NPROD>
 __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
   const uint32_t idesc1 = make_idesc(BM, c.BN, NPROD == 3);
   const uint32_t idesc2 = make_idesc(BM, 2 * c.BN, NPROD == 3);      // a0 x [w0; w1] -> MAIN | CORR
+  const bool comb = c.n_inner == 1;        // operands share the weight ring's barriers (SA == SB, slots advance together)
   int sa = 0, sb = 0;
   uint32_t pa = 0, pb = 0;                                           // ring parities
   uint32_t a_slot = c.smem_a, w_slot = c.smem_b;
@@ -258,7 +259,7 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
     const uint32_t acc_main = c.tmem_base + slot * c.acc_cols, acc_corr = acc_main + c.BN;
     uint32_t first = 0;                                              // 0 -> overwrite the accumulators
     for (int i = 0; i < c.nchunks; ++i) {
-      mbar_wait(&c.afull[sa], pa);
+      if (!comb) mbar_wait(&c.afull[sa], pa);
       uint32_t a_lo = desc_lo(a_slot);
       for (int j = 0; j < c.n_inner; ++j) {
         mbar_wait(&c.bfull[sb], pb);
@@ -291,7 +292,7 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
         w_slot += c.b_stage;
         if (++sb == c.SB) { sb = 0; pb ^= 1; w_slot = c.smem_b; }
       }
-      umma_commit(&c.afree[sa]);                                     // ... and so is the activation box
+      if (!comb) umma_commit(&c.afree[sa]);                          // ... and so is the activation box
       a_slot += c.a_stage;
       if (++sa == c.SA) { sa = 0; pa ^= 1; a_slot = c.smem_a; }
     }
@@ -358,6 +359,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   if (warp == 0) {
     // ================================ TMA producer ============================================
     if (lane == 0) {
+      const bool comb = n_inner == 1;
       int sa = 0, sb = 0;                                    // ring positions (A boxes, weight tiles)
       uint32_t pa = 1, pb = 1;                               // parity of the "free" phase to wait for (first lap passes)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -369,9 +371,17 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         const int ox0 = tile_x * p.tile_w, oy0 = tile_y * p.tile_h, n0 = n_tile * BN;
         Chunk ck{0, 0, 0};                                   // ck.tap = outer tap index
         for (int i = 0; i < nchunks; ++i) {
-          mbar_wait(&bar_afree[sa], pa);
-          uint8_t* adst = smem + (size_t)sa * a_stage;
-          mbar_expect_tx(&bar_afull[sa], (p.debug & 1) ? 0u : (uint32_t)a_stage);
+          // n_inner == 1 (one weight tile per activation box): both operands share the weight ring's
+          // barriers and slot index, i.e. one handshake per K step instead of two.
+          uint64_t* abar = comb ? &bar_bfull[sb] : &bar_afull[sa];
+          uint8_t* adst = smem + (size_t)(comb ? sb : sa) * a_stage;
+          if (comb) {
+            mbar_wait(&bar_bfree[sb], pb);
+            mbar_expect_tx(abar, (p.debug & 1) ? 0u : (uint32_t)(a_stage + b_stage));
+          } else {
+            mbar_wait(&bar_afree[sa], pa);
+            mbar_expect_tx(abar, (p.debug & 1) ? 0u : (uint32_t)a_stage);
+          }
           int c1, c2;                                        // box origin along tensor-map dims 1, 2
           if (p.mode == 0) {
             const int ky = ck.tap / p.kw, kx = ck.tap - ky * p.kw;
@@ -382,12 +392,14 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             c1 = oy0 + ck.tap - p.pad_h; c2 = ox0 - p.pad_w;
           }
           for (int pl = 0; pl < NPL && !(p.debug & 1); ++pl)
-            tma_load_5d(adst + pl * a_plane_bytes, &maps.a[ck.s], &bar_afull[sa], ck.c0, c1, c2, sample, pl);
+            tma_load_5d(adst + pl * a_plane_bytes, &maps.a[ck.s], abar, ck.c0, c1, c2, sample, pl);
           const int kcoord = p.src_off[ck.s] + ck.c0;
           for (int j = 0; j < n_inner; ++j) {
-            mbar_wait(&bar_bfree[sb], pb);
             uint8_t* wdst = smem_b + (size_t)sb * b_stage;
-            mbar_expect_tx(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)b_stage);
+            if (!comb) {
+              mbar_wait(&bar_bfree[sb], pb);
+              mbar_expect_tx(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)b_stage);
+            }
             const int tap = p.per_sample ? sample : p.mode == 0 ? ck.tap : p.mode == 1 ? j * p.kw + ck.tap : ck.tap * p.kw + j;
             for (int pl = 0; pl < NPL && !(p.debug & 1); ++pl)
               tma_load_4d(wdst + pl * w_plane_bytes, &maps.w, &bar_bfull[sb], kcoord, n0, tap, pl);
@@ -468,7 +480,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        __syncwarp();                         // the panel rows this warp reads back are the ones it staged
         const int nb = n0 + c + pc4 * 4;
         if (nb < p.cout && !(p.debug & 4)) {
           const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
@@ -477,7 +489,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           const bool vec4 = nb + 3 < p.cout;
 #pragma unroll 2
           for (int itr = 0; itr < 4; ++itr) {
-            const int row = itr * 32 + (st >> 2);
+            const int row = 32 * (warp & 3) + itr * 8 + (lane >> 2);
             const int r_slow = row >> p.tw_shift, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
             const int oy = oy0 + (p.mode == 2 ? r_fast : r_slow), ox = ox0 + (p.mode == 2 ? r_slow : r_fast);
             if (oy >= p.out_h || ox >= p.out_w) continue;
@@ -541,7 +553,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             }
           }
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        __syncwarp();
       }
     }
   }
