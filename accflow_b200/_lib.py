@@ -66,6 +66,7 @@ SIGNATURES = {
     "accflow_conv3x3_smallcout_f32": [fp, i, i, i, i, i, fp, fp, fp, i, i, fp, i, fp],
     "accflow_coords_init_f32": [fp, i, i, i, fp, fp],
     "accflow_axpy_f32": [fp, fp, f, ll, fp],
+    "accflow_tapsum3x3_f32": [fp, i, i, i, i, i, fp, fp, i, fp, i, fp, i, fp],
     "accflow_convex_upsample_f32": [fp, i, i, fp, i, i, i, i, fp, fp],
     "accflow_downflow8_f32": [fp, i, i, i, fp, fp],
     "accflow_warp_occ_f32": [fp, i, fp, i, fp, i, i, i, i, fp, i, fp, i, fp],

@@ -505,21 +505,33 @@ __global__ void __launch_bounds__(256) flow_patch_kernel(const float* __restrict
                                                          float* __restrict__ out, int out_ld,
                                                          __nv_bfloat16* __restrict__ out_pl, int pl_pitch,
                                                          long long pl_stride, int nplanes) {
+  // thread -> (pixel, tap): both flow channels of a tap are one float2; taps 49.. are the zero padding
+  const int taps = out_ld >> 1;
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long total = (long long)batch * h * w * out_ld;
-  if (i >= total) return;
-  const long long pix = i / out_ld;
-  const int k = (int)(i - pix * out_ld);
-  float v = 0.f;
-  if (k < 98) {
-    const int tap = k >> 1, c = k & 1;
+  if (i >= (long long)batch * h * w * taps) return;
+  const long long pix = i / taps;
+  const int tap = (int)(i - pix * taps);
+  float2 v = make_float2(0.f, 0.f);
+  if (tap < 49) {
     const int hw = h * w;
     const int b = (int)(pix / hw), pl = (int)(pix - (long long)b * hw);
-    const int y = pl / w + tap / 7 - 3, x = pl % w + tap % 7 - 3;
-    if (y >= 0 && y < h && x >= 0 && x < w) v = __ldg(flow + ((long long)(b * h + y) * w + x) * 2 + c);
+    const int ky = tap / 7, y = pl / w + ky - 3, x = pl % w + (tap - ky * 7) - 3;
+    if (y >= 0 && y < h && x >= 0 && x < w) v = __ldg(reinterpret_cast<const float2*>(flow) + (long long)(b * h + y) * w + x);
   }
-  out[i] = v;
-  if (out_pl) store_planes(out_pl + pix * pl_pitch + k, pl_stride, nplanes, v);
+  if (out) *reinterpret_cast<float2*>(out + pix * out_ld + 2 * tap) = v;
+  if (out_pl) {
+    __nv_bfloat16* d = out_pl + pix * pl_pitch + 2 * tap;
+    if (nplanes == 2) {          // fp16 hi + pre-scaled fp16 lo
+      const __half2 hi = __floats2half2_rn(v.x, v.y);
+      const float2 hf = __half22float2(hi);
+      *reinterpret_cast<__half2*>(d) = hi;
+      *reinterpret_cast<__half2*>(d + pl_stride) =
+          __floats2half2_rn((v.x - hf.x) * ACCFLOW_FP16X2_SCALE, (v.y - hf.y) * ACCFLOW_FP16X2_SCALE);
+    } else {
+      store_planes(d, pl_stride, nplanes, v.x);
+      store_planes(d + 1, pl_stride, nplanes, v.y);
+    }
+  }
 }
 
 template <int CIN, int KS, int STRIDE, int COUT, bool NCHW>
@@ -659,11 +671,50 @@ extern "C" int accflow_conv3x3_smallcout_f32(const float* x, int x_ld, int batch
   return fail(-1, "conv3x3_smallcout: cin must be 128 or 256 (got %d)", cin);
 }
 
+// 3x3 convolution with <= 4 output channels, second half.  The tensor-core path evaluates the filter as a
+// 1x1 convolution with 9*cout outputs, T[pix][tap*cout + o] = sum_c w[o][c][tap] * x[pix][c]  (every activation
+// is read once instead of nine times); this kernel adds the nine shifted taps, applies the affine and the
+// activation, and optionally accumulates the result into a second tensor (coords += delta_flow, raft.py:136).
+__global__ void __launch_bounds__(256) tapsum3x3_kernel(const float* __restrict__ t, int t_ld, int batch, int h, int w,
+                                                        int cout, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, int act,
+                                                        float* __restrict__ out, int out_ld, float* accum, int accum_ld) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (long long)batch * h * w * cout) return;
+  const long long pix = i / cout;
+  const int o = (int)(i - pix * cout);
+  const int hw = h * w;
+  const int b = (int)(pix / hw), pl = (int)(pix - (long long)b * hw);
+  const int py = pl / w, px = pl - py * w;
+  float acc = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+    if (iy >= 0 && iy < h && ix >= 0 && ix < w) acc += __ldg(t + ((long long)(b * h + iy) * w + ix) * t_ld + tap * cout + o);
+  }
+  const float r = act_apply(fmaf(acc, scale ? __ldg(scale + o) : 1.f, shift ? __ldg(shift + o) : 0.f), act);
+  out[pix * out_ld + o] = r;
+  if (accum) accum[pix * accum_ld + o] += r;
+}
+
+extern "C" int accflow_tapsum3x3_f32(const float* t, int t_ld, int batch, int h, int w, int cout, const float* scale,
+                                     const float* shift, int act, float* out, int out_ld, float* accum, int accum_ld,
+                                     void* stream) {
+  ACCFLOW_REQUIRE(t && out && batch > 0 && h > 0 && w > 0 && cout >= 1 && cout <= 4 && t_ld >= 9 * cout && out_ld >= cout &&
+                      (!accum || accum_ld >= cout), "tapsum3x3: bad arguments");
+  const long long total = (long long)batch * h * w * cout;
+  tapsum3x3_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(t, t_ld, batch, h, w, cout, scale, shift, act, out,
+                                                                       out_ld, accum, accum_ld);
+  return launched("tapsum3x3");
+}
+
 extern "C" int accflow_flow_patch_f32(const float* flow, int batch, int h, int w, float* out, int out_ld, void* out_planes,
                                       int pl_pitch, long long pl_stride, int nplanes, void* stream) {
-  ACCFLOW_REQUIRE(flow && out && batch > 0 && h > 0 && w > 0 && out_ld >= 98, "flow_patch: bad arguments");
-  ACCFLOW_REQUIRE(!out_planes || (nplanes >= 1 && nplanes <= 3), "flow_patch: nplanes must be 1, 2 or 3");
-  const long long total = (long long)batch * h * w * out_ld;
+  ACCFLOW_REQUIRE(flow && (out || out_planes) && batch > 0 && h > 0 && w > 0 && out_ld >= 98 && out_ld % 2 == 0,
+                  "flow_patch: bad arguments (out_ld even and >= 98; fp32 out and/or planes)");
+  ACCFLOW_REQUIRE(!out_planes || (nplanes >= 1 && nplanes <= 3 && pl_pitch % 2 == 0 && pl_stride % 2 == 0),
+                  "flow_patch: nplanes must be 1, 2 or 3, even plane pitch");
+  const long long total = (long long)batch * h * w * (out_ld / 2);
   flow_patch_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(flow, batch, h, w, out, out_ld,
                                                                         reinterpret_cast<__nv_bfloat16*>(out_planes),
                                                                         pl_pitch, pl_stride, nplanes);

@@ -508,7 +508,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
 #pragma unroll
                   for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
                 }
-                *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
+                if (p.out) *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
                 if (p.out_pl.ptr) store_planes4(p.out_pl, NPL, pix, nb, y);
               } else {
 #pragma unroll
@@ -523,7 +523,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
                       p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
                       if (p.out2_pl.ptr) store_planes1(p.out2_pl, NPL, pix, n - p.act_split, o);
                     } else {
-                      p.out[pix * p.out_ld + n] = o;
+                      if (p.out) p.out[pix * p.out_ld + n] = o;
                       if (p.out_pl.ptr) store_planes1(p.out_pl, NPL, pix, n, o);
                     }
                   }
@@ -540,7 +540,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
                 const int n = nb - hd;
                 const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + n);
                 float o[4] = {g4[0] * hh.x, g4[1] * hh.y, g4[2] * hh.z, g4[3] * hh.w};
-                *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
+                if (p.out2) *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
                 if (p.out2_pl.ptr) store_planes4(p.out2_pl, NPL, pix, n, o);
               }
             } else {
@@ -833,7 +833,7 @@ conv_tc2_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPa
 #pragma unroll
                   for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
                 }
-                *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
+                if (p.out) *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
                 if (p.out_pl.ptr) store_planes4(p.out_pl, NPL, pix, nb, y);
               } else {
 #pragma unroll
@@ -848,7 +848,7 @@ conv_tc2_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPa
                       p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
                       if (p.out2_pl.ptr) store_planes1(p.out2_pl, NPL, pix, n - p.act_split, o);
                     } else {
-                      p.out[pix * p.out_ld + n] = o;
+                      if (p.out) p.out[pix * p.out_ld + n] = o;
                       if (p.out_pl.ptr) store_planes1(p.out_pl, NPL, pix, n, o);
                     }
                   }
@@ -865,7 +865,7 @@ conv_tc2_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPa
                 const int n = nb - hd;
                 const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + n);
                 float o[4] = {g4[0] * hh.x, g4[1] * hh.y, g4[2] * hh.z, g4[3] * hh.w};
-                *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
+                if (p.out2) *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
                 if (p.out2_pl.ptr) store_planes4(p.out2_pl, NPL, pix, n, o);
               }
             } else {
@@ -1097,11 +1097,12 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
                       plane_out(io.h_planes, io.h_pitch, io.h_plane_stride, p.h_pl),
                   "conv2d_tc: output planes must be 8B aligned with pitch % 4 == 0");
   if (d.epilogue == ACCFLOW_EPI_STORE) {
-    ACCFLOW_REQUIRE(d.out != nullptr, "conv2d_tc: null output");
+    ACCFLOW_REQUIRE(d.out != nullptr || io.out_planes != nullptr, "conv2d_tc: null output (fp32 and planes)");
   } else if (d.epilogue == ACCFLOW_EPI_GRU_ZR) {
-    ACCFLOW_REQUIRE(d.z && d.h && d.out2 && d.cout % 8 == 0, "conv2d_tc: GRU_ZR needs z, h, out2 and cout % 8 == 0");
+    ACCFLOW_REQUIRE(d.z && d.h && (d.out2 || io.out2_planes) && d.cout % 8 == 0,
+                    "conv2d_tc: GRU_ZR needs z, h, out2 (fp32 and/or planes) and cout % 8 == 0");
     ACCFLOW_REQUIRE(aligned16(d.z) && aligned16(d.h) && aligned16(d.out2) && d.z_ld % 4 == 0 && d.h_ld % 4 == 0 &&
-                        d.out2_ld % 4 == 0, "conv2d_tc: GRU buffers must be 16B aligned");
+                        (!d.out2 || d.out2_ld % 4 == 0), "conv2d_tc: GRU buffers must be 16B aligned");
   } else if (d.epilogue == ACCFLOW_EPI_GRU_Q) {
     ACCFLOW_REQUIRE(d.z && d.h && d.cout % 4 == 0, "conv2d_tc: GRU_Q needs z, h and cout % 4 == 0");
     ACCFLOW_REQUIRE(aligned16(d.z) && aligned16(d.h) && d.z_ld % 4 == 0 && d.h_ld % 4 == 0,
@@ -1109,7 +1110,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   } else {
     return fail(-1, "conv2d_tc: unknown epilogue %d", d.epilogue);
   }
-  p.out_vec = d.epilogue == ACCFLOW_EPI_STORE && d.act_split == 0 && aligned16(d.out) && d.out_ld % 4 == 0 &&
+  p.out_vec = d.epilogue == ACCFLOW_EPI_STORE && d.act_split == 0 && aligned16(d.out) && (!d.out || d.out_ld % 4 == 0) &&
               (!d.residual || (aligned16(d.residual) && d.res_ld % 4 == 0));
 
   tc::EncodeTiledFn enc = tc::encode_fn();

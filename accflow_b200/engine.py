@@ -108,6 +108,19 @@ class PackedConv:
             self._as1x1 = pc
         return self._as1x1
 
+    def as_taps1x1(self) -> "PackedConv":
+        """A 3x3 filter with few outputs as a 1x1 conv with 9*cout outputs (row = tap*cout + o); bias, scale and
+        activation are applied after the nine taps are summed (accflow_tapsum3x3_f32)."""
+        if getattr(self, "_astaps", None) is None:
+            w = self.w_oihw.permute(2, 3, 0, 1).reshape(self.kh * self.kw * self.cout, self.cin, 1, 1).contiguous()
+            pc = PackedConv.__new__(PackedConv)
+            pc.w_oihw, pc._tc, pc._as1x1, pc._astaps = w, None, None, None
+            pc.cout, pc.cin, pc.kh, pc.kw = w.shape
+            pc.stride, pc.pad_h, pc.pad_w, pc.cout_pad = 1, 0, 0, (pc.cout + 3) // 4 * 4
+            pc.w, pc.scale, pc.shift, pc.has_bias = None, None, None, False
+            self._astaps = pc
+        return self._astaps
+
     def tc_weights(self, fp16x2: bool = False) -> "L.TcWeights":
         """16-bit operand planes [planes][taps][cout][k_pitch] for accflow_conv2d_tc."""
         if self._tc is None:
@@ -241,7 +254,9 @@ class Kernels:
              act_split=0, act2=L.ACT_NONE, out2: Optional[View] = None, residual: Optional[View] = None,
              post_relu=False, epilogue=L.EPI_STORE, h: Optional[View] = None, z: Optional[View] = None,
              weight_ptr: Optional[int] = None, weight_batch_stride=0, cout=None, cout_pad=None,
-             use_affine=True, tc_b: Optional["L.TcWeights"] = None, tc_src_planes=None):
+             use_affine=True, tc_b: Optional["L.TcWeights"] = None, tc_src_planes=None, planes_only=False):
+        """``planes_only``: the output (``out``; ``out2`` for the GRU z|r epilogue) is read by tensor-core
+        convolutions only, so in the tensor-core modes its fp32 copy is not written (half the store bytes)."""
         d = L.ConvDesc()
         cin = 0
         for k, s in enumerate(srcs):
@@ -296,6 +311,11 @@ class Kernels:
                     written.append(tv)
                 else:
                     self.wrote(tv)
+            if planes_only and written:      # the planes carry the result; drop the fp32 store
+                if epilogue == L.EPI_STORE and not act_split and written[0] is out:
+                    d.out = None
+                elif epilogue == L.EPI_GRU_ZR and written[0] is out2:
+                    d.out2 = None
             tw = tc_b if tc_b is not None else pc.tc_weights(self.precision == "fp16x2")
             args = ("accflow_conv2d_tc", C.byref(d), C.byref(io), C.byref(tw), self.NPROD[self.precision], _stream())
         else:
@@ -332,24 +352,38 @@ class Kernels:
                act, out.ptr, out.ld, pl[0], pl[1], pl[2], self.nplanes, _stream())
         self._done(out, pl[0] is not None)
 
-    def flow_conv7(self, tag: str, flow: torch.Tensor, batch: int, h: int, w: int, pc: PackedConv, out: View):
+    def flow_conv7(self, tag: str, flow: torch.Tensor, batch: int, h: int, w: int, pc: PackedConv, out: View,
+                   planes_only=False):
         """relu(conv7x7(flow)) for a 2-channel flow field [batch, h*w, 2] (raft/update.py:92, AccFlow_.py:62)."""
         if not self.tc:
             self.conv_smallc(flow.data_ptr(), False, batch, 2, h, w, pc, L.ACT_RELU, out)
             return
         patch = self.view(tag + ".fpatch", batch, h, w, 104)
         pl = self.planes_ptr(patch, create=True)
-        L.call("accflow_flow_patch_f32", flow.data_ptr(), batch, h, w, patch.ptr, patch.ld, pl[0], pl[1], pl[2],
-               self.nplanes, _stream())
+        L.call("accflow_flow_patch_f32", flow.data_ptr(), batch, h, w, None, patch.ld, pl[0], pl[1], pl[2],
+               self.nplanes, _stream())          # planes only: nothing reads the fp32 patch
         self._stale[patch.t.data_ptr()] = []
-        self.conv(pc.as_1x1(), [patch.ch(0, 98)], out, act=L.ACT_RELU)
+        self.conv(pc.as_1x1(), [patch.ch(0, 98)], out, act=L.ACT_RELU, planes_only=planes_only)
 
-    def conv_smallcout(self, pc: PackedConv, x: View, out: View, act=L.ACT_NONE):
-        """3x3 conv with <= 4 output channels on the bandwidth kernel (always fp32 arithmetic)."""
+    def conv_smallcout(self, pc: PackedConv, x: View, out: View, act=L.ACT_NONE, accum: Optional[torch.Tensor] = None,
+                       accum_ld: int = 0):
+        """3x3 conv with <= 4 output channels; ``accum`` (optional, [pixels, accum_ld]) += result.
+        Tensor-core modes: a 1x1 conv with 9*cout outputs (each activation read once) + a 9-tap sum;
+        fp32 mode: the FFMA bandwidth kernel."""
         assert pc.kh == 3 and pc.kw == 3 and pc.stride == 1 and pc.cout <= 4 and pc.cout_pad == 4 and x.c == pc.cin
-        L.call("accflow_conv3x3_smallcout_f32", x.ptr, x.ld, x.b, x.h, x.w, x.c, pc.w.data_ptr(),
-               None if pc.scale is None else pc.scale.data_ptr(), pc.shift.data_ptr(), pc.cout, act, out.ptr, out.ld,
-               _stream())
+        scale = None if pc.scale is None else pc.scale.data_ptr()
+        if self.tc:
+            n9 = 9 * pc.cout
+            t = self.view(f"tapsum{n9}", x.b, x.h, x.w, (n9 + 3) // 4 * 4)
+            self.conv(pc.as_taps1x1(), [x], t.ch(0, n9))
+            L.call("accflow_tapsum3x3_f32", t.ptr, t.ld, x.b, x.h, x.w, pc.cout, scale, pc.shift.data_ptr(), act,
+                   out.ptr, out.ld, None if accum is None else accum.data_ptr(), accum_ld, _stream())
+        else:
+            L.call("accflow_conv3x3_smallcout_f32", x.ptr, x.ld, x.b, x.h, x.w, x.c, pc.w.data_ptr(), scale,
+                   pc.shift.data_ptr(), pc.cout, act, out.ptr, out.ld, _stream())
+            if accum is not None:
+                assert accum_ld == out.ld == pc.cout
+                L.call("accflow_axpy_f32", accum.data_ptr(), out.ptr, 1.0, x.b * x.h * x.w * pc.cout, _stream())
         self.wrote(out)
 
     def corr_lookup(self, lv, radius: int, coords: torch.Tensor, out: View, flow: torch.Tensor, mf_tail: View):
@@ -702,23 +736,22 @@ class FlowEstimatorEngine:
                coords.data_ptr(), s())
         for _ in range(iters):
             k.corr_lookup(lv, self.RADIUS, coords, corr, flow, mf.ch(126, 128))
-            k.conv(self.convc1, [corr], cor1, act=L.ACT_RELU)
-            k.conv(self.convc2, [cor1], cf.ch(0, 192), act=L.ACT_RELU)
-            k.flow_conv7(tag, flow, B, h, w, self.convf1, flo1)
-            k.conv(self.convf2, [flo1], cf.ch(192, 256), act=L.ACT_RELU)
-            k.conv(self.convm, [cf], mf.ch(0, 126), act=L.ACT_RELU)
+            k.conv(self.convc1, [corr], cor1, act=L.ACT_RELU, planes_only=True)
+            k.conv(self.convc2, [cor1], cf.ch(0, 192), act=L.ACT_RELU, planes_only=True)
+            k.flow_conv7(tag, flow, B, h, w, self.convf1, flo1, planes_only=True)
+            k.conv(self.convf2, [flo1], cf.ch(192, 256), act=L.ACT_RELU, planes_only=True)
+            k.conv(self.convm, [cf], mf.ch(0, 126), act=L.ACT_RELU, planes_only=not self.gma)
             if self.gma:
                 # Aggregate.forward (gma/modules.py:102-115): mf + gamma * (attn @ to_v(mf))
                 k.conv(self.to_v, [mf], vbuf)
                 k.gemm_nn(tag + ".agg", View(st["attn"].view(B, h, w, P)), vbuf, mfg, alpha=self.gamma, residual=mf)
             for zr, q in self.gru:
-                k.conv(zr, [hid] + x_srcs, epilogue=L.EPI_GRU_ZR, h=hid, z=z, out2=rh)
+                k.conv(zr, [hid] + x_srcs, epilogue=L.EPI_GRU_ZR, h=hid, z=z, out2=rh, planes_only=True)
                 k.conv(q, [rh] + x_srcs, epilogue=L.EPI_GRU_Q, h=hid, z=z)
-            k.conv(self.fh1, [hid], fh, act=L.ACT_RELU)
-            k.conv_smallcout(self.fh2, fh, delta)
-            L.call("accflow_axpy_f32", coords.data_ptr(), delta.ptr, 1.0, B * P * 2, s())
+            k.conv(self.fh1, [hid], fh, act=L.ACT_RELU, planes_only=True)
+            k.conv_smallcout(self.fh2, fh, delta, accum=coords, accum_ld=2)     # coords1 += delta_flow
         # mask head + convex upsample: only the last iteration's is observable (raft.py:139-146)
-        k.conv(self.mk1, [hid], fh, act=L.ACT_RELU)
+        k.conv(self.mk1, [hid], fh, act=L.ACT_RELU, planes_only=True)
         mask = k.view(tag + ".mask", B, h, w, 576)
         k.conv(self.mk2, [fh], mask)
         out = torch.empty(B, 2, H, W, device=self.device, dtype=F32)

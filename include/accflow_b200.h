@@ -106,7 +106,9 @@ typedef struct accflow_tc_weights {
 /* bf16 planes that travel next to the fp32 activations (x = p0 + p1 + p2): element (plane, pixel,
  * channel) of a slice lives at planes[plane*plane_stride + pixel*pitch + channel].  Sources are
  * mandatory (the tensor cores read only planes); the planes of the outputs are optional and
- * are written by the epilogue so that the next convolution can consume them without a pass. */
+ * are written by the epilogue so that the next convolution can consume them without a pass.
+ * An output whose only consumers are tensor-core convolutions may be planes-only: pass the planes
+ * here and a NULL fp32 pointer (`out`, or `out2` of the GRU z|r epilogue) in the descriptor. */
 typedef struct accflow_tc_io {
   const void* src_planes[ACCFLOW_MAX_SRC];
   int src_pitch[ACCFLOW_MAX_SRC];
@@ -195,6 +197,14 @@ ACCFLOW_API int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, co
 /* coords1 = grid + flow_init (raft/raft.py:121-124); flow_init NULL -> zeros.  NCHW (B,2,h,w) in. */
 ACCFLOW_API int accflow_coords_init_f32(const float* flow_init_nchw, int batch, int h, int w, float* coords, void* stream);
 /* coords += delta ([B,h*w,2] both; raft/raft.py:136) */
+/* Second half of a 3x3 conv with cout <= 4 evaluated as a 1x1 conv with 9*cout outputs on the tensor cores
+ * (FlowHead.conv2 raft/update.py:13-14, FlowDecoder.flow[2] AccFlow_.py:40-45, Blending mask AccFlow_.py:122):
+ * out[n,y,x,o] = act(scale[o] * sum_tap t[n, y+ky-1, x+kx-1, tap*cout + o] + shift[o]), zero outside the map;
+ * if accum != NULL also accum[pix*accum_ld + o] += out (coords1 = coords1 + delta_flow, raft/raft.py:136). */
+ACCFLOW_API int accflow_tapsum3x3_f32(const float* t, int t_ld, int batch, int h, int w, int cout, const float* scale,
+                                      const float* shift, int act, float* out, int out_ld, float* accum, int accum_ld,
+                                      void* stream);
+
 ACCFLOW_API int accflow_axpy_f32(float* y, const float* x, float a, long long n, void* stream);
 
 /* Convex 8x upsampling (raft/raft.py:81-92, gma/gma.py:57-68, AccFlow_.py:27-38).

@@ -281,6 +281,55 @@ def test_conv3x3_smallcout(K):
         assert maxdiff(out.permute(0, 3, 1, 2), ref) < 1e-5
 
 
+def test_conv3x3_smallcout_all_modes(KP):
+    """The same op in every arithmetic mode (tensor-core modes: 1x1 conv with 9*cout outputs + tap sum),
+    including the fused accumulate (coords1 += delta_flow, raft/raft.py:136) and ragged map sizes."""
+    K, tol = KP
+    from accflow_b200 import _lib as L
+    from accflow_b200.engine import PackedConv, View
+    g = torch.Generator().manual_seed(19)
+    for cout, act, tact, hw in ((2, L.ACT_NONE, lambda t: t, (13, 11)), (1, L.ACT_SIGMOID, torch.sigmoid, (9, 20)),
+                                (2, L.ACT_NONE, lambda t: t, (16, 16))):
+        x = torch.randn(2, 256, *hw, generator=g)
+        w = torch.randn(cout, 256, 3, 3, generator=g) * 0.02
+        b = torch.randn(cout, generator=g)
+        ref = tact(F.conv2d(x, w, b, padding=1))
+        out = torch.empty(2, *hw, cout, device="cuda")
+        acc0 = torch.randn(2, *hw, cout, generator=g)
+        acc = acc0.cuda()
+        K.conv_smallcout(PackedConv([dev(w)], [dev(b)], 1, (1, 1)), View(dev(nhwc(x))), View(out), act=act,
+                         accum=acc, accum_ld=cout)
+        torch.cuda.synchronize()
+        assert maxdiff(out.permute(0, 3, 1, 2), ref) < tol
+        assert maxdiff(acc.permute(0, 3, 1, 2), acc0.permute(0, 3, 1, 2) + ref) < tol
+
+
+def test_flow_conv7_all_modes(KP):
+    """7x7 2->128 flow conv (raft/update.py:85,92): patch gather (planes only) + K=98 1x1 conv, planes-only output
+    consumed by a following tensor-core conv."""
+    K, tol = KP
+    from accflow_b200 import _lib as L
+    from accflow_b200.engine import PackedConv, View
+    g = torch.Generator().manual_seed(23)
+    B, h, w = 2, 12, 20
+    flow = torch.randn(B, 2, h, w, generator=g) * 3
+    w7 = torch.randn(128, 2, 7, 7, generator=g) * 0.1
+    b7 = torch.randn(128, generator=g) * 0.1
+    w3 = torch.randn(64, 128, 3, 3, generator=g) * 0.03
+    b3 = torch.randn(64, generator=g) * 0.1
+    mid = torch.relu(F.conv2d(flow, w7, b7, padding=3))
+    ref = torch.relu(F.conv2d(mid, w3, b3, padding=1))
+    pc7, pc3 = PackedConv([dev(w7)], [dev(b7)], 1, (3, 3)), PackedConv([dev(w3)], [dev(b3)], 1, (1, 1))
+    fl = dev(flow.permute(0, 2, 3, 1).reshape(B, h * w, 2).contiguous())
+    flo1 = View(torch.empty(B, h, w, 128, device="cuda"))
+    out = View(torch.empty(B, h, w, 64, device="cuda"))
+    for it in range(2):      # second pass: the planes of flo1 exist, so its fp32 copy is skipped
+        K.flow_conv7("t7", fl, B, h, w, pc7, flo1, planes_only=True)
+        K.conv(pc3, [flo1], out, act=L.ACT_RELU)
+    torch.cuda.synchronize()
+    assert maxdiff(out.t.permute(0, 3, 1, 2), ref) < tol * 3
+
+
 def test_softmax_and_transpose(K):
     from accflow_b200.engine import View
     g = torch.Generator().manual_seed(8)
