@@ -58,6 +58,7 @@ SIGNATURES = {
     "accflow_conv_smallc_f32": [fp, i, i, i, i, i, fp, fp, fp, i, i, i, i, fp, i, fp, i, ll, i, fp],
     "accflow_instnorm_chunks": [i],
     "accflow_instnorm_f32": [fp, i, i, i, f, i, fp, i, fp, fp, fp, fp],
+    "accflow_instnorm_planes_f32": [fp, i, i, i, f, i, fp, i, fp, fp, fp, fp, i, ll, i, fp],
     "accflow_nhwc_transpose_f32": [fp, i, i, i, i, fp, i, fp],
     "accflow_corr_pool_f32": [fp, ll, i, i, fp, fp, fp, fp],
     "accflow_corr_lookup_f32": [fp, fp, fp, fp, i, i, i, i, fp, fp, i, fp, fp, i, fp, i, ll, fp, i, ll, i, fp],

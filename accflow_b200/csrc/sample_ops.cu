@@ -73,7 +73,9 @@ __global__ void instnorm_finalize_kernel(const float* __restrict__ x, const floa
 // x and out may alias (in-place normalisation): no __restrict__ / read-only loads on them.
 __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* x, const float* __restrict__ stats,
                                                              long long n4, int hw, int c, int relu,
-                                                             const float* residual, int post_relu, float* out) {
+                                                             const float* residual, int post_relu, float* out,
+                                                             __nv_bfloat16* out_pl, int pl_pitch, long long pl_stride,
+                                                             int nplanes) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n4) return;
   const int c4n = c >> 2;
@@ -95,7 +97,8 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* x, con
 #pragma unroll
     for (int k = 0; k < 4; ++k) r[k] = fmaxf(r[k], 0.f);
   }
-  reinterpret_cast<float4*>(out)[i] = make_float4(r[0], r[1], r[2], r[3]);
+  if (out) reinterpret_cast<float4*>(out)[i] = make_float4(r[0], r[1], r[2], r[3]);
+  if (out_pl) store_planes4_at(out_pl + (i / c4n) * pl_pitch + c4 * 4, pl_stride, nplanes, r);   // operand planes for the next conv
 }
 
 // =============================== transpose [B,HW,C] -> [B,C,HW] ============================
@@ -570,7 +573,18 @@ extern "C" int accflow_instnorm_chunks(int hw) { return cdiv(hw, IN_CHUNK); }
 extern "C" int accflow_instnorm_f32(const float* x, int batch, int hw, int c, float eps, int relu,
                                     const float* residual, int post_relu, float* out, float* partial,
                                     float* stats, void* stream) {
-  ACCFLOW_REQUIRE(x && out && partial && stats, "instnorm: null pointer");
+  return accflow_instnorm_planes_f32(x, batch, hw, c, eps, relu, residual, post_relu, out, partial, stats, nullptr, 0, 0, 0,
+                                     stream);
+}
+
+extern "C" int accflow_instnorm_planes_f32(const float* x, int batch, int hw, int c, float eps, int relu,
+                                           const float* residual, int post_relu, float* out, float* partial,
+                                           float* stats, void* out_planes, int pl_pitch, long long pl_stride, int nplanes,
+                                           void* stream) {
+  ACCFLOW_REQUIRE(x && (out || out_planes) && partial && stats, "instnorm: null pointer");
+  ACCFLOW_REQUIRE(!out_planes || (nplanes >= 1 && nplanes <= 3 && pl_pitch % 4 == 0 && pl_pitch >= c && pl_stride % 4 == 0 &&
+                                  (reinterpret_cast<uintptr_t>(out_planes) & 7u) == 0),
+                  "instnorm: planes must be 8B aligned, pitch %% 4 == 0, nplanes 1..3");
   ACCFLOW_REQUIRE(batch > 0 && hw > 0 && c > 0 && c <= 256 && c % 4 == 0, "instnorm: bad shape b=%d hw=%d c=%d", batch, hw, c);
   ACCFLOW_REQUIRE(aligned16(x) && aligned16(out) && aligned16(stats) && (!residual || aligned16(residual)), "instnorm: 16B alignment");
   const int chunks = cdiv(hw, IN_CHUNK);
@@ -579,7 +593,8 @@ extern "C" int accflow_instnorm_f32(const float* x, int batch, int hw, int c, fl
   instnorm_finalize_kernel<<<batch, 256, 0, ST>>>(x, partial, hw, c, chunks, eps, stats);
   if (int e = launched("instnorm_finalize")) return e;
   const long long n4 = (long long)batch * hw * c / 4;
-  instnorm_apply_kernel<<<cdiv(n4, 256), 256, 0, ST>>>(x, stats, n4, hw, c, relu, residual, post_relu, out);
+  instnorm_apply_kernel<<<cdiv(n4, 256), 256, 0, ST>>>(x, stats, n4, hw, c, relu, residual, post_relu, out,
+                                                       reinterpret_cast<__nv_bfloat16*>(out_planes), pl_pitch, pl_stride, nplanes);
   return launched("instnorm_apply");
 }
 

@@ -172,10 +172,6 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n, bool fp16) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
 
 struct Chunk {  // iterator over (tap, source, 64-channel block)
   int tap, s, c0;
@@ -194,29 +190,7 @@ struct Chunk {  // iterator over (tap, source, 64-channel block)
 
 // Writes 4 consecutive channels of one pixel into the bf16 planes of an output.
 __device__ __forceinline__ void store_planes4(const PlaneOut& po, int nplanes, long long pix, int n, const float* y) {
-  __nv_bfloat16* base = po.ptr + pix * po.pitch + n;
-  if (nplanes == 2) {   // fp16 hi + pre-scaled fp16 lo
-    const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
-    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-    const __half2 l01 = __floats2half2_rn((y[0] - f01.x) * ACCFLOW_FP16X2_SCALE, (y[1] - f01.y) * ACCFLOW_FP16X2_SCALE);
-    const __half2 l23 = __floats2half2_rn((y[2] - f23.x) * ACCFLOW_FP16X2_SCALE, (y[3] - f23.y) * ACCFLOW_FP16X2_SCALE);
-    *reinterpret_cast<uint2*>(base) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-    *reinterpret_cast<uint2*>(base + po.plane_stride) =
-        make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
-    return;
-  }
-  const __nv_bfloat162 a01 = __floats2bfloat162_rn(y[0], y[1]), a23 = __floats2bfloat162_rn(y[2], y[3]);
-  *reinterpret_cast<uint2*>(base) = make_uint2(*reinterpret_cast<const uint32_t*>(&a01), *reinterpret_cast<const uint32_t*>(&a23));
-  if (nplanes > 1) {
-    const float r0 = y[0] - __bfloat162float(a01.x), r1 = y[1] - __bfloat162float(a01.y);
-    const float r2 = y[2] - __bfloat162float(a23.x), r3 = y[3] - __bfloat162float(a23.y);
-    const __nv_bfloat162 b01 = __floats2bfloat162_rn(r0, r1), b23 = __floats2bfloat162_rn(r2, r3);
-    *reinterpret_cast<uint2*>(base + po.plane_stride) =
-        make_uint2(*reinterpret_cast<const uint32_t*>(&b01), *reinterpret_cast<const uint32_t*>(&b23));
-    *reinterpret_cast<uint2*>(base + 2 * po.plane_stride) =
-        make_uint2(pack_bf16(r0 - __bfloat162float(b01.x), r1 - __bfloat162float(b01.y)),
-                   pack_bf16(r2 - __bfloat162float(b23.x), r3 - __bfloat162float(b23.y)));
-  }
+  store_planes4_at(po.ptr + pix * po.pitch + n, po.plane_stride, nplanes, y);
 }
 __device__ __forceinline__ void store_planes1(const PlaneOut& po, int nplanes, long long pix, int n, float y) {
   store_planes(po.ptr + pix * po.pitch + n, po.plane_stride, nplanes, y);

@@ -395,16 +395,27 @@ class Kernels:
         self._done(out, pl[0] is not None)
         self._done(mf_tail, tl[0] is not None)
 
-    def instnorm(self, x: View, relu: bool, residual: Optional[View], post_relu: bool, out: View, eps=1e-5):
+    def instnorm(self, x: View, relu: bool, residual: Optional[View], post_relu: bool, out: View, eps=1e-5,
+                 planes_only=False):
+        """InstanceNorm2d (+ReLU, +residual, +ReLU).  Tensor-core modes: the apply pass also writes the operand
+        planes of ``out`` (no split pass before the next conv); ``planes_only`` additionally drops the fp32
+        copy when tensor-core convolutions are the only readers."""
         assert x.c == x.ld and out.c == out.ld
         hw = x.h * x.w
         chunks = L.call("accflow_instnorm_chunks", hw)
         partial = self.buf("in_partial", x.b * chunks * x.c * 2)
         stats = self.buf("in_stats", x.b * x.c * 2)
-        L.call("accflow_instnorm_f32", x.ptr, x.b, hw, x.c, eps, int(relu),
-               None if residual is None else residual.ptr, int(post_relu), out.ptr, partial.data_ptr(),
-               stats.data_ptr(), _stream())
-        self.wrote(out)
+        pl = self.planes_ptr(out, create=True) if self.tc and out.full_rows and out.c % 8 == 0 else None
+        if pl is None:
+            L.call("accflow_instnorm_f32", x.ptr, x.b, hw, x.c, eps, int(relu),
+                   None if residual is None else residual.ptr, int(post_relu), out.ptr, partial.data_ptr(),
+                   stats.data_ptr(), _stream())
+            self.wrote(out)
+            return
+        L.call("accflow_instnorm_planes_f32", x.ptr, x.b, hw, x.c, eps, int(relu),
+               None if residual is None else residual.ptr, int(post_relu), None if planes_only else out.ptr,
+               partial.data_ptr(), stats.data_ptr(), pl[0], pl[1], pl[2], self.nplanes, _stream())
+        self._fresh(out)
 
     def gemm_nt(self, tag: str, a: View, b: View, out: View, alpha=1.0):
         """out[s, m, n] = alpha * sum_k a[s, m, k] * b[s, n, k]  (per sample s; b given row-major [n][k]).
@@ -576,7 +587,7 @@ class EncoderPlan:
             y2 = k.view(f"{tag}.b{bi}.y2", n, oh, ow, c2.cout)
             if inst:
                 k.conv(c1, [x], y1)
-                k.instnorm(y1, True, None, False, y1)
+                k.instnorm(y1, True, None, False, y1, planes_only=True)      # only conv2 reads y1
                 k.conv(c2, [y1], y2)
                 res = x
                 if dn is not None:

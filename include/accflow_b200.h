@@ -170,6 +170,13 @@ ACCFLOW_API int accflow_instnorm_chunks(int hw);
 ACCFLOW_API int accflow_instnorm_f32(const float* x, int batch, int hw, int c, float eps, int relu,
                          const float* residual, int post_relu, float* out, float* partial,
                          float* stats, void* stream);
+/* Same, additionally emitting the 16-bit operand planes of the result (see accflow_tc_io) so that the
+ * tensor-core convolution that follows needs no split pass; `out` may be NULL when only the planes are
+ * consumed (conv1 -> norm1 -> relu -> conv2 inside a ResidualBlock, raft/extractor.py:46-55). */
+ACCFLOW_API int accflow_instnorm_planes_f32(const float* x, int batch, int hw, int c, float eps, int relu,
+                                            const float* residual, int post_relu, float* out, float* partial,
+                                            float* stats, void* out_planes, int pl_pitch, long long pl_plane_stride,
+                                            int nplanes, void* stream);
 
 /* [B,HW,C] (NHWC slice) -> [B,C,HW]: fmap2 / k operand of the per-sample GEMMs
  * (raft/corr.py:49-53 `fmap1.transpose(1,2) @ fmap2`; gma/modules.py:66-73). */
