@@ -43,9 +43,9 @@ def test_two_rank_metric_gather():
     procs = [ctx.Process(target=_worker, args=(r, world, port, n_clips, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=120) for _ in range(world)]
+    results = [q.get(timeout=600) for _ in range(world)]   # spawn re-imports torch: slow on a loaded box
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=300)
         assert p.exitcode == 0
     expect = torch.tensor([[i + 0.25, 10.0 * i, -float(i)] for i in range(n_clips)])
     for rank, ids, table in results:
