@@ -254,9 +254,11 @@ class Kernels:
              act_split=0, act2=L.ACT_NONE, out2: Optional[View] = None, residual: Optional[View] = None,
              post_relu=False, epilogue=L.EPI_STORE, h: Optional[View] = None, z: Optional[View] = None,
              weight_ptr: Optional[int] = None, weight_batch_stride=0, cout=None, cout_pad=None,
-             use_affine=True, tc_b: Optional["L.TcWeights"] = None, tc_src_planes=None, planes_only=False):
+             use_affine=True, tc_b: Optional["L.TcWeights"] = None, tc_src_planes=None, planes_only=False,
+             emit_planes=True):
         """``planes_only``: the output (``out``; ``out2`` for the GRU z|r epilogue) is read by tensor-core
-        convolutions only, so in the tensor-core modes its fp32 copy is not written (half the store bytes)."""
+        convolutions only, so in the tensor-core modes its fp32 copy is not written (half the store bytes).
+        ``emit_planes=False``: the next reader is not a tensor-core conv (InstanceNorm), so no planes are written."""
         d = L.ConvDesc()
         cin = 0
         for k, s in enumerate(srcs):
@@ -303,7 +305,7 @@ class Kernels:
             for name, tv in targets:
                 if tv is None:
                     continue
-                got = self.planes_ptr(tv, create=False)
+                got = self.planes_ptr(tv, create=False) if emit_planes else None
                 if got is not None and tv.c0 % 4 == 0:
                     setattr(io, name + "_planes", got[0])
                     setattr(io, name + "_pitch", got[1])
@@ -396,7 +398,7 @@ class Kernels:
         self._done(mf_tail, tl[0] is not None)
 
     def instnorm(self, x: View, relu: bool, residual: Optional[View], post_relu: bool, out: View, eps=1e-5,
-                 planes_only=False):
+                 planes_only=False, emit_planes=True):
         """InstanceNorm2d (+ReLU, +residual, +ReLU).  Tensor-core modes: the apply pass also writes the operand
         planes of ``out`` (no split pass before the next conv); ``planes_only`` additionally drops the fp32
         copy when tensor-core convolutions are the only readers."""
@@ -405,7 +407,7 @@ class Kernels:
         chunks = L.call("accflow_instnorm_chunks", hw)
         partial = self.buf("in_partial", x.b * chunks * x.c * 2)
         stats = self.buf("in_stats", x.b * x.c * 2)
-        pl = self.planes_ptr(out, create=True) if self.tc and out.full_rows and out.c % 8 == 0 else None
+        pl = self.planes_ptr(out, create=True) if self.tc and emit_planes and out.full_rows and out.c % 8 == 0 else None
         if pl is None:
             L.call("accflow_instnorm_f32", x.ptr, x.b, hw, x.c, eps, int(relu),
                    None if residual is None else residual.ptr, int(post_relu), out.ptr, partial.data_ptr(),
@@ -570,7 +572,7 @@ class EncoderPlan:
                        patches.data_ptr() + 2 * b0 * h2 * w2 * pitch, pitch, stride_pl, k.nplanes, _stream())
                 b0 += nb
             k.conv(self.stem.as_1x1(), [PlanesOnly(n, h2, w2, 147, pitch)], x, act=relu,
-                   tc_src_planes=[(patches.data_ptr(), pitch, stride_pl)])
+                   tc_src_planes=[(patches.data_ptr(), pitch, stride_pl)], emit_planes=not inst)
         else:
             for im in images:
                 assert im.dtype == F32 and im.is_contiguous() and im.shape[1] == 3
@@ -586,17 +588,17 @@ class EncoderPlan:
             y1 = k.view(f"{tag}.b{bi}.y1", n, oh, ow, c1.cout)
             y2 = k.view(f"{tag}.b{bi}.y2", n, oh, ow, c2.cout)
             if inst:
-                k.conv(c1, [x], y1)
+                k.conv(c1, [x], y1, emit_planes=False)                       # InstanceNorm reads fp32 and writes the planes
                 k.instnorm(y1, True, None, False, y1, planes_only=True)      # only conv2 reads y1
-                k.conv(c2, [y1], y2)
+                k.conv(c2, [y1], y2, emit_planes=False)
                 res = x
                 if dn is not None:
                     res = k.view(f"{tag}.b{bi}.dn", n, oh, ow, dn.cout)
-                    k.conv(dn, [x], res)
-                    k.instnorm(res, False, None, False, res)
+                    k.conv(dn, [x], res, emit_planes=False)
+                    k.instnorm(res, False, None, False, res, emit_planes=False)     # read as the fp32 residual only
                 k.instnorm(y2, True, res, True, y2)
             else:
-                k.conv(c1, [x], y1, act=L.ACT_RELU)
+                k.conv(c1, [x], y1, act=L.ACT_RELU, planes_only=True)        # only conv2 reads y1
                 res = x
                 if dn is not None:
                     res = k.view(f"{tag}.b{bi}.dn", n, oh, ow, dn.cout)
