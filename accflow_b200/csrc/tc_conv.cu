@@ -56,6 +56,7 @@ struct Params {
   //   mode 2: slow axis = x (tensor map dims permuted to C,H,W): box = 8 y-pixels x (16 + kw - 1)
   //           x-pixels per (ky, K block); tap kx is 1024*kx bytes further.  Tile = 16 wide x 8 tall.
   int mode, n_outer, n_inner, tile_w, tile_h, a_plane_bytes, stages_b;
+  int pool_w;  // ACCFLOW_EPI_STORE_POOL: width of the map the N axis is a row-major view of
   int debug;   // perf experiments only (ACCFLOW_TC_DEBUG): bit 0 = no TMA loads, bit 1 = no MMAs (results are garbage)
   float alpha;
   const float* scale;
@@ -431,6 +432,72 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       tc_fence_after();
       asm volatile("bar.sync 3, 256;" ::: "memory");             // staged affine visible to both warp sets
       const uint32_t lane_addr = tmem_base + slot * acc_cols + ((uint32_t)(32 * (warp & 3)) << 16);
+      if (p.epilogue == ACCFLOW_EPI_STORE_POOL) {
+        // Correlation volume + first pyramid level (raft/corr.py:47-55 and :20-22).  The N axis of the tile is a
+        // (BN / w) x w piece of the target map; this warp set owns the x range [half*w/2, (half+1)*w/2) of every
+        // row, so a thread holds the two vertically adjacent 16-column runs of a row pair in registers: the 2x2
+        // means go straight to level 1 (8 floats = one 32-byte sector per thread), the scaled level-0 values
+        // through the staging panel as coalesced float4 rows.
+        const int w = p.pool_w, hw2 = w >> 1;
+        const int my_slow = trow >> p.tw_shift, my_fast = trow & (p.tw - 1);
+        const int my_oy = oy0 + my_slow, my_ox = ox0 + my_fast;
+        const bool my_in = my_oy < p.out_h && my_ox < p.out_w;
+        const long long my_pix = ((long long)sample * p.out_h + my_oy) * p.out_w + my_ox;
+        const int npairs = BN / (2 * w), nsteps = hw2 >> 4;
+        float* stg_w = stg + 0;                                   // this warp reads back only the rows it staged
+        for (int pr = 0; pr < npairs; ++pr) {
+          for (int xs = 0; xs < nsteps; ++xs) {
+            const int cc[2] = {2 * pr * w + half * hw2 + xs * 16, 2 * pr * w + half * hw2 + xs * 16 + w};
+            float y[2][16];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              float acc[16];
+              tmem_ld16(lane_addr + cc[rr], acc);
+              if (p.nprod > 1) {
+                float corr[16];
+                tmem_ld16(lane_addr + BN + cc[rr], corr);
+                const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) y[rr][j] = fmaf(acc[j], s_scale[lt & 1][cc[rr] + j], s_shift[lt & 1][cc[rr] + j]);
+            }
+            if (pr == npairs - 1 && xs == nsteps - 1) {            // last TMEM read of this tile
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
+            }
+            if (my_in) {
+              float pl[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pl[j] = (((y[0][2 * j] + y[0][2 * j + 1]) + y[1][2 * j]) + y[1][2 * j + 1]) * 0.25f;
+              float* d1 = p.out2 + my_pix * p.out2_ld + (((n0 / w) >> 1) + pr) * hw2 + ((half * hw2 + xs * 16) >> 1);
+              *reinterpret_cast<float4*>(d1) = make_float4(pl[0], pl[1], pl[2], pl[3]);
+              *reinterpret_cast<float4*>(d1 + 4) = make_float4(pl[4], pl[5], pl[6], pl[7]);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              float4* d4 = reinterpret_cast<float4*>(stg_w + trow * PITCH);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) d4[j] = make_float4(y[rr][4 * j], y[rr][4 * j + 1], y[rr][4 * j + 2], y[rr][4 * j + 3]);
+              __syncwarp();
+              const int nb = n0 + cc[rr] + pc4 * 4;
+#pragma unroll
+              for (int itr = 0; itr < 4; ++itr) {
+                const int row = 32 * (warp & 3) + itr * 8 + (lane >> 2);
+                const int oy = oy0 + (row >> p.tw_shift), ox = ox0 + (row & (p.tw - 1));
+                if (oy >= p.out_h || ox >= p.out_w || nb >= p.cout) continue;
+                const long long pix = ((long long)sample * p.out_h + oy) * p.out_w + ox;
+                *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) =
+                    *reinterpret_cast<const float4*>(stg_w + row * PITCH + pc4 * 4);
+              }
+              __syncwarp();
+            }
+          }
+        }
+        continue;
+      }
       for (int c = cbeg; c < cend; c += 16) {
         {
           float acc[16];
@@ -1081,6 +1148,13 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     ACCFLOW_REQUIRE(d.z && d.h && d.cout % 4 == 0, "conv2d_tc: GRU_Q needs z, h and cout % 4 == 0");
     ACCFLOW_REQUIRE(aligned16(d.z) && aligned16(d.h) && d.z_ld % 4 == 0 && d.h_ld % 4 == 0,
                     "conv2d_tc: GRU buffers must be 16B aligned");
+  } else if (d.epilogue == ACCFLOW_EPI_STORE_POOL) {
+    ACCFLOW_REQUIRE(per_sample && !pair && p.mode == 0 && d.out && d.out2 && d.pool_w >= 32 && d.pool_w % 32 == 0 &&
+                        bn % (2 * d.pool_w) == 0 && d.cout % bn == 0 && d.act == ACCFLOW_ACT_NONE && !d.residual &&
+                        d.act_split == 0 && aligned16(d.out) && aligned16(d.out2) && d.out_ld % 4 == 0 && d.out2_ld % 8 == 0,
+                    "conv2d_tc: STORE_POOL needs a per-sample GEMM whose N tile (%d) covers whole row pairs of the "
+                    "pool_w=%d wide map, pool_w %% 32 == 0, 16B-aligned outputs", bn, d.pool_w);
+    p.pool_w = d.pool_w;
   } else {
     return fail(-1, "conv2d_tc: unknown epilogue %d", d.epilogue);
   }

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -255,7 +256,7 @@ class Kernels:
              post_relu=False, epilogue=L.EPI_STORE, h: Optional[View] = None, z: Optional[View] = None,
              weight_ptr: Optional[int] = None, weight_batch_stride=0, cout=None, cout_pad=None,
              use_affine=True, tc_b: Optional["L.TcWeights"] = None, tc_src_planes=None, planes_only=False,
-             emit_planes=True):
+             emit_planes=True, pool_w=0):
         """``planes_only``: the output (``out``; ``out2`` for the GRU z|r epilogue) is read by tensor-core
         convolutions only, so in the tensor-core modes its fp32 copy is not written (half the store bytes).
         ``emit_planes=False``: the next reader is not a tensor-core conv (InstanceNorm), so no planes are written."""
@@ -281,7 +282,7 @@ class Kernels:
         d.act, d.act_split, d.act2 = act, act_split, act2
         if residual is not None:
             d.residual, d.res_ld = residual.ptr, residual.ld
-        d.post_relu, d.epilogue = int(post_relu), epilogue
+        d.post_relu, d.epilogue, d.pool_w = int(post_relu), epilogue, pool_w
         if out is not None:
             d.out, d.out_ld = out.ptr, out.ld
         if out2 is not None:
@@ -296,7 +297,9 @@ class Kernels:
                 io.src_planes[k], io.src_pitch[k], io.src_plane_stride[k] = (
                     tc_src_planes[k] if tc_src_planes is not None else self.ensure_planes(sv))
             written = []
-            if epilogue == L.EPI_STORE:
+            if epilogue == L.EPI_STORE_POOL:
+                targets = ()
+            elif epilogue == L.EPI_STORE:
                 targets = (("out", out), ("out2", out2 if act_split else None))
             elif epilogue == L.EPI_GRU_ZR:
                 targets = (("out2", out2),)
@@ -419,7 +422,8 @@ class Kernels:
                partial.data_ptr(), stats.data_ptr(), pl[0], pl[1], pl[2], self.nplanes, _stream())
         self._fresh(out)
 
-    def gemm_nt(self, tag: str, a: View, b: View, out: View, alpha=1.0):
+    def gemm_nt(self, tag: str, a: View, b: View, out: View, alpha=1.0, pool_out: Optional[torch.Tensor] = None,
+                pool_w: int = 0):
         """out[s, m, n] = alpha * sum_k a[s, m, k] * b[s, n, k]  (per sample s; b given row-major [n][k]).
         corr volume (raft/corr.py:47-55) and q k^T (gma/modules.py:66-73)."""
         B, K, N = a.b, a.c, b.h * b.w
@@ -437,6 +441,10 @@ class Kernels:
         L.call("accflow_split_bf16_planes", b.ptr, B * N, K, b.ld, K, pitch, B * N * pitch, npl, planes.data_ptr(),
                _stream())
         tw = L.TcWeights(planes.data_ptr(), npl, N, K, pitch, B)
+        if pool_out is not None:      # fused first pyramid level (ACCFLOW_EPI_STORE_POOL)
+            self.conv(_Gemm(K, N, N), [a], out, alpha=alpha, weight_batch_stride=1, use_affine=False, tc_b=tw,
+                      epilogue=L.EPI_STORE_POOL, out2=View(pool_out.view(B, a.h, a.w, -1)), pool_w=pool_w)
+            return
         self.conv(_Gemm(K, N, N), [a], out, alpha=alpha, weight_batch_stride=1, use_affine=False, tc_b=tw)
 
     def gemm_nn(self, tag: str, a: View, b: View, out: View, alpha=1.0, residual: Optional[View] = None):
@@ -702,6 +710,16 @@ class FlowEstimatorEngine:
         for l in range(1, 4):
             hh, ww = hh // 2, ww // 2
             lv.append(k.buf(f"{tag}.pyr{l}", B * P, hh * ww))
+        if (k.tc and k.precision != "bf16x3" and w % 32 == 0 and h % 16 == 0 and (2 * w) <= 128
+                and os.environ.get("ACCFLOW_FUSED_POOL", "1") != "0"):
+            # level 1 comes out of the GEMM epilogue (2x2 means of the scaled volume); levels 2, 3 are pooled
+            # from level 1 (a quarter of the bytes of level 0)
+            k.gemm_nt(tag + ".corr", f1, f2, View(lv[0].view(B, h, w, P)), alpha=1.0 / math.sqrt(D),
+                      pool_out=lv[1], pool_w=w)
+            spare = k.buf(tag + ".pyr4", B * P, (h // 16) * (w // 16))
+            L.call("accflow_corr_pool_f32", lv[1].data_ptr(), B * P, h // 2, w // 2, lv[2].data_ptr(), lv[3].data_ptr(),
+                   spare.data_ptr(), _stream())
+            return lv
         k.gemm_nt(tag + ".corr", f1, f2, View(lv[0].view(B, h, w, P)), alpha=1.0 / math.sqrt(D))
         L.call("accflow_corr_pool_f32", lv[0].data_ptr(), B * P, h, w, lv[1].data_ptr(), lv[2].data_ptr(),
                lv[3].data_ptr(), _stream())

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ACCFLOW_ABI_VERSION 1
+#define ACCFLOW_ABI_VERSION 2
 #if defined(__GNUC__)
 #define ACCFLOW_API __attribute__((visibility("default")))
 #else
@@ -41,7 +41,11 @@ enum { ACCFLOW_ACT_NONE = 0, ACCFLOW_ACT_RELU = 1, ACCFLOW_ACT_SIGMOID = 2, ACCF
 enum {
   ACCFLOW_EPI_STORE = 0,  /* out = post(res + act(acc*alpha*scale[c] + shift[c]))                 */
   ACCFLOW_EPI_GRU_ZR = 1, /* cout = 2*hd: z=sigmoid -> z buffer; r=sigmoid -> out2 = r*h          */
-  ACCFLOW_EPI_GRU_Q = 2   /* q = tanh(.) ; h = (1-z)*h + z*q  (in place)                          */
+  ACCFLOW_EPI_GRU_Q = 2,  /* q = tanh(.) ; h = (1-z)*h + z*q  (in place)                          */
+  /* tensor-core per-sample GEMM only: out = acc*alpha (the correlation volume, raft/corr.py:47-55) and
+   * out2 = 2x2 mean over the N axis viewed as a row-major map of width pool_w (first avg_pool2d of the
+   * pyramid, raft/corr.py:20-22); out2 row stride = out2_ld. */
+  ACCFLOW_EPI_STORE_POOL = 3
 };
 
 #define ACCFLOW_MAX_SRC 4
@@ -77,6 +81,7 @@ typedef struct accflow_conv_desc {
   float* out2; int out2_ld; /* split destination / GRU r*h destination */
   float* h;    int h_ld;    /* GRU hidden state (read for ZR, read+written for Q) */
   float* z;    int z_ld;    /* GRU update gate buffer (written by ZR, read by Q) */
+  int pool_w;               /* ACCFLOW_EPI_STORE_POOL: width of the target map (multiple of 32) */
 } accflow_conv_desc;
 
 ACCFLOW_API int accflow_abi_version(void);

@@ -224,6 +224,30 @@ def test_corr_pyramid_and_lookup(KP, golden):
     assert maxdiff(flow.view(B, h, w, 2).permute(0, 3, 1, 2), coords - ops.coords_grid(B, h, w)) < 1e-6
 
 
+@pytest.mark.parametrize("hw", [(32, 32), (16, 64), (64, 64)])
+def test_corr_volume_with_fused_first_level(hw):
+    """CorrBlock.__init__ (raft/corr.py:8-22, 47-55) through the engine path whose GEMM epilogue emits level 1:
+    volume = f1 . f2^T / sqrt(D); levels 1..3 = successive 2x2 means.  Checked against torch in every
+    tensor-core mode at map sizes that take the fused path (w % 32 == 0)."""
+    from accflow_b200.engine import FlowEstimatorEngine, Kernels, View
+    h, w = hw
+    B, D = 2, 256
+    g = torch.Generator().manual_seed(31)
+    f1 = torch.randn(B, h, w, D, generator=g)
+    f2 = torch.randn(B, h, w, D, generator=g)
+    vol = torch.einsum("bpc,bqc->bpq", f1.reshape(B, h * w, D), f2.reshape(B, h * w, D)) / math.sqrt(D)
+    ref = [vol.reshape(B * h * w, 1, h, w)]
+    for _ in range(3):
+        ref.append(F.avg_pool2d(ref[-1], 2, stride=2))
+    for prec, tol in (("fp16x2", 3e-5), ("bf16", 0.1)):
+        eng = FlowEstimatorEngine.__new__(FlowEstimatorEngine)
+        eng.k = Kernels(torch.device("cuda:0"), prec)
+        lv = eng.corr_pyramid(View(f1.cuda()), View(f2.cuda()), "t.corr")
+        torch.cuda.synchronize()
+        for l in range(4):
+            assert maxdiff(lv[l].reshape(ref[l].shape), ref[l]) < tol * 4, (prec, l)
+
+
 def test_convex_upsample(golden):
     from accflow_b200 import ops as P
     g, _ = golden
