@@ -56,6 +56,8 @@ struct Params {
   //   mode 2: slow axis = x (tensor map dims permuted to C,H,W): box = 8 y-pixels x (16 + kw - 1)
   //           x-pixels per (ky, K block); tap kx is 1024*kx bytes further.  Tile = 16 wide x 8 tall.
   int mode, n_outer, n_inner, tile_w, tile_h, a_plane_bytes, stages_b;
+  int msub;    // shift modes, narrow N tiles: 128-pixel sub-tiles per CTA tile (stacked along the slow axis, one
+               // activation box); every weight tile is used msub times, i.e. 1/msub of the weight bytes per pixel
   int pool_w;  // ACCFLOW_EPI_STORE_POOL: width of the map the N axis is a row-major view of
   int debug;   // perf experiments only (ACCFLOW_TC_DEBUG): bit 0 = no TMA loads, bit 1 = no MMAs (results are garbage)
   float alpha;
@@ -205,7 +207,7 @@ __device__ __forceinline__ void store_planes1(const PlaneOut& po, int nplanes, l
 // products share one instruction: the weight planes w0 | w1 are contiguous in shared memory and the
 // MAIN | CORR accumulators are contiguous in TMEM, so  a0 x [w0; w1]  is a single N = 2*BN MMA.
 struct MmaCtx {
-  int total_tiles, stride_tiles, first_tile, nchunks, n_inner, SA, SB, BN, a_stage, b_stage, debug;
+  int total_tiles, stride_tiles, first_tile, nchunks, n_inner, SA, SB, BN, a_stage, b_stage, debug, msub, sub_cols;
   uint32_t a_plane16, w_plane16, smem_a, smem_b, tmem_base, acc_cols;
   uint64_t *afull, *afree, *bfull, *bfree, *acc_full, *acc_empty;
 };
@@ -241,27 +243,32 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
         tc_fence_after();
         const uint32_t w_lo = desc_lo(w_slot);
         if (!(c.debug & 2)) {
+          for (int sub = 0; sub < c.msub; ++sub) {                   // sub-tile = the box read 16 slow-axis rows further
+            const uint32_t as_lo = a_lo + sub * (16 * 1024 >> 4);
+            const uint32_t sm_main = acc_main + sub * c.sub_cols, sm_corr = acc_corr + sub * c.sub_cols;
 #pragma unroll
-          for (int k4 = 0; k4 < KC / 16; ++k4) {                     // 16 elements = 32 B = 2 descriptor units
-            const uint64_t a0 = desc_from_lo(a_lo + 2 * k4), w0 = desc_from_lo(w_lo + 2 * k4);
-            if (NPROD == 1) {
-              umma_bf16(acc_main, a0, w0, idesc1, first);
-            } else {
-              const uint64_t a1 = desc_from_lo(a_lo + c.a_plane16 + 2 * k4);
-              umma_bf16(acc_main, a0, w0, idesc2, first);            // MAIN += a0 w0 ; CORR += a0 w1
-              umma_bf16(acc_corr, a1, w0, idesc1, 1);                // CORR += a1 w0
-              if (NPROD == 6) {
-                const uint64_t w1 = desc_from_lo(w_lo + c.w_plane16 + 2 * k4);
-                const uint64_t a2 = desc_from_lo(a_lo + 2 * c.a_plane16 + 2 * k4);
-                const uint64_t w2 = desc_from_lo(w_lo + 2 * c.w_plane16 + 2 * k4);
-                umma_bf16(acc_corr, a1, w1, idesc1, 1);
-                umma_bf16(acc_corr, a0, w2, idesc1, 1);
-                umma_bf16(acc_corr, a2, w0, idesc1, 1);
+            for (int k4 = 0; k4 < KC / 16; ++k4) {                   // 16 elements = 32 B = 2 descriptor units
+              const uint64_t a0 = desc_from_lo(as_lo + 2 * k4), w0 = desc_from_lo(w_lo + 2 * k4);
+              const uint32_t acc = first | (uint32_t)k4;
+              if (NPROD == 1) {
+                umma_bf16(sm_main, a0, w0, idesc1, acc);
+              } else {
+                const uint64_t a1 = desc_from_lo(as_lo + c.a_plane16 + 2 * k4);
+                umma_bf16(sm_main, a0, w0, idesc2, acc);             // MAIN += a0 w0 ; CORR += a0 w1
+                umma_bf16(sm_corr, a1, w0, idesc1, 1);               // CORR += a1 w0
+                if (NPROD == 6) {
+                  const uint64_t w1 = desc_from_lo(w_lo + c.w_plane16 + 2 * k4);
+                  const uint64_t a2 = desc_from_lo(as_lo + 2 * c.a_plane16 + 2 * k4);
+                  const uint64_t w2 = desc_from_lo(w_lo + 2 * c.w_plane16 + 2 * k4);
+                  umma_bf16(sm_corr, a1, w1, idesc1, 1);
+                  umma_bf16(sm_corr, a0, w2, idesc1, 1);
+                  umma_bf16(sm_corr, a2, w0, idesc1, 1);
+                }
               }
             }
-            first = 1;
           }
         }
+        first = 1;
         umma_commit(&c.bfree[sb]);                                   // weight tile reusable once these MMAs retire
         a_lo += 1024 >> 4;                                           // shift modes: next tap = 8 pixel rows further
         w_slot += c.b_stage;
@@ -302,7 +309,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   int nchunks = 0;
   for (int s = 0; s < p.nsrc; ++s) nchunks += (p.src_c[s] + KC - 1) / KC;
   nchunks *= n_outer;
-  const int acc_cols = (p.nprod > 1 ? 2 : 1) * BN;              // TMEM columns of one accumulator slot
+  const int sub_cols = (p.nprod > 1 ? 2 : 1) * BN;              // TMEM columns of one 128-pixel sub-tile (MAIN | CORR)
+  const int acc_cols = p.msub * sub_cols;                       // TMEM columns of one accumulator slot
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
   const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
@@ -393,7 +401,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       c.nchunks = nchunks; c.n_inner = n_inner; c.SA = SA; c.SB = SB; c.BN = BN;
       c.a_stage = a_stage; c.b_stage = b_stage; c.a_plane16 = a_plane_bytes >> 4; c.w_plane16 = w_plane_bytes >> 4;
       c.smem_a = smem_u32(smem); c.smem_b = smem_u32(smem_b);
-      c.tmem_base = tmem_base; c.acc_cols = acc_cols; c.debug = p.debug;
+      c.tmem_base = tmem_base; c.acc_cols = acc_cols; c.debug = p.debug; c.msub = p.msub; c.sub_cols = sub_cols;
       c.afull = bar_afull; c.afree = bar_afree; c.bfull = bar_bfull; c.bfree = bar_bfree;
       c.acc_full = bar_acc_full; c.acc_empty = bar_acc_empty;
       if (p.nprod == 3) mma_issue_loop<3>(c);
@@ -498,16 +506,17 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         }
         continue;
       }
+      for (int sub = 0; sub < p.msub; ++sub)
       for (int c = cbeg; c < cend; c += 16) {
         {
           float acc[16];
           if (p.debug & 8) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-          } else tmem_ld16(lane_addr + c, acc);
+          } else tmem_ld16(lane_addr + sub * sub_cols + c, acc);
           if (p.nprod > 1 && !(p.debug & 8)) {
             float corr[16];
-            tmem_ld16(lane_addr + BN + c, corr);
+            tmem_ld16(lane_addr + sub * sub_cols + BN + c, corr);
             const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;   // fp16x2: lo planes carry 2^11
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
@@ -516,7 +525,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
 #pragma unroll
           for (int j = 0; j < 4; ++j) d4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         }
-        if (c + 16 >= cend) {                 // last TMEM read of this tile: hand the slot back to the MMA warp
+        if (c + 16 >= cend && sub == p.msub - 1) {   // last TMEM read of this tile: hand the slot back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
@@ -531,7 +540,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
 #pragma unroll 2
           for (int itr = 0; itr < 4; ++itr) {
             const int row = 32 * (warp & 3) + itr * 8 + (lane >> 2);
-            const int r_slow = row >> p.tw_shift, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
+            const int r_slow = (row >> p.tw_shift) + 16 * sub, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
             const int oy = oy0 + (p.mode == 2 ? r_fast : r_slow), ox = ox0 + (p.mode == 2 ? r_slow : r_fast);
             if (oy >= p.out_h || ox >= p.out_w) continue;
             const long long pix = ((long long)sample * p.out_h + oy) * p.out_w + ox;
@@ -1098,7 +1107,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
       p.tiles_x = cdiv(p.out_w, p.tile_w); p.tiles_y = cdiv(p.out_h, p.tile_h);
     }
   }
-  p.a_plane_bytes = (tc::BM + 8 * (p.n_inner - 1)) * tc::KC * 2;
+  p.msub = 1;
   if (const char* e = getenv("ACCFLOW_TC_DEBUG")) p.debug = atoi(e);
   // N tile: multiple of 32.  Single CTA: the split modes keep two accumulators x two TMEM slots (BN <= 128);
   // CTA pair: each CTA holds half of the weight tile, BN up to 256 (one TMEM slot in the split modes).
@@ -1109,6 +1118,20 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   if (pair && bn % 64 != 0) bn = cdiv(bn, 64) * 64;      // each CTA's half must be a multiple of 32 rows
   p.bn = bn;
   p.n_tiles = cdiv(d.cout, bn);
+  // Narrow N tiles in the shift modes: two 128-pixel sub-tiles per CTA tile share every weight tile (the
+  // small-channel encoder layers were bound by re-fetching the whole filter from L2 for every 128 pixels).
+  // TMEM: msub * (MAIN | CORR) * bn columns per slot, two slots.
+  {
+    static bool msub_env_read = false, msub_enabled = true;
+    if (!msub_env_read) { if (const char* e = getenv("ACCFLOW_TC_MSUB")) msub_enabled = atoi(e) != 0; msub_env_read = true; }
+    const int sub_cols = (nprod > 1 ? 2 : 1) * bn;
+    const int slow_extent = p.mode == 1 ? p.out_h : p.out_w;
+    if (msub_enabled && p.mode != 0 && 2 * 2 * sub_cols <= 512 && slow_extent > 16 && m_tiles_all >= 4 * 148) {
+      p.msub = 2;
+      if (p.mode == 1) { p.tile_h = 32; p.tiles_y = cdiv(p.out_h, 32); } else { p.tile_w = 32; p.tiles_x = cdiv(p.out_w, 32); }
+    }
+  }
+  p.a_plane_bytes = (tc::BM * p.msub + 8 * (p.n_inner - 1)) * tc::KC * 2;
   const int a_stage = nplanes * p.a_plane_bytes, b_stage = nplanes * (pair ? bn / 2 : bn) * tc::KC * 2;
   const int stage_bytes = a_stage + b_stage;
   const int epi_bytes = 2 * tc::BM * 20 * 4;                 // two 128 x (16+4)-float epilogue panels
@@ -1189,7 +1212,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
                           (cuuint64_t)nplanes};
     cuuint64_t gstr[4] = {pitchb, pitchb * d.in_w, pitchb * d.in_w * d.in_h, (cuuint64_t)io.src_plane_stride[s] * 2};
     cuuint32_t box[5] = {(cuuint32_t)tc::KC, (cuuint32_t)(p.tw * d.stride), (cuuint32_t)(p.th * d.stride), 1, 1};
-    if (p.mode) box[2] = (cuuint32_t)(16 + p.n_inner - 1);           // 8 fast-axis pixels x (16 + halo) slow-axis pixels
+    if (p.mode) box[2] = (cuuint32_t)(16 * p.msub + p.n_inner - 1);  // 8 fast-axis pixels x (16 * msub + halo) slow-axis pixels
     if (p.mode == 2) {                                               // dims (C, H, W, B, plane): x is the slow axis
       gdim[1] = (cuuint64_t)d.in_h; gdim[2] = (cuuint64_t)d.in_w;
       gstr[0] = pitchb * d.in_w; gstr[1] = pitchb;

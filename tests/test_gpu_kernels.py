@@ -70,6 +70,8 @@ CONV_CASES = [
     (1, [128, 128, 128, 128], 24, 40, 256, 5, 1, 1, 2, 0),   # GMA GRU (4 sources), vertical taps
     (1, [128, 128, 128, 128], 24, 40, 128, 1, 5, 1, 0, 2),   # GMA GRU q conv, horizontal taps (x-major tiles)
     (1, [256], 33, 47, 192, 3, 3, 1, 1, 1),              # convc2: two 96-wide N tiles
+    (2, [64], 200, 200, 64, 3, 3, 1, 1, 1),              # enough narrow tiles for two sub-tiles per CTA tile (ragged 8x32)
+    (1, [128], 280, 300, 64, 1, 5, 1, 0, 2),             # same, horizontal taps (32x8 tiles)
 ]
 
 
