@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupP p) {
   const int r = RADIUS > 0 ? RADIUS : p.radius, k1 = 2 * r + 1, k2 = k1 * k1, pd = k1 + 3;   // 1 texel of slack below, 2 above
   const float cx = __ldg(p.coords + pix * 2), cy = __ldg(p.coords + pix * 2 + 1);
   float* pt = patch[wib];
-  float* orow = p.out + pix * p.out_ld;
+  float* orow = p.out ? p.out + pix * p.out_ld : nullptr;
   for (int lvl = 0; lvl < 4; ++lvl) {
     const int H = p.lh[lvl], W = p.lw[lvl];
     const float inv = 1.f / (float)(1 << lvl);
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupP p) {
         v += q[pd] * (ex.y * ey.z);
         v += q[pd + 1] * (ex.z * ey.z);
       }
-      orow[lvl * k2 + t] = v;
+      if (orow) orow[lvl * k2 + t] = v;
       if (p.out_pl) store_planes(p.out_pl + pix * p.pl_pitch + lvl * k2 + t, p.pl_stride, p.nplanes, v);
     }
   }
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) corr_lookup_fast_kernel(const LookupP p) 
   const long long pix = (long long)blockIdx.x * 8 + wib;
   if (pix >= (long long)p.batch * p.h * p.w) return;
   const float cx = __ldg(p.coords + pix * 2), cy = __ldg(p.coords + pix * 2 + 1);
-  float* orow = p.out + pix * p.out_ld;
+  float* orow = p.out ? p.out + pix * p.out_ld : nullptr;        // NULL: planes only (the tensor-core convc1 reads nothing else)
   __nv_bfloat16* prow = p.out_pl ? p.out_pl + pix * p.pl_pitch : nullptr;
   const int xx = lane & 15, yh = lane >> 4;     // patch loader: column, row parity
   int tap_q[NIT];                               // (a, b) of every tap this lane owns: channel t = a*K1 + b
@@ -352,12 +352,12 @@ __global__ void __launch_bounds__(256) corr_lookup_fast_kernel(const LookupP p) 
           v += q[PD] * (ex.y * ey.z);
           v += q[PD + 1] * (ex.z * ey.z);
         }
-        orow[t] = v;
+        if (orow) orow[t] = v;
         if (prow) store_planes(prow + t, p.pl_stride, p.nplanes, v);
       }
     }
     __syncwarp();                               // axis[] is rewritten by the next level
-    orow += K2;
+    if (orow) orow += K2;
     if (prow) prow += K2;
   }
   if (lane == 0) {
@@ -743,7 +743,7 @@ extern "C" int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, con
                                        int out_ld, float* flow_out, float* mf_tail, int mf_ld, void* out_planes,
                                        int pl_pitch, long long pl_stride, void* tail_planes, int tail_pitch,
                                        long long tail_stride, int nplanes, void* stream) {
-  ACCFLOW_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && coords && out, "corr_lookup: null pointer");
+  ACCFLOW_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && coords && (out || out_planes), "corr_lookup: null pointer");
   ACCFLOW_REQUIRE(batch > 0 && h >= 8 && w >= 8 && radius >= 0 && radius <= 8, "corr_lookup: bad shape");
   const int nch = 4 * (2 * radius + 1) * (2 * radius + 1);
   ACCFLOW_REQUIRE(out_ld >= nch, "corr_lookup: out_ld %d < %d channels", out_ld, nch);

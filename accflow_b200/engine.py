@@ -391,11 +391,13 @@ class Kernels:
                 L.call("accflow_axpy_f32", accum.data_ptr(), out.ptr, 1.0, x.b * x.h * x.w * pc.cout, _stream())
         self.wrote(out)
 
-    def corr_lookup(self, lv, radius: int, coords: torch.Tensor, out: View, flow: torch.Tensor, mf_tail: View):
+    def corr_lookup(self, lv, radius: int, coords: torch.Tensor, out: View, flow: torch.Tensor, mf_tail: View,
+                    planes_only=False):
         """CorrBlock.__call__ for all four levels; also emits flow = coords - grid."""
         pl, tl = self._out_planes(out), self._out_planes(mf_tail)
+        out_f32 = None if (planes_only and pl[0] is not None) else out.ptr      # convc1 reads the planes only
         L.call("accflow_corr_lookup_f32", lv[0].data_ptr(), lv[1].data_ptr(), lv[2].data_ptr(), lv[3].data_ptr(),
-               out.b, out.h, out.w, radius, coords.data_ptr(), out.ptr, out.ld, flow.data_ptr(), mf_tail.ptr, mf_tail.ld,
+               out.b, out.h, out.w, radius, coords.data_ptr(), out_f32, out.ld, flow.data_ptr(), mf_tail.ptr, mf_tail.ld,
                pl[0], pl[1], pl[2], tl[0], tl[1], tl[2], self.nplanes, _stream())
         self._done(out, pl[0] is not None)
         self._done(mf_tail, tl[0] is not None)
@@ -766,7 +768,7 @@ class FlowEstimatorEngine:
         L.call("accflow_coords_init_f32", None if flow_init is None else flow_init.data_ptr(), B, h, w,
                coords.data_ptr(), s())
         for _ in range(iters):
-            k.corr_lookup(lv, self.RADIUS, coords, corr, flow, mf.ch(126, 128))
+            k.corr_lookup(lv, self.RADIUS, coords, corr, flow, mf.ch(126, 128), planes_only=True)
             k.conv(self.convc1, [corr], cor1, act=L.ACT_RELU, planes_only=True)
             k.conv(self.convc2, [cor1], cf.ch(0, 192), act=L.ACT_RELU, planes_only=True)
             k.flow_conv7(tag, flow, B, h, w, self.convf1, flo1, planes_only=True)

@@ -197,7 +197,8 @@ ACCFLOW_API int accflow_corr_pool_f32(const float* lvl0, long long n_rows, int h
  * bilinear window lookup, zero padding.  coords: [B,h*w,2] (x,y).  out: NHWC slice with
  * 4*(2r+1)^2 channels, channel = lvl*(2r+1)^2 + a*(2r+1) + b, a -> x offset, b -> y offset.
  * Also emits flow = coords - grid (raft/raft.py:131) to flow_out [B,h*w,2] and, if mf_tail
- * is non-NULL, into channels [0,2) of that slice (the cat([out, flow]) of update.py:97). */
+ * is non-NULL, into channels [0,2) of that slice (the cat([out, flow]) of update.py:97).
+ * `out` may be NULL when out_planes is given (the only reader is the tensor-core convc1). */
 ACCFLOW_API int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                             int batch, int h, int w, int radius, const float* coords, float* out,
                             int out_ld, float* flow_out, float* mf_tail, int mf_ld,
