@@ -562,7 +562,30 @@ class EncoderPlan:
                     down=pc(p + "downsample.0", s, 0, p + "norm3") if s != 1 else None))
         self.head = pc(pfx + "conv2", 1, 0)
 
-    def run(self, k: Kernels, images: Sequence[torch.Tensor], tag: str, head_kwargs=None, head_out: Optional[View] = None) -> Optional[View]:
+    @staticmethod
+    def stem_patches(k: Kernels, images: Sequence[torch.Tensor]):
+        """im2col of the 7x7/s2 stem (K = 147, raft/extractor.py:163) straight into operand planes.  The patches
+        depend on the image only, so one gather serves every encoder that reads the same frames
+        -> (base pointer, pitch, plane stride in elements, bytes per image)."""
+        n = sum(int(im.shape[0]) for im in images)
+        H, W = int(images[0].shape[-2]), int(images[0].shape[-1])
+        h2, w2 = (H + 1) // 2, (W + 1) // 2
+        pitch = 152
+        patches = k.buf16("stem.patches", 3, n, h2, w2, pitch)
+        stride_pl = n * h2 * w2 * pitch
+        b0 = 0
+        for im in images:
+            assert im.dtype == F32 and im.is_contiguous() and im.shape[1] == 3
+            nb = int(im.shape[0])
+            L.call("accflow_stem_patch_planes", im.data_ptr(), nb, H, W,
+                   patches.data_ptr() + 2 * b0 * h2 * w2 * pitch, pitch, stride_pl, k.nplanes, _stream())
+            b0 += nb
+        return patches.data_ptr(), pitch, stride_pl, 2 * h2 * w2 * pitch
+
+    def run(self, k: Kernels, images: Sequence[torch.Tensor], tag: str, head_kwargs=None, head_out: Optional[View] = None,
+            patches=None, patch_image0: int = 0) -> Optional[View]:
+        """``patches``: result of ``stem_patches`` over a superset of ``images`` (same order); ``patch_image0`` is the
+        index of this call's first image inside it."""
         n = sum(int(im.shape[0]) for im in images)
         H, W = int(images[0].shape[-2]), int(images[0].shape[-1])
         inst = self.norm == "instance"
@@ -572,17 +595,11 @@ class EncoderPlan:
         b0 = 0
         if k.tc:
             # im2col (7x7/s2, K=147) straight into operand planes, then a 1x1 conv on the tensor cores
-            pitch = 152
-            patches = k.buf16("stem.patches", 3, n, h2, w2, pitch)      # shared by the encoders (used back to back)
-            stride_pl = n * h2 * w2 * pitch
-            for im in images:
-                assert im.dtype == F32 and im.is_contiguous() and im.shape[1] == 3
-                nb = int(im.shape[0])
-                L.call("accflow_stem_patch_planes", im.data_ptr(), nb, H, W,
-                       patches.data_ptr() + 2 * b0 * h2 * w2 * pitch, pitch, stride_pl, k.nplanes, _stream())
-                b0 += nb
+            if patches is None:
+                patches, patch_image0 = self.stem_patches(k, images), 0
+            pptr, pitch, stride_pl, img_bytes = patches
             k.conv(self.stem.as_1x1(), [PlanesOnly(n, h2, w2, 147, pitch)], x, act=relu,
-                   tc_src_planes=[(patches.data_ptr(), pitch, stride_pl)], emit_planes=not inst)
+                   tc_src_planes=[(pptr + patch_image0 * img_bytes, pitch, stride_pl)], emit_planes=not inst)
         else:
             for im in images:
                 assert im.dtype == F32 and im.is_contiguous() and im.shape[1] == 3
@@ -670,11 +687,11 @@ class FlowEstimatorEngine:
             self.qk_scale = 128 ** -0.5
 
     # ------------------------------------------------------------------------------------
-    def run_fnet(self, images: Sequence[torch.Tensor], tag: str) -> View:
+    def run_fnet(self, images: Sequence[torch.Tensor], tag: str, **patch_kw) -> View:
         """Feature encoder (InstanceNorm) on a list of (n_i,3,H,W) images -> [sum n_i, h, w, 256]."""
-        return self.fnet.run(self.k, images, tag + ".fnet")
+        return self.fnet.run(self.k, images, tag + ".fnet", **patch_kw)
 
-    def run_cnet(self, images: Sequence[torch.Tensor], tag: str):
+    def run_cnet(self, images: Sequence[torch.Tensor], tag: str, **patch_kw):
         """Context encoder (eval BatchNorm) -> (tanh(net), relu(inp)), each [N, h, w, 128] (raft.py:115-119)."""
         k = self.k
         n = sum(int(im.shape[0]) for im in images)
@@ -682,7 +699,7 @@ class FlowEstimatorEngine:
         hid = k.view(tag + ".h", n, h, w, 128)
         inp = k.view(tag + ".inp", n, h, w, 128)
         self.cnet.run(k, images, tag + ".cnet", head_kwargs=dict(out=hid, out2=inp, act=L.ACT_TANH, act_split=128,
-                                                                 act2=L.ACT_RELU))
+                                                                 act2=L.ACT_RELU), **patch_kw)
         return hid, inp
 
     def prepare(self, f1: View, f2: View, hid: View, inp: View, H: int, W: int, tag: str):
@@ -960,9 +977,11 @@ class AccFlowEngine:
             n, b = len(imgs), int(imgs[0].shape[0])
             H, W = int(imgs[0].shape[-2]), int(imgs[0].shape[-1])
             assert H % 8 == 0 and W % 8 == 0 and H >= 128 and W >= 128, "H, W must be multiples of 8 and >= 128"
-            fm = ofe.run_fnet(list(imgs), "clip")                    # frame f -> rows [f*b, (f+1)*b)
-            hid_all, inp_all = ofe.run_cnet(list(imgs[1:]), "clip")  # frame f (>=1) -> rows [(f-1)*b, f*b)
-            ctx = self.context.run(k, list(imgs), "clip.ctx")
+            # the three encoders share one stem im2col of the frames (tensor-core modes)
+            pk = dict(patches=EncoderPlan.stem_patches(k, imgs)) if k.tc else {}
+            fm = ofe.run_fnet(list(imgs), "clip", **pk)                    # frame f -> rows [f*b, (f+1)*b)
+            hid_all, inp_all = ofe.run_cnet(list(imgs[1:]), "clip", patch_image0=b, **pk)  # frame f (>=1) -> rows [(f-1)*b, f*b)
+            ctx = self.context.run(k, list(imgs), "clip.ctx", **pk)
             h, w = fm.h, fm.w
 
             def gather(src: View, frames, name):
