@@ -14,7 +14,7 @@ def timeit(fn, n=3):
     for _ in range(n): fn()
     torch.cuda.synchronize(); return (time.time()-t)/n
 
-for prec in ("bf16x3", "bf16"):
+for prec in os.environ.get("SANITY_PREC", "fp16x2,bf16").split(","):
     m = AccFlow(build_flow_estimator("acc|gma")); m.load_state_dict(make_state_dict("acc+gma", seed=2)); m = m.cuda().eval(); m.ofe.precision = prec
     b = make_batch([0, 1], size=512)
     imgs = [t.cuda() for t in b["imgs"]]
