@@ -210,7 +210,6 @@ struct MmaCtx {
   int total_tiles, stride_tiles, first_tile, nchunks, n_inner, SA, SB, BN, a_stage, b_stage, debug, msub, sub_cols;
   uint32_t a_plane16, w_plane16, smem_a, smem_b, tmem_base, acc_cols;
   uint64_t *afull, *afree, *bfull, *bfree, *acc_full, *acc_empty;
-  const Params* p;
 };
 __device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) {
   // high word: SBO = 1024 B (>>4) at [32,46), version 1 at [46,48), SWIZZLE_128B (2) at [61,64)
@@ -221,7 +220,7 @@ __device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) {
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 
-template <int NPROD>
+template <int NPROD, int MSUB>
 __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
   const uint32_t idesc1 = make_idesc(BM, c.BN, NPROD == 3);
   const uint32_t idesc2 = make_idesc(BM, 2 * c.BN, NPROD == 3);      // a0 x [w0; w1] -> MAIN | CORR
@@ -236,12 +235,7 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
     tc_fence_after();
     const uint32_t acc_main = c.tmem_base + slot * c.acc_cols, acc_corr = acc_main + c.BN;
     uint32_t first = 0;                                              // 0 -> overwrite the accumulators
-    Chunk ck{0, 0, 0};
     for (int i = 0; i < c.nchunks; ++i) {
-      // K16 steps that carry channels: the tail of a source (324 = 5*64 + 4, 147, 98, 257 ...) is zero-filled by
-      // TMA up to 64 channels, and MMAs over all-zero K16 slices are skipped
-      const int ksteps = min(KC / 16, (c.p->src_c[ck.s] - ck.c0 + 15) >> 4);
-      ck.next(*c.p, c.p->n_outer);
       if (!comb) mbar_wait(&c.afull[sa], pa);
       uint32_t a_lo = desc_lo(a_slot);
       for (int j = 0; j < c.n_inner; ++j) {
@@ -249,12 +243,12 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
         tc_fence_after();
         const uint32_t w_lo = desc_lo(w_slot);
         if (!(c.debug & 2)) {
-          for (int sub = 0; sub < c.msub; ++sub) {                   // sub-tile = the box read 16 slow-axis rows further
+#pragma unroll
+          for (int sub = 0; sub < MSUB; ++sub) {                     // sub-tile = the box read 16 slow-axis rows further
             const uint32_t as_lo = a_lo + sub * (16 * 1024 >> 4);
             const uint32_t sm_main = acc_main + sub * c.sub_cols, sm_corr = acc_corr + sub * c.sub_cols;
 #pragma unroll
             for (int k4 = 0; k4 < KC / 16; ++k4) {                   // 16 elements = 32 B = 2 descriptor units
-              if (k4 >= ksteps) break;
               const uint64_t a0 = desc_from_lo(as_lo + 2 * k4), w0 = desc_from_lo(w_lo + 2 * k4);
               const uint32_t acc = first | (uint32_t)k4;
               if (NPROD == 1) {
@@ -410,10 +404,10 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       c.smem_a = smem_u32(smem); c.smem_b = smem_u32(smem_b);
       c.tmem_base = tmem_base; c.acc_cols = acc_cols; c.debug = p.debug; c.msub = p.msub; c.sub_cols = sub_cols;
       c.afull = bar_afull; c.afree = bar_afree; c.bfull = bar_bfull; c.bfree = bar_bfree;
-      c.acc_full = bar_acc_full; c.acc_empty = bar_acc_empty; c.p = &p;
-      if (p.nprod == 3) mma_issue_loop<3>(c);
-      else if (p.nprod == 1) mma_issue_loop<1>(c);
-      else mma_issue_loop<6>(c);
+      c.acc_full = bar_acc_full; c.acc_empty = bar_acc_empty;
+      if (p.nprod == 3) { if (p.msub == 2) mma_issue_loop<3, 2>(c); else mma_issue_loop<3, 1>(c); }
+      else if (p.nprod == 1) { if (p.msub == 2) mma_issue_loop<1, 2>(c); else mma_issue_loop<1, 1>(c); }
+      else mma_issue_loop<6, 1>(c);
     }
   } else {
     // ================================ epilogue ================================================
