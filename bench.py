@@ -247,13 +247,20 @@ def run_b200(args):
              "bf16": "conv_tc_kernel (tcgen05 implicit-GEMM conv, bf16 products)"}[args.precision]
     issued = achieved * {"bf16x3": 6, "fp16x2": 3}.get(args.precision, 1)
     traffic, traffic_note = None, None
+    tnew = os.path.join(ROOT, "profiles", f"r1b_conv_tc_zr_{args.precision}_ncu_full.jsonl")
     tfile = os.path.join(ROOT, "profiles", f"r1_conv_tc_zr_{args.precision}_ncu_full.json")
-    if os.path.exists(tfile):
+    note = ("dram__bytes_read+write of one GRU z|r conv launch (1x5, 384->256, 8 pairs x 64x64; `ncu --set full`) from "
+            "profiles/{}; algorithmic bytes of that launch ~104 MB (operand planes 50 MB + weights 4 MB + h 17 MB "
+            "read, z 17 MB + r*h planes 17 MB written), part of it served by the 126 MB L2")
+    if os.path.exists(tnew):
+        t = json.loads(open(tnew).readline())
+        traffic = (t["dram_read_MB"] + t["dram_write_MB"]) * 1e6
+        traffic_note = note.format(os.path.basename(tnew))
+    elif os.path.exists(tfile):
         t = json.load(open(tfile))
         scale_b = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         traffic = sum(float(t[k]["value"]) * scale_b[t[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        traffic_note = ("dram__bytes_read+write of one GRU z|r conv launch (1x5, 384->256, 8 pairs x 64x64) from "
-                        "profiles/" + os.path.basename(tfile) + "; algorithmic bytes of that launch ~154 MB")
+        traffic_note = note.format(os.path.basename(tfile))
     roofline = {"bound": "tensor", "kernel": kname, "issued_mma_tflops": issued, "issued_frac": issued / pk["bf16_tflops_sustained"],
                 "traffic_note": traffic_note,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
