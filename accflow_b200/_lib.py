@@ -54,6 +54,7 @@ SIGNATURES = {
     "accflow_launch_count_add": [ll],
     "accflow_conv2d_f32": [C.POINTER(ConvDesc), fp],
     "accflow_conv2d_tc": [C.POINTER(ConvDesc), C.POINTER(TcIO), C.POINTER(TcWeights), i, fp],
+    "accflow_tc_debug_trace": [fp, i],
     "accflow_split_bf16_planes": [fp, ll, i, i, i, i, ll, i, fp, fp],
     "accflow_conv_smallc_f32": [fp, i, i, i, i, i, fp, fp, fp, i, i, i, i, fp, i, fp, i, ll, i, fp],
     "accflow_instnorm_chunks": [i],

@@ -176,6 +176,10 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n, bool fp16) {
 }
 
 
+// Perf-experiment trace (ACCFLOW_TC_DEBUG bit 4 = 16): clock64 stamps of CTA 0's MMA-issuing thread, three per weight
+// tile (barriers passed, last MMA issued, commit issued); read back with accflow_tc_debug_trace.
+__device__ long long g_tc_trace[3 * 1024];
+
 struct Chunk {  // iterator over (tap, source, 64-channel block)
   int tap, s, c0;
   __device__ __forceinline__ bool next(const Params& p, int taps) {
@@ -225,7 +229,7 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
   const uint32_t idesc1 = make_idesc(BM, c.BN, NPROD == 3);
   const uint32_t idesc2 = make_idesc(BM, 2 * c.BN, NPROD == 3);      // a0 x [w0; w1] -> MAIN | CORR
   const bool comb = c.n_inner == 1;        // operands share the weight ring's barriers (SA == SB, slots advance together)
-  int sa = 0, sb = 0;
+  int sa = 0, sb = 0, ntr = 0;
   uint32_t pa = 0, pb = 0;                                           // ring parities
   uint32_t a_slot = c.smem_a, w_slot = c.smem_b;
   int lt = 0;
@@ -241,6 +245,8 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
       for (int j = 0; j < c.n_inner; ++j) {
         mbar_wait(&c.bfull[sb], pb);
         tc_fence_after();
+        const bool tr = (c.debug & 16) && blockIdx.x == 0 && ntr < 1024;
+        if (tr) g_tc_trace[3 * ntr] = clock64();
         const uint32_t w_lo = desc_lo(w_slot);
         if (!(c.debug & 2)) {
 #pragma unroll
@@ -270,7 +276,9 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
           }
         }
         first = 1;
+        if (tr) g_tc_trace[3 * ntr + 1] = clock64();
         umma_commit(&c.bfree[sb]);                                   // weight tile reusable once these MMAs retire
+        if (tr) { g_tc_trace[3 * ntr + 2] = clock64(); ++ntr; }
         a_lo += 1024 >> 4;                                           // shift modes: next tap = 8 pixel rows further
         w_slot += c.b_stage;
         if (++sb == c.SB) { sb = 0; pb ^= 1; w_slot = c.smem_b; }
@@ -1019,6 +1027,11 @@ static EncodeTiledFn encode_fn() {
 }  // namespace accflow
 
 using namespace accflow;
+
+extern "C" int accflow_tc_debug_trace(long long* host, int n) {
+  if (!host || n <= 0 || n > 3 * 1024) return -1;
+  return (int)cudaMemcpyFromSymbol(host, tc::g_tc_trace, sizeof(long long) * n);
+}
 
 extern "C" int accflow_split_bf16_planes(const float* x, long long rows, int k, int ld, int k_fill, int pitch,
                                          long long plane_stride, int nplanes, void* out_planes, void* stream) {

@@ -132,6 +132,10 @@ typedef struct accflow_tc_io {
 ACCFLOW_API int accflow_conv2d_tc(const accflow_conv_desc* d, const accflow_tc_io* io, const accflow_tc_weights* w,
                                   int nprod, void* stream);
 
+/* Perf experiments: with ACCFLOW_TC_DEBUG bit 4 set, accflow_conv2d_tc records clock64 stamps of CTA 0's MMA-issuing
+ * thread (3 per weight tile: barriers passed, last MMA issued, commit issued; first 1024 tiles); this copies n of them. */
+ACCFLOW_API int accflow_tc_debug_trace(long long* host, int n);
+
 /* fp32 [rows][k] (row stride ld) -> bf16 planes out[pl*plane_stride + row*pitch + c] for c < k_fill
  * (zero for k <= c < k_fill).  Used for activations produced by non-tensor-core kernels and for
  * the per-sample B operands (fmap2 of raft/corr.py:47-55, k / v of gma/modules.py:57-113). */
