@@ -108,6 +108,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
   __trap();
 }
+// Non-blocking probe of a barrier phase.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -230,6 +244,7 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
   const uint32_t idesc2 = make_idesc(BM, 2 * c.BN, NPROD == 3);      // a0 x [w0; w1] -> MAIN | CORR
   const bool comb = c.n_inner == 1;        // operands share the weight ring's barriers (SA == SB, slots advance together)
   int sa = 0, sb = 0, ntr = 0;
+  bool next_ready = false, a_ready = false;
   uint32_t pa = 0, pb = 0;                                           // ring parities
   uint32_t a_slot = c.smem_a, w_slot = c.smem_b;
   int lt = 0;
@@ -240,11 +255,17 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
     const uint32_t acc_main = c.tmem_base + slot * c.acc_cols, acc_corr = acc_main + c.BN;
     uint32_t first = 0;                                              // 0 -> overwrite the accumulators
     for (int i = 0; i < c.nchunks; ++i) {
-      if (!comb) mbar_wait(&c.afull[sa], pa);
+      if (!comb && !a_ready) mbar_wait(&c.afull[sa], pa);
+      a_ready = false;
+      const int san = sa + 1 == c.SA ? 0 : sa + 1;                  // ring successor of the activation box
+      const uint32_t pan = sa + 1 == c.SA ? pa ^ 1u : pa;
       uint32_t a_lo = desc_lo(a_slot);
       for (int j = 0; j < c.n_inner; ++j) {
-        mbar_wait(&c.bfull[sb], pb);
+        if (!next_ready) mbar_wait(&c.bfull[sb], pb);
         tc_fence_after();
+        // probe target: the next weight tile's barrier (ring successor), tested while this tile's MMAs drain
+        const int sbn = sb + 1 == c.SB ? 0 : sb + 1;
+        const uint32_t pbn = sb + 1 == c.SB ? pb ^ 1u : pb;
         const bool tr = (c.debug & 16) && blockIdx.x == 0 && ntr < 1024;
         if (tr) g_tc_trace[3 * ntr] = clock64();
         const uint32_t w_lo = desc_lo(w_slot);
@@ -255,6 +276,13 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
             const uint32_t sm_main = acc_main + sub * c.sub_cols, sm_corr = acc_corr + sub * c.sub_cols;
 #pragma unroll
             for (int k4 = 0; k4 < KC / 16; ++k4) {                   // 16 elements = 32 B = 2 descriptor units
+              // The issue of a tile's MMAs is paced by the tensor pipe's short queue (scripts/mma_trace.py: ~590 clk until
+              // the commit is accepted, 768 clk of work), so a barrier probe issued in the middle costs nothing, while the
+              // same ~100 clk after the commit would be tensor idle time.
+              if (sub == MSUB - 1 && k4 == KC / 32) {
+                next_ready = mbar_test(&c.bfull[sbn], pbn);
+                if (!comb && j == c.n_inner - 1) a_ready = mbar_test(&c.afull[san], pan);
+              }
               const uint64_t a0 = desc_from_lo(as_lo + 2 * k4), w0 = desc_from_lo(w_lo + 2 * k4);
               const uint32_t acc = first | (uint32_t)k4;
               if (NPROD == 1) {
