@@ -378,7 +378,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
 
   if (warp == 0) {
     // ================================ TMA producer ============================================
-    if (lane == 0) {
+    if (lane == 0 && !(n_inner > 1 && p.stages_b - 1 < n_inner - 1)) {
       const bool comb = n_inner == 1;
       int sa = 0, sb = 0;                                    // ring positions (A boxes, weight tiles)
       uint32_t pa = 1, pb = 1;                               // parity of the "free" phase to wait for (first lap passes)
@@ -428,6 +428,85 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           if (++sa == SA) { sa = 0; pa ^= 1; }
           ck.next(p, n_outer);
         }
+      }
+    }
+    if (lane == 0 && n_inner > 1 && p.stages_b - 1 < n_inner - 1) {   // activation boxes requested one chunk ahead
+      const bool comb = n_inner == 1;
+      int sa = 0, sb = 0;                                    // ring positions (A boxes, weight tiles)
+      uint32_t pa = 1, pb = 1;                               // parity of the "free" phase to wait for (first lap passes)
+      // Cursor over (tile, chunk): tile decode + the chunk iterator.  The activation boxes have their own cursor that
+      // runs one chunk ahead of the weight tiles (shift modes): the box of chunk c+1 is requested after the first
+      // SB-1 weight tiles of chunk c - the moment its ring slot is released anyway - instead of after the last one,
+      // which left it ~2 weight tiles of lead and stalled the MMA thread at every chunk boundary.
+      struct Cur {
+        int tile, i, sample, ox0, oy0, n0;
+        Chunk ck;
+      };
+      auto decode = [&](Cur& c) {
+        const int n_tile = c.tile / m_tiles;
+        int t = c.tile - n_tile * m_tiles;
+        const int tile_x = t % p.tiles_x; t /= p.tiles_x;
+        const int tile_y = t % p.tiles_y;
+        c.sample = t / p.tiles_y;
+        c.ox0 = tile_x * p.tile_w; c.oy0 = tile_y * p.tile_h; c.n0 = n_tile * BN;
+        c.i = 0; c.ck = Chunk{0, 0, 0};                      // ck.tap = outer tap index
+      };
+      auto advance = [&](Cur& c) {
+        c.ck.next(p, n_outer);
+        if (++c.i == nchunks) {
+          c.tile += gridDim.x;
+          if (c.tile < total_tiles) decode(c);
+        }
+      };
+      auto issue_a = [&](const Cur& c, uint64_t* abar, uint8_t* adst) {
+        int c1, c2;                                          // box origin along tensor-map dims 1, 2
+        if (p.mode == 0) {
+          const int ky = c.ck.tap / p.kw, kx = c.ck.tap - ky * p.kw;
+          c1 = c.ox0 * p.stride + kx - p.pad_w; c2 = c.oy0 * p.stride + ky - p.pad_h;
+        } else if (p.mode == 1) {                            // dims (C, W, H): outer tap = kx, halo along y
+          c1 = c.ox0 + c.ck.tap - p.pad_w; c2 = c.oy0 - p.pad_h;
+        } else {                                             // dims (C, H, W): outer tap = ky, halo along x
+          c1 = c.oy0 + c.ck.tap - p.pad_h; c2 = c.ox0 - p.pad_w;
+        }
+        for (int pl = 0; pl < NPL && !(p.debug & 1); ++pl)
+          tma_load_5d(adst + pl * a_plane_bytes, &maps.a[c.ck.s], abar, c.ck.c0, c1, c2, c.sample, pl);
+      };
+      auto issue_a_ring = [&](const Cur& c) {               // shift modes: the box goes to the activation ring
+        mbar_wait(&bar_afree[sa], pa);
+        mbar_expect_tx(&bar_afull[sa], (p.debug & 1) ? 0u : (uint32_t)a_stage);
+        issue_a(c, &bar_afull[sa], smem + (size_t)sa * a_stage);
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+      };
+      Cur cb;
+      cb.tile = blockIdx.x;
+      if (cb.tile < total_tiles) decode(cb);
+      Cur ca = cb;
+      const int ja = SB - 1;                                 // weight tile after which the next box is requested
+      const bool ahead = !comb && ja < n_inner - 1;          // else: the box of a chunk is requested at the chunk's start
+      if (ahead && ca.tile < total_tiles) { issue_a_ring(ca); advance(ca); }
+      while (cb.tile < total_tiles) {
+        const int kcoord = p.src_off[cb.ck.s] + cb.ck.c0;
+        if (!comb && !ahead) issue_a_ring(cb);
+        if (comb) {
+          // n_inner == 1 (one weight tile per activation box): both operands share the weight ring's
+          // barriers and slot index, i.e. one handshake per K step instead of two.
+          mbar_wait(&bar_bfree[sb], pb);
+          mbar_expect_tx(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)(a_stage + b_stage));
+          issue_a(cb, &bar_bfull[sb], smem + (size_t)sb * a_stage);
+        }
+        for (int j = 0; j < n_inner; ++j) {
+          uint8_t* wdst = smem_b + (size_t)sb * b_stage;
+          if (!comb) {
+            mbar_wait(&bar_bfree[sb], pb);
+            mbar_expect_tx(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)b_stage);
+          }
+          const int tap = p.per_sample ? cb.sample : p.mode == 0 ? cb.ck.tap : p.mode == 1 ? j * p.kw + cb.ck.tap : cb.ck.tap * p.kw + j;
+          for (int pl = 0; pl < NPL && !(p.debug & 1); ++pl)
+            tma_load_4d(wdst + pl * w_plane_bytes, &maps.w, &bar_bfull[sb], kcoord, cb.n0, tap, pl);
+          if (++sb == SB) { sb = 0; pb ^= 1; }
+          if (ahead && j == ja && ca.tile < total_tiles) { issue_a_ring(ca); advance(ca); }
+        }
+        advance(cb);
       }
     }
   } else if (warp == 1) {
