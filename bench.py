@@ -247,7 +247,9 @@ def run_b200(args):
              "bf16": "conv_tc_kernel (tcgen05 implicit-GEMM conv, bf16 products)"}[args.precision]
     issued = achieved * {"bf16x3": 6, "fp16x2": 3}.get(args.precision, 1)
     traffic, traffic_note = None, None
-    tnew = os.path.join(ROOT, "profiles", f"r1b_conv_tc_zr_{args.precision}_ncu_full.jsonl")
+    tnew = os.path.join(ROOT, "profiles", f"r1c_conv_tc_zr_{args.precision}_ncu_full.jsonl")
+    if not os.path.exists(tnew):
+        tnew = os.path.join(ROOT, "profiles", f"r1b_conv_tc_zr_{args.precision}_ncu_full.jsonl")
     tfile = os.path.join(ROOT, "profiles", f"r1_conv_tc_zr_{args.precision}_ncu_full.json")
     note = ("dram__bytes_read+write of one GRU z|r conv launch (1x5, 384->256, 8 pairs x 64x64; `ncu --set full`) from "
             "profiles/{}; algorithmic bytes of that launch ~104 MB (operand planes 50 MB + weights 4 MB + h 17 MB "
