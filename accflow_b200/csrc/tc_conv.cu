@@ -176,6 +176,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Two 16-column loads (MAIN and CORR accumulators) in flight together, one wait.
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, float* v0, float* v1) {
+  uint32_t r[16], q[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr0)
+      : "memory");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(taddr1)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(r[i]); v1[i] = __uint_as_float(q[i]); }
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B)
 //   [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
@@ -411,8 +431,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           } else {                                           // dims (C, H, W): outer tap = ky, halo along x
             c1 = oy0 + ck.tap - p.pad_h; c2 = ox0 - p.pad_w;
           }
-          for (int pl = 0; pl < NPL && !(p.debug & 1); ++pl)
-            tma_load_5d(adst + pl * a_plane_bytes, &maps.a[ck.s], abar, ck.c0, c1, c2, sample, pl);
+          // one TMA op brings all operand planes (the plane index is the box's outermost dimension)
+          if (!(p.debug & 1)) tma_load_5d(adst, &maps.a[ck.s], abar, ck.c0, c1, c2, sample, 0);
           const int kcoord = p.src_off[ck.s] + ck.c0;
           for (int j = 0; j < n_inner; ++j) {
             uint8_t* wdst = smem_b + (size_t)sb * b_stage;
@@ -421,8 +441,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
               mbar_expect_tx(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)b_stage);
             }
             const int tap = p.per_sample ? sample : p.mode == 0 ? ck.tap : p.mode == 1 ? j * p.kw + ck.tap : ck.tap * p.kw + j;
-            for (int pl = 0; pl < NPL && !(p.debug & 1); ++pl)
-              tma_load_4d(wdst + pl * w_plane_bytes, &maps.w, &bar_bfull[sb], kcoord, n0, tap, pl);
+            if (!(p.debug & 1)) tma_load_4d(wdst, &maps.w, &bar_bfull[sb], kcoord, n0, tap, 0);
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
           if (++sa == SA) { sa = 0; pa ^= 1; }
@@ -468,8 +487,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         } else {                                             // dims (C, H, W): outer tap = ky, halo along x
           c1 = c.oy0 + c.ck.tap - p.pad_h; c2 = c.ox0 - p.pad_w;
         }
-        for (int pl = 0; pl < NPL && !(p.debug & 1); ++pl)
-          tma_load_5d(adst + pl * a_plane_bytes, &maps.a[c.ck.s], abar, c.ck.c0, c1, c2, c.sample, pl);
+        if (!(p.debug & 1)) tma_load_5d(adst, &maps.a[c.ck.s], abar, c.ck.c0, c1, c2, c.sample, 0);
       };
       auto issue_a_ring = [&](const Cur& c) {               // shift modes: the box goes to the activation ring
         mbar_wait(&bar_afree[sa], pa);
@@ -501,8 +519,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             mbar_expect_tx(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)b_stage);
           }
           const int tap = p.per_sample ? cb.sample : p.mode == 0 ? cb.ck.tap : p.mode == 1 ? j * p.kw + cb.ck.tap : cb.ck.tap * p.kw + j;
-          for (int pl = 0; pl < NPL && !(p.debug & 1); ++pl)
-            tma_load_4d(wdst + pl * w_plane_bytes, &maps.w, &bar_bfull[sb], kcoord, cb.n0, tap, pl);
+          if (!(p.debug & 1)) tma_load_4d(wdst, &maps.w, &bar_bfull[sb], kcoord, cb.n0, tap, 0);
           if (++sb == SB) { sb = 0; pb ^= 1; }
           if (ahead && j == ja && ca.tile < total_tiles) { issue_a_ring(ca); advance(ca); }
         }
@@ -576,10 +593,10 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
               float acc[16];
-              tmem_ld16(lane_addr + cc[rr], acc);
+              if (p.nprod == 1) tmem_ld16(lane_addr + cc[rr], acc);
               if (p.nprod > 1) {
                 float corr[16];
-                tmem_ld16(lane_addr + BN + cc[rr], corr);
+                tmem_ld16x2(lane_addr + cc[rr], lane_addr + BN + cc[rr], acc, corr);
                 const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
@@ -629,10 +646,10 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           if (p.debug & 8) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-          } else tmem_ld16(lane_addr + sub * sub_cols + c, acc);
+          } else if (p.nprod == 1) tmem_ld16(lane_addr + sub * sub_cols + c, acc);
           if (p.nprod > 1 && !(p.debug & 8)) {
             float corr[16];
-            tmem_ld16(lane_addr + sub * sub_cols + BN + c, corr);
+            tmem_ld16x2(lane_addr + sub * sub_cols + c, lane_addr + sub * sub_cols + BN + c, acc, corr);
             const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;   // fp16x2: lo planes carry 2^11
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
@@ -870,10 +887,8 @@ conv_tc2_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPa
           const int kcoord = p.src_off[ck.s] + ck.c0;
           const int tw_ = p.per_sample ? sample : ck.tap;
           const uint32_t bar = full_leader + s * 8;
-          for (int pl = 0; pl < NPL; ++pl) {
-            tma2_load_5d(adst + pl * A_PLANE_BYTES, &maps.a[ck.s], bar, ck.c0, ix, iy, sample, pl);
-            tma2_load_4d(wdst + pl * w_plane_bytes, &maps.w, bar, kcoord, n0, tw_, pl);
-          }
+          tma2_load_5d(adst, &maps.a[ck.s], bar, ck.c0, ix, iy, sample, 0);     // all planes per op (box outermost dim)
+          tma2_load_4d(wdst, &maps.w, bar, kcoord, n0, tw_, 0);
           ck.next(p, taps);
         }
       }
@@ -1319,7 +1334,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     const cuuint64_t gdim[4] = {(cuuint64_t)w.k, (cuuint64_t)w.rows, (cuuint64_t)w.t, (cuuint64_t)w.nplanes};
     const cuuint64_t gstr[3] = {(cuuint64_t)w.k_pitch * 2, (cuuint64_t)w.k_pitch * 2 * w.rows,
                                 (cuuint64_t)w.k_pitch * 2 * w.rows * w.t};
-    const cuuint32_t box[4] = {(cuuint32_t)tc::KC, (cuuint32_t)(pair ? bn / 2 : bn), 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)tc::KC, (cuuint32_t)(pair ? bn / 2 : bn), 1, (cuuint32_t)nplanes};   // all planes in one op
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult cr = enc(&maps.w, nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w.planes), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
@@ -1332,7 +1347,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     cuuint64_t gdim[5] = {(cuuint64_t)d.src_c[s], (cuuint64_t)d.in_w, (cuuint64_t)d.in_h, (cuuint64_t)d.batch,
                           (cuuint64_t)nplanes};
     cuuint64_t gstr[4] = {pitchb, pitchb * d.in_w, pitchb * d.in_w * d.in_h, (cuuint64_t)io.src_plane_stride[s] * 2};
-    cuuint32_t box[5] = {(cuuint32_t)tc::KC, (cuuint32_t)(p.tw * d.stride), (cuuint32_t)(p.th * d.stride), 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)tc::KC, (cuuint32_t)(p.tw * d.stride), (cuuint32_t)(p.th * d.stride), 1, (cuuint32_t)nplanes};
     if (p.mode) box[2] = (cuuint32_t)(16 * p.msub + p.n_inner - 1);  // 8 fast-axis pixels x (16 * msub + halo) slow-axis pixels
     if (p.mode == 2) {                                               // dims (C, H, W, B, plane): x is the slow axis
       gdim[1] = (cuuint64_t)d.in_h; gdim[2] = (cuuint64_t)d.in_w;
