@@ -116,3 +116,32 @@ def test_cvo_record_helpers():
     assert float((out["imgs"][3] - b["imgs"][3]).abs().max()) < 1e-6
     with pytest.raises(ValueError):
         preprocess({"other": torch.zeros(1, 3, 8, 8)})
+
+
+def test_packed_conv_1x1_rewrites_are_the_same_filter():
+    """Host-side weight rewrites used by the tensor-core path (no GPU): a 3x3 conv with few outputs as a 1x1 conv
+    with 9*cout outputs + a 9-tap shifted sum (PackedConv.as_taps1x1 + accflow_tapsum3x3_f32), and a KxK conv as a
+    1x1 conv over im2col'd input (PackedConv.as_1x1, flow / stem patch kernels)."""
+    import torch.nn.functional as F
+    from accflow_b200.engine import PackedConv
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 16, 9, 11, generator=g)
+    w = torch.randn(2, 16, 3, 3, generator=g)
+    b = torch.randn(2, generator=g)
+    ref = F.conv2d(x, w, b, padding=1)
+    pc = PackedConv([w], [b], 1, (1, 1))
+    t = F.conv2d(x, pc.as_taps1x1().w_oihw)                   # (2, 9*cout, H, W), channel = tap*cout + o
+    tp = F.pad(t, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for tap in range(9):
+        ky, kx = divmod(tap, 3)
+        out += tp[:, tap * 2:tap * 2 + 2, ky:ky + 9, kx:kx + 11]
+    out += pc.shift.view(1, 2, 1, 1)
+    assert float((out - ref).abs().max()) < 5e-5              # fp32 summation order only (values ~ +-20)
+    # KxK conv == 1x1 conv over patches ordered (ky, kx, cin)
+    w7 = torch.randn(8, 2, 7, 7, generator=g)
+    f = torch.randn(1, 2, 10, 12, generator=g)
+    ref7 = F.conv2d(f, w7, None, padding=3)
+    cols = F.unfold(f, 7, padding=3).view(1, 2, 49, 10 * 12).permute(0, 2, 1, 3).reshape(1, 98, 10, 12)   # (tap, cin) order
+    pc7 = PackedConv([w7], [None], 1, (3, 3))
+    assert float((F.conv2d(cols, pc7.as_1x1().w_oihw) - ref7).abs().max()) < 5e-5
