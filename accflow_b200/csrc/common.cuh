@@ -72,9 +72,14 @@ __device__ __forceinline__ float grid_roundtrip(float x, int size) {
 //   nplanes = 2 : fp16 hi = fp16(x), lo = fp16((x - hi) * 2^11)  ("fp16x2" mode, 3 products);
 //                 the lo plane is pre-scaled so it never underflows; the kernel multiplies the
 //                 cross-term accumulator by 2^-11.
+//                 Operands are saturated to the fp16 range (+-65504) first, so an out-of-range activation
+//                 degrades to a clipped value instead of hi = inf, lo = -inf -> NaN through the whole recurrence.
 #define ACCFLOW_FP16X2_SCALE 2048.0f
+#define ACCFLOW_FP16_MAX 65504.0f
+__device__ __forceinline__ float sat_fp16(float v) { return fminf(fmaxf(v, -ACCFLOW_FP16_MAX), ACCFLOW_FP16_MAX); }
 __device__ __forceinline__ void store_planes(__nv_bfloat16* dst, long long plane_stride, int nplanes, float v) {
   if (nplanes == 2) {
+    v = sat_fp16(v);
     __half* d = reinterpret_cast<__half*>(dst);
     const __half hi = __float2half_rn(v);
     d[0] = hi;
@@ -96,8 +101,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 // 4 consecutive channels (8-byte aligned destination) into the operand planes: one 8-byte store per plane.
-__device__ __forceinline__ void store_planes4_at(__nv_bfloat16* base, long long plane_stride, int nplanes, const float* y) {
+__device__ __forceinline__ void store_planes4_at(__nv_bfloat16* base, long long plane_stride, int nplanes, const float* yin) {
   if (nplanes == 2) {   // fp16 hi + pre-scaled fp16 lo
+    const float y[4] = {sat_fp16(yin[0]), sat_fp16(yin[1]), sat_fp16(yin[2]), sat_fp16(yin[3])};
     const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
     const __half2 l01 = __floats2half2_rn((y[0] - f01.x) * ACCFLOW_FP16X2_SCALE, (y[1] - f01.y) * ACCFLOW_FP16X2_SCALE);
@@ -107,6 +113,7 @@ __device__ __forceinline__ void store_planes4_at(__nv_bfloat16* base, long long 
         make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
     return;
   }
+  const float* y = yin;
   const __nv_bfloat162 a01 = __floats2bfloat162_rn(y[0], y[1]), a23 = __floats2bfloat162_rn(y[2], y[3]);
   *reinterpret_cast<uint2*>(base) = make_uint2(*reinterpret_cast<const uint32_t*>(&a01), *reinterpret_cast<const uint32_t*>(&a23));
   if (nplanes > 1) {

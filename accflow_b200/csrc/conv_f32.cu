@@ -153,6 +153,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_f32_kernel(const ConvK p) {
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = fmaf(acc[i][j], sc[j], sh[j]);
+    if (d.pre_add) {   // cout % 4 == 0 (host check): the group is whole
+      const float4 a = *reinterpret_cast<const float4*>(d.pre_add + pix * d.pre_ld + nb);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+    }
     if (d.epilogue == ACCFLOW_EPI_STORE) {
       if (p.out_vec && nb + 3 < d.cout) {
 #pragma unroll
@@ -595,6 +599,8 @@ extern "C" int accflow_conv2d_f32(const accflow_conv_desc* dp, void* stream) {
   }
   k.out_vec = d.epilogue == ACCFLOW_EPI_STORE && d.act_split == 0 && aligned16(d.out) && d.out_ld % 4 == 0 &&
               (!d.residual || (aligned16(d.residual) && d.res_ld % 4 == 0));
+  ACCFLOW_REQUIRE(!d.pre_add || (aligned16(d.pre_add) && d.pre_ld % 4 == 0 && d.cout % 4 == 0),
+                  "conv2d: pre_add must be 16B aligned with pre_ld %% 4 == 0 and cout %% 4 == 0");
   dim3 grid(cdiv((long long)k.out_h * k.out_w, BM), cdiv(d.cout, BN), d.batch);
   conv_f32_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(k);
   return launched("conv2d_f32");

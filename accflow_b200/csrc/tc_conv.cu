@@ -66,6 +66,7 @@ struct Params {
   int act, act_split, act2;
   const float* residual;
   int res_ld, post_relu, epilogue, out_vec;
+  const float* pre_add; int pre_ld;         // added before the activation / gate math (hoisted GRU `inp` term)
   float* out; int out_ld;
   float* out2; int out2_ld;
   float* h; int h_ld;
@@ -679,6 +680,10 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             const long long pix = ((long long)sample * p.out_h + oy) * p.out_w + ox;
             const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
             float y[4] = {fmaf(a4.x, sc[0], sh[0]), fmaf(a4.y, sc[1], sh[1]), fmaf(a4.z, sc[2], sh[2]), fmaf(a4.w, sc[3], sh[3])};
+            if (p.pre_add) {
+              const float4 pa = __ldg(reinterpret_cast<const float4*>(p.pre_add + pix * p.pre_ld + nb));
+              y[0] += pa.x; y[1] += pa.y; y[2] += pa.z; y[3] += pa.w;
+            }
             if (p.epilogue == ACCFLOW_EPI_STORE) {
               if (p.out_vec && vec4) {
 #pragma unroll
@@ -748,330 +753,6 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   }
 }
 
-// ---------------------------------------------------------------------------------- CTA-pair helpers
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of the same shared variable in CTA rank 0 (the MMA leader) of the cluster
-__device__ __forceinline__ uint32_t mapa_rank0(uint32_t local_addr) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local_addr));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma2_load_4d(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
-                                             int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma2_load_5d(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
-                                             int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// ---- CTA-pair variant (tcgen05 cta_group::2) --------------------------------------------------
-// A cluster of two CTAs computes a 256-pixel x BN tile: each CTA stages its own 128 pixel rows
-// of A and HALF of the weight tile; the leader CTA issues M=256 MMAs that read both CTAs'
-// shared memory, so the weight bytes landing per SM halve and BN can be 256 (operand bytes per
-// MAC: 1/2 of the single-CTA kernel at BN=128).  Each CTA's 128 x BN accumulator lives in its
-// own TMEM and is drained by its own epilogue warps.  Barriers: both CTAs' TMA bytes complete
-// on the LEADER's `full` barrier; tcgen05.commit multicasts `free` / `acc_full` to both CTAs;
-// both CTAs' epilogue warps arrive on the leader's `acc_empty`.
-__global__ void __launch_bounds__(NTHREADS, 1)
-conv_tc2_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPack maps) {
-  extern __shared__ __align__(1024) uint8_t smem_dyn[];
-  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_free[MAX_STAGES], bar_acc_full[2], bar_acc_empty[2];
-  __shared__ uint32_t tmem_slot;
-  // per-tile epilogue affine (alpha folded in), staged once per tile; two copies: a warp set may run one tile ahead
-  __shared__ __align__(16) float s_scale[2][256], s_shift[2][256];
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int taps = p.kh * p.kw;
-  const int BN = p.bn, S = p.stages, NPL = p.nplanes;
-  const int w_plane_bytes = (BN / 2) * KC * 2;          // this CTA's half of the weight tile
-  const int stage_bytes = NPL * (A_PLANE_BYTES + w_plane_bytes);
-  // 1024-byte aligned carve-up (SWIZZLE_128B atoms): [stages][A planes | W planes] then the epilogue panels
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  constexpr int PITCH = 20;                                     // floats per staged row: 16 columns + 4 pad
-  float* stg_base = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);
-
-  int nchunks = 0;
-  for (int s = 0; s < p.nsrc; ++s) nchunks += (p.src_c[s] + KC - 1) / KC;
-  nchunks *= taps;
-  const int acc_cols = (p.nprod > 1 ? 2 : 1) * BN;              // TMEM columns of one accumulator slot
-  const int slots = 2 * acc_cols <= 512 ? 2 : 1;                // double-buffer the accumulator when it fits
-  uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < slots * acc_cols) tmem_cols <<= 1;
-  const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
-  const int m_pairs = (m_tiles + 1) >> 1;
-  const int total_tiles = m_pairs * p.n_tiles;                  // pair tiles
-  const uint32_t crank = cluster_ctarank();
-  const bool leader = crank == 0;
-  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_free[s], 1);
-    }
-    for (int j = 0; j < 2; ++j) {
-      mbar_init(&bar_acc_full[j], 1);
-      mbar_init(&bar_acc_empty[j], 16);     // one arrival per epilogue warp of both CTAs (leader's copy is used)
-    }
-    fence_barrier_init();
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
-    for (int s = 0; s < p.nsrc; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
-  }
-  if (warp == 1) tmem_alloc2(&tmem_slot, tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                 // peer barriers are initialised before anything signals them
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
-
-  if (warp == 0) {
-    // ================================ TMA producer ============================================
-    if (lane == 0) {
-      int it = 0;                                            // global chunk counter (ring position)
-      const uint32_t full_leader = mapa_rank0(smem_u32(&bar_full[0]));   // leader's copy of bar_full[0]
-      for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
-        const int n_tile = tile / m_pairs;
-        int t = 2 * (tile - n_tile * m_pairs) + (int)crank;              // this CTA's 128-pixel tile
-        const int tile_x = t % p.tiles_x; t /= p.tiles_x;
-        const int tile_y = t % p.tiles_y;
-        const int sample = t / p.tiles_y;                                 // >= batch for the phantom tile: TMA zero-fills
-        const int ox0 = tile_x * p.tw, oy0 = tile_y * p.th, n0 = n_tile * BN + (int)crank * (BN / 2);
-        Chunk ck{0, 0, 0};
-        for (int i = 0; i < nchunks; ++i, ++it) {
-          const int s = it % S, round = it / S;
-          if (round > 0) mbar_wait(&bar_free[s], (round - 1) & 1);
-          uint8_t* adst = smem + (size_t)s * stage_bytes;
-          uint8_t* wdst = adst + NPL * A_PLANE_BYTES;
-          if (leader) mbar_expect_tx(&bar_full[s], (uint32_t)(2 * stage_bytes));   // bytes of both CTAs land here
-          const int ky = ck.tap / p.kw, kx = ck.tap - ky * p.kw;
-          const int ix = ox0 * p.stride + kx - p.pad_w, iy = oy0 * p.stride + ky - p.pad_h;
-          const int kcoord = p.src_off[ck.s] + ck.c0;
-          const int tw_ = p.per_sample ? sample : ck.tap;
-          const uint32_t bar = full_leader + s * 8;
-          tma2_load_5d(adst, &maps.a[ck.s], bar, ck.c0, ix, iy, sample, 0);     // all planes per op (box outermost dim)
-          tma2_load_4d(wdst, &maps.w, bar, kcoord, n0, tw_, 0);
-          ck.next(p, taps);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ==============================================
-    if (lane == 0 && leader) {
-      const uint32_t idesc = make_idesc(2 * BM, BN, p.nprod == 3);
-      int it = 0, lt = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += nclusters, ++lt) {
-        const int slot = slots == 2 ? (lt & 1) : 0, use = slots == 2 ? (lt >> 1) : lt;
-        mbar_wait(&bar_acc_empty[slot], (use & 1) ^ 1);     // epilogue has drained this slot (first use passes)
-        tc_fence_after();
-        const uint32_t acc_main = tmem_base + slot * acc_cols, acc_corr = acc_main + BN;
-        uint32_t first_main = 0, first_corr = 0;            // 0 -> overwrite accumulator
-        for (int i = 0; i < nchunks; ++i, ++it) {
-          const int s = it % S, round = it / S;
-          mbar_wait(&bar_full[s], round & 1);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t w_base = a_base + NPL * A_PLANE_BYTES;
-#pragma unroll
-          for (int k4 = 0; k4 < KC / 16; ++k4) {
-            const uint32_t koff = k4 * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
-            const uint64_t a0 = make_desc(a_base + koff), w0 = make_desc(w_base + koff);
-            umma2_bf16(acc_main, a0, w0, idesc, first_main);
-            first_main = 1;
-            if (p.nprod > 1) {
-              const uint64_t a1 = make_desc(a_base + A_PLANE_BYTES + koff), w1 = make_desc(w_base + w_plane_bytes + koff);
-              umma2_bf16(acc_corr, a0, w1, idesc, first_corr);
-              first_corr = 1;
-              umma2_bf16(acc_corr, a1, w0, idesc, 1);
-              if (p.nprod == 6) {
-                const uint64_t a2 = make_desc(a_base + 2 * A_PLANE_BYTES + koff), w2 = make_desc(w_base + 2 * w_plane_bytes + koff);
-                umma2_bf16(acc_corr, a1, w1, idesc, 1);
-                umma2_bf16(acc_corr, a0, w2, idesc, 1);
-                umma2_bf16(acc_corr, a2, w0, idesc, 1);
-              }
-            }
-          }
-          umma2_commit_mc(&bar_free[s]);  // both CTAs' smem of this stage is reusable once these MMAs retire
-        }
-        umma2_commit_mc(&bar_acc_full[slot]);
-      }
-    }
-  } else {
-    // ================================ epilogue ================================================
-    // Phase 1: TMEM -> registers (MAIN + CORR) -> padded smem panel (16 columns).  Phase 2: coalesced
-    // global traffic with the affine / activation / GRU math, fp32 stores + bf16 planes.
-    const int half = (warp - 2) >> 2;
-    float* stg = stg_base + half * (BM * PITCH);
-    const int trow = 32 * (warp & 3) + lane;                    // TMEM lane owned by this thread
-    const int st = tid - 64 - 128 * half;                       // 0..127 inside this warp set
-    const int pc4 = st & 3;                                     // float4 group inside the 16-column panel
-    const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
-    int lt = 0;
-    const uint32_t empty_leader = mapa_rank0(smem_u32(&bar_acc_empty[0]));
-    for (int tile = cluster_id; tile < total_tiles; tile += nclusters, ++lt) {
-      const int n_tile = tile / m_pairs;
-      int t = 2 * (tile - n_tile * m_pairs) + (int)crank;
-      const int tile_x = t % p.tiles_x; t /= p.tiles_x;
-      const int tile_y = t % p.tiles_y;
-      const int sample = t / p.tiles_y;
-      const int ox0 = tile_x * p.tw, oy0 = tile_y * p.th, n0 = n_tile * BN;
-      const int slot = slots == 2 ? (lt & 1) : 0, use = slots == 2 ? (lt >> 1) : lt;
-      {  // stage this tile's scale / shift (global-load latency off the per-panel critical path)
-        const int et = tid - 64;                                  // 0..255
-        if (et < BN) {
-          const int n = n0 + et;
-          const bool ok = n < p.cout;
-          s_scale[lt & 1][et] = p.alpha * ((p.scale && ok) ? __ldg(p.scale + n) : 1.f);
-          s_shift[lt & 1][et] = (p.shift && ok) ? __ldg(p.shift + n) : 0.f;
-        }
-      }
-      mbar_wait(&bar_acc_full[slot], use & 1);
-      tc_fence_after();
-      asm volatile("bar.sync 3, 256;" ::: "memory");             // staged affine visible to both warp sets
-      const uint32_t lane_addr = tmem_base + slot * acc_cols + ((uint32_t)(32 * (warp & 3)) << 16);
-      for (int c = cbeg; c < cend; c += 16) {
-        {
-          float acc[16];
-          tmem_ld16(lane_addr + c, acc);
-          if (p.nprod > 1) {
-            float corr[16];
-            tmem_ld16(lane_addr + BN + c, corr);
-            const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;   // fp16x2: lo planes carry 2^11
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
-          }
-          float4* d4 = reinterpret_cast<float4*>(stg + trow * PITCH);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) d4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-        }
-        if (c + 16 >= cend) {                 // last TMEM read of this tile: hand the slot back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(empty_leader + slot * 8);
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-        const int nb = n0 + c + pc4 * 4;
-        if (nb < p.cout) {
-          const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
-          const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[lt & 1][c + pc4 * 4]);
-          const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
-          const bool vec4 = nb + 3 < p.cout;
-#pragma unroll 2
-          for (int itr = 0; itr < 4; ++itr) {
-            const int row = itr * 32 + (st >> 2);
-            const int oy = oy0 + (row >> p.tw_shift), ox = ox0 + (row & (p.tw - 1));
-            if (oy >= p.out_h || ox >= p.out_w || sample >= p.batch) continue;
-            const long long pix = ((long long)sample * p.out_h + oy) * p.out_w + ox;
-            const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
-            float y[4] = {fmaf(a4.x, sc[0], sh[0]), fmaf(a4.y, sc[1], sh[1]), fmaf(a4.z, sc[2], sh[2]), fmaf(a4.w, sc[3], sh[3])};
-            if (p.epilogue == ACCFLOW_EPI_STORE) {
-              if (p.out_vec && vec4) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) y[j] = act_apply(y[j], p.act);
-                if (p.residual) {
-                  const float4 r = *reinterpret_cast<const float4*>(p.residual + pix * p.res_ld + nb);
-                  y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
-                }
-                if (p.post_relu) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
-                }
-                if (p.out) *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
-                if (p.out_pl.ptr) store_planes4(p.out_pl, NPL, pix, nb, y);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int n = nb + j;
-                  if (n < p.cout) {
-                    const bool second = p.act_split > 0 && n >= p.act_split;
-                    float o = act_apply(y[j], second ? p.act2 : p.act);
-                    if (p.residual) o += p.residual[pix * p.res_ld + n];
-                    if (p.post_relu) o = fmaxf(o, 0.f);
-                    if (second && p.out2) {
-                      p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
-                      if (p.out2_pl.ptr) store_planes1(p.out2_pl, NPL, pix, n - p.act_split, o);
-                    } else {
-                      if (p.out) p.out[pix * p.out_ld + n] = o;
-                      if (p.out_pl.ptr) store_planes1(p.out_pl, NPL, pix, n, o);
-                    }
-                  }
-                }
-              }
-            } else if (p.epilogue == ACCFLOW_EPI_GRU_ZR) {
-              const int hd = p.cout >> 1;   // multiple of 4 (checked on the host): a group never straddles z | r
-              float g4[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) g4[j] = 1.f / (1.f + expf(-y[j]));
-              if (nb < hd) {
-                *reinterpret_cast<float4*>(p.z + pix * p.z_ld + nb) = make_float4(g4[0], g4[1], g4[2], g4[3]);
-              } else {
-                const int n = nb - hd;
-                const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + n);
-                float o[4] = {g4[0] * hh.x, g4[1] * hh.y, g4[2] * hh.z, g4[3] * hh.w};
-                if (p.out2) *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
-                if (p.out2_pl.ptr) store_planes4(p.out2_pl, NPL, pix, n, o);
-              }
-            } else {
-              const float4 zz = *reinterpret_cast<const float4*>(p.z + pix * p.z_ld + nb);
-              const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + nb);
-              float o[4] = {(1.f - zz.x) * hh.x + zz.x * tanhf(y[0]), (1.f - zz.y) * hh.y + zz.y * tanhf(y[1]),
-                            (1.f - zz.z) * hh.z + zz.z * tanhf(y[2]), (1.f - zz.w) * hh.w + zz.w * tanhf(y[3])};
-              *reinterpret_cast<float4*>(p.h + pix * p.h_ld + nb) = make_float4(o[0], o[1], o[2], o[3]);
-              if (p.h_pl.ptr) store_planes4(p.h_pl, NPL, pix, nb, o);
-            }
-          }
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-      }
-    }
-  }
-  __syncthreads();
-  cluster_sync_all();                 // nobody leaves while the peer may still read its smem / signal its barriers
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc2(tmem_base, tmem_cols);
-  }
-}
-
 // fp32 [rows][k] (row stride ld) -> 16-bit operand planes: out[pl*plane_stride + row*pitch + c], c < k_fill
 // (columns k..k_fill-1 are zero-filled).  Scalar version + a vector version (8 channels per thread, 16-byte stores).
 __global__ void split_planes_kernel(const float* __restrict__ x, long long rows, int k, int ld, int k_fill, int pitch,
@@ -1092,10 +773,12 @@ __global__ void split_planes_vec8_kernel(const float* __restrict__ x, long long 
   const int c = (int)(i - r * k8) * 8;
   const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
   const float4 b = __ldg(reinterpret_cast<const float4*>(x + r * ld + c) + 1);
-  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
   __nv_bfloat16* dst = out + r * pitch + c;
   uint32_t p0[4], p1[4], p2[4];
   if (nplanes == 2) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = sat_fp16(v[e]);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const __half2 hi = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
@@ -1213,20 +896,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   p.cout = d.cout;
   p.nprod = nprod;
   p.nplanes = nplanes;
-  // CTA pairs (cta_group::2): implemented and parity-tested, but OPT-IN (ACCFLOW_TC_2CTA=1).  On isolated
-  // large split-mode convs they are 1.2-1.45x faster (half the weight bytes per SM, BN = 256), but with the
-  // full 512-column accumulator the epilogue cannot overlap the next tile and a whole AccFlow step comes
-  // out 1 % slower than the single-CTA kernel (profiles/README.md), so the default stays single-CTA.
   const int m_tiles_all = p.tiles_x * p.tiles_y * d.batch;
-  int k_steps = 0;
-  for (int s = 0; s < d.nsrc; ++s) k_steps += cdiv(d.src_c[s], tc::KC);
-  k_steps *= per_sample ? 1 : d.kh * d.kw;
-  bool pair = false;
-  if (const char* e = getenv("ACCFLOW_TC_2CTA")) {
-    const int mode = atoi(e);   // 1: heuristic (split modes, >= 9 K steps, >= 8 tiles); 2: every shape that allows it
-    const bool allowed = m_tiles_all >= 2 && (!per_sample || (p.tiles_x * p.tiles_y) % 2 == 0);
-    pair = mode == 2 ? allowed : (mode == 1 && allowed && m_tiles_all >= 8 && nprod > 1 && k_steps >= 9);
-  }
   // Shift modes (see Params): stride-1 multi-tap convs load each activation box once per K block and
   // serve kh (mode 1) or kw (mode 2) taps from it.  ACCFLOW_TC_SHIFT=0 forces one box per tap.
   static bool shift_env_read = false, shift_enabled = true;
@@ -1235,7 +905,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     shift_env_read = true;
   }
   p.mode = 0; p.n_outer = per_sample ? 1 : d.kh * d.kw; p.n_inner = 1;
-  if (shift_enabled && !pair && !per_sample && d.stride == 1 && d.kh * d.kw > 1 && nplanes <= 2 && d.kh <= 7 && d.kw <= 7) {
+  if (shift_enabled && !per_sample && d.stride == 1 && d.kh * d.kw > 1 && nplanes <= 2 && d.kh <= 7 && d.kw <= 7) {
     if (d.kh > 1) { p.mode = 1; p.n_outer = d.kw; p.n_inner = d.kh; p.tile_w = 8; p.tile_h = 16; }
     else if (!tc::mode2_rejected) { p.mode = 2; p.n_outer = d.kh; p.n_inner = d.kw; p.tile_w = 16; p.tile_h = 8; }
     if (p.mode) {
@@ -1245,13 +915,10 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   }
   p.msub = 1;
   if (const char* e = getenv("ACCFLOW_TC_DEBUG")) p.debug = atoi(e);
-  // N tile: multiple of 32.  Single CTA: the split modes keep two accumulators x two TMEM slots (BN <= 128);
-  // CTA pair: each CTA holds half of the weight tile, BN up to 256 (one TMEM slot in the split modes).
-  const int bn_cap = pair ? 256 : (nprod == 1 ? 256 : 128);
+  // N tile: multiple of 32; the split modes keep two accumulators (MAIN | CORR) x two TMEM slots (BN <= 128).
+  const int bn_cap = nprod == 1 ? 256 : 128;
   int ntiles = cdiv(d.cout, bn_cap);
   int bn = cdiv(cdiv(d.cout, ntiles), 32) * 32;
-  p.bn = bn;
-  if (pair && bn % 64 != 0) bn = cdiv(bn, 64) * 64;      // each CTA's half must be a multiple of 32 rows
   p.bn = bn;
   p.n_tiles = cdiv(d.cout, bn);
   // Narrow N tiles in the shift modes: two 128-pixel sub-tiles per CTA tile share every weight tile (the
@@ -1268,7 +935,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     }
   }
   p.a_plane_bytes = (tc::BM * p.msub + 8 * (p.n_inner - 1)) * tc::KC * 2;
-  const int a_stage = nplanes * p.a_plane_bytes, b_stage = nplanes * (pair ? bn / 2 : bn) * tc::KC * 2;
+  const int a_stage = nplanes * p.a_plane_bytes, b_stage = nplanes * bn * tc::KC * 2;
   const int stage_bytes = a_stage + b_stage;
   const int epi_bytes = 2 * tc::BM * 20 * 4;                 // two 128 x (16+4)-float epilogue panels
   const int ring_bytes = 222 * 1024 - 1024 - epi_bytes;
@@ -1308,7 +975,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     ACCFLOW_REQUIRE(aligned16(d.z) && aligned16(d.h) && d.z_ld % 4 == 0 && d.h_ld % 4 == 0,
                     "conv2d_tc: GRU buffers must be 16B aligned");
   } else if (d.epilogue == ACCFLOW_EPI_STORE_POOL) {
-    ACCFLOW_REQUIRE(per_sample && !pair && p.mode == 0 && d.out && d.out2 && d.pool_w >= 32 && d.pool_w % 32 == 0 &&
+    ACCFLOW_REQUIRE(per_sample && p.mode == 0 && d.out && d.out2 && d.pool_w >= 32 && d.pool_w % 32 == 0 &&
                         bn % (2 * d.pool_w) == 0 && d.cout % bn == 0 && d.act == ACCFLOW_ACT_NONE && !d.residual &&
                         d.act_split == 0 && aligned16(d.out) && aligned16(d.out2) && d.out_ld % 4 == 0 && d.out2_ld % 8 == 0,
                     "conv2d_tc: STORE_POOL needs a per-sample GEMM whose N tile (%d) covers whole row pairs of the "
@@ -1319,6 +986,10 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   }
   p.out_vec = d.epilogue == ACCFLOW_EPI_STORE && d.act_split == 0 && aligned16(d.out) && (!d.out || d.out_ld % 4 == 0) &&
               (!d.residual || (aligned16(d.residual) && d.res_ld % 4 == 0));
+  ACCFLOW_REQUIRE(!d.pre_add || (aligned16(d.pre_add) && d.pre_ld % 4 == 0 && d.cout % 4 == 0 &&
+                                 d.epilogue != ACCFLOW_EPI_STORE_POOL),
+                  "conv2d_tc: pre_add must be 16B aligned with pre_ld %% 4 == 0 and cout %% 4 == 0");
+  p.pre_add = d.pre_add; p.pre_ld = d.pre_ld;
 
   tc::EncodeTiledFn enc = tc::encode_fn();
   ACCFLOW_REQUIRE(enc != nullptr, "conv2d_tc: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -1334,7 +1005,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     const cuuint64_t gdim[4] = {(cuuint64_t)w.k, (cuuint64_t)w.rows, (cuuint64_t)w.t, (cuuint64_t)w.nplanes};
     const cuuint64_t gstr[3] = {(cuuint64_t)w.k_pitch * 2, (cuuint64_t)w.k_pitch * 2 * w.rows,
                                 (cuuint64_t)w.k_pitch * 2 * w.rows * w.t};
-    const cuuint32_t box[4] = {(cuuint32_t)tc::KC, (cuuint32_t)(pair ? bn / 2 : bn), 1, (cuuint32_t)nplanes};   // all planes in one op
+    const cuuint32_t box[4] = {(cuuint32_t)tc::KC, (cuuint32_t)bn, 1, (cuuint32_t)nplanes};   // all planes in one op
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult cr = enc(&maps.w, nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w.planes), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
@@ -1375,32 +1046,6 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   }
   static thread_local int sm_count = 0;
   if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
-  if (pair) {
-    static thread_local int cfg2_dev = -1;
-    if (cfg2_dev != dev) {
-      cudaError_t e = cudaFuncSetAttribute(tc::conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
-      if (e != cudaSuccess) return fail((int)e, "conv2d_tc: smem attribute (pair kernel): %s", cudaGetErrorString(e));
-      cfg2_dev = dev;
-    }
-    const int pair_tiles = ((m_tiles_all + 1) / 2) * p.n_tiles;
-    const int nclusters = pair_tiles < sm_count / 2 ? pair_tiles : sm_count / 2;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * nclusters, 1, 1);
-    cfg.blockDim = dim3(tc::NTHREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc::conv_tc2_kernel, p, maps);
-    if (e != cudaSuccess) return fail((int)e, "conv2d_tc: cluster launch failed: %s", cudaGetErrorString(e));
-    return launched("conv2d_tc2");
-  }
   const int total_tiles = p.tiles_x * p.tiles_y * d.batch * p.n_tiles;
   dim3 grid(total_tiles < sm_count ? total_tiles : sm_count, 1, 1);
   tc::conv_tc_kernel<<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);

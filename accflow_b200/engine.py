@@ -141,6 +141,7 @@ def split_planes_torch(x: torch.Tensor, fp16x2: bool = False) -> torch.Tensor:
     """x (fp32) -> stacked 16-bit planes (one-off weight packing): bf16 p0, p1, p2 with x ~= p0 + p1 + p2,
     or fp16 (hi, lo * 2^11) when ``fp16x2``."""
     if fp16x2:
+        x = x.clamp(-65504.0, 65504.0)           # same saturation as the device-side split (common.cuh sat_fp16)
         hi = x.to(torch.float16)
         lo = ((x - hi.float()) * 2048.0).to(torch.float16)
         return torch.stack([hi, lo]).contiguous()
@@ -215,7 +216,7 @@ class Kernels:
             if not create:
                 return None
             cp, _ = self._plane_geom(v)
-            pl = torch.empty(3, v.t.shape[0], v.h, v.w, cp, device=self.device, dtype=torch.bfloat16)
+            pl = torch.empty(self.nplanes, v.t.shape[0], v.h, v.w, cp, device=self.device, dtype=torch.bfloat16)
             self._planes[key] = pl
             self._stale[key] = [(0, v.ld)]
             self._roots[key] = v.t
@@ -256,10 +257,11 @@ class Kernels:
              post_relu=False, epilogue=L.EPI_STORE, h: Optional[View] = None, z: Optional[View] = None,
              weight_ptr: Optional[int] = None, weight_batch_stride=0, cout=None, cout_pad=None,
              use_affine=True, tc_b: Optional["L.TcWeights"] = None, tc_src_planes=None, planes_only=False,
-             emit_planes=True, pool_w=0):
+             emit_planes=True, pool_w=0, pre_add: Optional[View] = None):
         """``planes_only``: the output (``out``; ``out2`` for the GRU z|r epilogue) is read by tensor-core
         convolutions only, so in the tensor-core modes its fp32 copy is not written (half the store bytes).
-        ``emit_planes=False``: the next reader is not a tensor-core conv (InstanceNorm), so no planes are written."""
+        ``emit_planes=False``: the next reader is not a tensor-core conv (InstanceNorm), so no planes are written.
+        ``pre_add``: fp32 slice added before the activation / gate math (the hoisted GRU ``inp`` term)."""
         d = L.ConvDesc()
         cin = 0
         for k, s in enumerate(srcs):
@@ -291,6 +293,9 @@ class Kernels:
             d.h, d.h_ld = h.ptr, h.ld
         if z is not None:
             d.z, d.z_ld = z.ptr, z.ld
+        if pre_add is not None:
+            assert pre_add.c == d.cout and pre_add.b == s0.b
+            d.pre_add, d.pre_ld = pre_add.ptr, pre_add.ld
         if tc:
             io = L.TcIO()
             for k, sv in enumerate(srcs):
@@ -316,7 +321,7 @@ class Kernels:
                     written.append(tv)
                 else:
                     self.wrote(tv)
-            if planes_only and written:      # the planes carry the result; drop the fp32 store
+            if planes_only and written and written[0].full_rows:      # the planes carry the result; drop the fp32 store
                 if epilogue == L.EPI_STORE and not act_split and written[0] is out:
                     d.out = None
                 elif epilogue == L.EPI_GRU_ZR and written[0] is out2:
@@ -520,7 +525,8 @@ class GraphCache:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = L.call("accflow_launch_count", 0)
-            with torch.cuda.graph(graph):
+            # thread_local: under nn.DataParallel the other replicas' threads keep launching while this one captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 out = fn(*ent["in"])
             ent["graph"], ent["out"] = graph, out
             ent["launches"] = L.call("accflow_launch_count", 0) - n0
@@ -571,7 +577,7 @@ class EncoderPlan:
         H, W = int(images[0].shape[-2]), int(images[0].shape[-1])
         h2, w2 = (H + 1) // 2, (W + 1) // 2
         pitch = 152
-        patches = k.buf16("stem.patches", 3, n, h2, w2, pitch)
+        patches = k.buf16("stem.patches", k.nplanes, n, h2, w2, pitch)
         stride_pl = n * h2 * w2 * pitch
         b0 = 0
         for im in images:
@@ -669,13 +675,21 @@ class FlowEstimatorEngine:
         self.convf1.w = sd[u + "encoder.convf1.weight"].to(F32).permute(2, 3, 1, 0).reshape(98, 128).contiguous()
         self.convf2 = pc(u + "encoder.convf2", (1, 1))
         self.convm = pc(u + "encoder.conv", (1, 1))
+        # SepConvGRU (raft/update.py:45-60) reads cat[h, inp, mf(, mf_global)].  `inp` (input channels 128..255) does
+        # not change over the iterations of one pair, so the filters are split: the `inp` columns are applied once per
+        # frame (gru_inp_terms) and enter every iteration as a pre-activation addend; the per-iteration convolutions
+        # contract over [h, mf(, mf_global)] only (2/3 resp. 3/4 of the reference's GRU multiply-adds).
         g = u + "gru."
-        self.gru = []
+        self.gru, self.gru_inp = [], []
         for tag, pad in (("1", (0, 2)), ("2", (2, 0))):
-            zr = PackedConv([sd[f"{g}convz{tag}.weight"], sd[f"{g}convr{tag}.weight"]],
-                            [sd[f"{g}convz{tag}.bias"], sd[f"{g}convr{tag}.bias"]], 1, pad)
-            q = pc(f"{g}convq{tag}", pad)
+            wz, wr, wq = (sd[f"{g}conv{n}{tag}.weight"] for n in "zrq")
+            rest = lambda w: torch.cat([w[:, :128], w[:, 256:]], 1)
+            only = lambda w: w[:, 128:256]
+            zr = PackedConv([rest(wz), rest(wr)], [sd[f"{g}convz{tag}.bias"], sd[f"{g}convr{tag}.bias"]], 1, pad)
+            q = PackedConv([rest(wq)], [sd[f"{g}convq{tag}.bias"]], 1, pad)
             self.gru.append((zr, q))
+            self.gru_inp.append((PackedConv([only(wz), only(wr)], [None, None], 1, pad),
+                                 PackedConv([only(wq)], [None], 1, pad)))
         self.fh1 = pc(u + "flow_head.conv1", (1, 1))
         self.fh2 = pc(u + "flow_head.conv2", (1, 1))
         self.mk1 = pc(u + "mask.0", (1, 1))
@@ -702,10 +716,26 @@ class FlowEstimatorEngine:
                                                                  act2=L.ACT_RELU), **patch_kw)
         return hid, inp
 
-    def prepare(self, f1: View, f2: View, hid: View, inp: View, H: int, W: int, tag: str):
-        """Correlation pyramid (+ GMA attention) for a batch of pairs whose features are given."""
+    def gru_inp_terms(self, inp: View, tag: str):
+        """conv_{z|r}(inp), conv_q(inp) of both GRU halves for a batch of context maps: the part of
+        SepConvGRU's six convolutions (raft/update.py:47-58) that is constant over the refinement loop.
+        -> [(zr1, q1), (zr2, q2)], fp32 [n, h, w, 256 | 128]."""
+        k = self.k
+        out = []
+        for half, (zr_i, q_i) in enumerate(self.gru_inp):
+            gzr = k.view(f"{tag}.gi_zr{half}", inp.b, inp.h, inp.w, 256)
+            gq = k.view(f"{tag}.gi_q{half}", inp.b, inp.h, inp.w, 128)
+            k.conv(zr_i, [inp], gzr, emit_planes=False)
+            k.conv(q_i, [inp], gq, emit_planes=False)
+            out.append((gzr, gq))
+        return out
+
+    def prepare(self, f1: View, f2: View, hid: View, inp: View, H: int, W: int, tag: str, gru_pre=None):
+        """Correlation pyramid (+ GMA attention, + the constant GRU terms unless given) for a batch of pairs whose
+        features are given."""
         B, h, w = f1.b, f1.h, f1.w
         st = dict(B=B, h=h, w=w, P=h * w, H=H, W=W, hid=hid, inp=inp)
+        st["gru_pre"] = gru_pre if gru_pre is not None else self.gru_inp_terms(inp, tag)
         st["pyr"] = self.corr_pyramid(f1, f2, tag)
         if self.gma:
             st["attn"] = self.attention(inp, tag)
@@ -774,11 +804,11 @@ class FlowEstimatorEngine:
         z = k.view(tag + ".z", B, h, w, 128)
         fh = k.view(tag + ".fh", B, h, w, 256)
         delta = k.view(tag + ".delta", B, h, w, 2)
-        x_srcs = [inp, mf]
+        x_srcs = [mf]                      # `inp` enters through st["gru_pre"]
         if self.gma:
             vbuf = k.view(tag + ".v", B, h, w, 128)
             mfg = k.view(tag + ".mfg", B, h, w, 128)
-            x_srcs = [inp, mf, mfg]
+            x_srcs = [mf, mfg]
         if flow_init is not None:
             flow_init = flow_init.to(device=self.device, dtype=F32).contiguous()
             assert tuple(flow_init.shape) == (B, 2, h, w)
@@ -795,9 +825,9 @@ class FlowEstimatorEngine:
                 # Aggregate.forward (gma/modules.py:102-115): mf + gamma * (attn @ to_v(mf))
                 k.conv(self.to_v, [mf], vbuf)
                 k.gemm_nn(tag + ".agg", View(st["attn"].view(B, h, w, P)), vbuf, mfg, alpha=self.gamma, residual=mf)
-            for zr, q in self.gru:
-                k.conv(zr, [hid] + x_srcs, epilogue=L.EPI_GRU_ZR, h=hid, z=z, out2=rh, planes_only=True)
-                k.conv(q, [rh] + x_srcs, epilogue=L.EPI_GRU_Q, h=hid, z=z)
+            for (zr, q), (pre_zr, pre_q) in zip(self.gru, st["gru_pre"]):
+                k.conv(zr, [hid] + x_srcs, epilogue=L.EPI_GRU_ZR, h=hid, z=z, out2=rh, planes_only=True, pre_add=pre_zr)
+                k.conv(q, [rh] + x_srcs, epilogue=L.EPI_GRU_Q, h=hid, z=z, pre_add=pre_q)
             k.conv(self.fh1, [hid], fh, act=L.ACT_RELU, planes_only=True)
             k.conv_smallcout(self.fh2, fh, delta, accum=coords, accum_ld=2)     # coords1 += delta_flow
         # mask head + convex upsample: only the last iteration's is observable (raft.py:139-146)
@@ -961,14 +991,21 @@ class AccFlowEngine:
         k.conv(self.dm2, [t256], mask)
         out = torch.empty(b, 2, H, W, device=dev, dtype=F32)
         L.call("accflow_convex_upsample_f32", small.data_ptr(), 2, 0, mask.ptr, mask.ld, b, h, w, out.data_ptr(), s())
+        self.last_dflow = dflow.view(b, h, w, 2).permute(0, 3, 1, 2).contiguous()     # F(i -> i-1) at 1/8 (warm start)
         return small.permute(0, 3, 1, 2).contiguous(), out
 
-    def forward(self, images: List[torch.Tensor], iters=12, graph=False) -> List[torch.Tensor]:
+    def forward(self, images: List[torch.Tensor], iters=12, graph=False, warm_start=False,
+                warm_iters: Optional[int] = None) -> List[torch.Tensor]:
         """AccFlow.forward (AccFlow_.py:157-175) with every encoder evaluated once per distinct frame.
 
         The reference re-runs fnet / cnet / context on the same frames at every accumulation step
         (22 / 11 / 15 image passes per 7-frame clip for 7 / 6 / 7 distinct frames, SURVEY.md §3.2);
         all three encoders are per-sample functions, so the cached features are identical.
+
+        ``warm_start`` (the reference README's open TODO "Add warmstart mode"; the estimators already take
+        ``flow_init``, raft/raft.py:123-124): from the second accumulation step on, the pair (i -> i-1) starts from
+        the previous step's F(i-1 -> i-2) and the pair (i -> 0) from the previous accumulated flow F(i-1 -> 0), both
+        at 1/8 resolution, and may run ``warm_iters`` (<= iters) refinement iterations.
         """
         images = [t.to(device=self.device, dtype=F32).contiguous() for t in images]
 
@@ -982,6 +1019,7 @@ class AccFlowEngine:
             fm = ofe.run_fnet(list(imgs), "clip", **pk)                    # frame f -> rows [f*b, (f+1)*b)
             hid_all, inp_all = ofe.run_cnet(list(imgs[1:]), "clip", patch_image0=b, **pk)  # frame f (>=1) -> rows [(f-1)*b, f*b)
             ctx = self.context.run(k, list(imgs), "clip.ctx", **pk)
+            gi_all = ofe.gru_inp_terms(inp_all, "clip")                   # constant GRU terms, once per frame
             h, w = fm.h, fm.w
 
             def gather(src: View, frames, name):
@@ -998,9 +1036,14 @@ class AccFlowEngine:
                 f1 = gather(fm, [p[0] for p in pairs], tag + ".f1")
                 f2 = gather(fm, [p[1] for p in pairs], tag + ".f2")
                 hid = gather(hid_all, [p[0] - 1 for p in pairs], tag + ".hid")
-                inp = gather(inp_all, [p[0] - 1 for p in pairs], tag + ".inpg")
-                st = ofe.prepare(f1, f2, hid, inp, H, W, tag)
-                flows = ofe.iterate(st, iters, None, tag)
+                inp = gather(inp_all, [p[0] - 1 for p in pairs], tag + ".inpg") if ofe.gma else None   # attention only
+                pre = [tuple(gather(t, [p[0] - 1 for p in pairs], f"{tag}.gi{hf}{j}") for j, t in enumerate(pr))
+                       for hf, pr in enumerate(gi_all)]
+                st = ofe.prepare(f1, f2, hid, inp, H, W, tag, gru_pre=pre)
+                if warm_start and flow is not None:
+                    flows = ofe.iterate(st, warm_iters or iters, torch.cat([self.last_dflow, flow]), tag)
+                else:
+                    flows = ofe.iterate(st, iters, None, tag)
                 flow, up = self._accumulate(flows, b, ctx.rows(i * b, (i + 1) * b), ctx.rows((i - 1) * b, i * b),
                                             ctx.rows(0, b), flow)
                 outs.append(up)
@@ -1009,5 +1052,5 @@ class AccFlowEngine:
         with torch.cuda.device(self.device):
             if not graph:
                 return eager(*images)
-            key = (tuple(images[0].shape), len(images), iters)
+            key = (tuple(images[0].shape), len(images), iters, bool(warm_start), warm_iters)
             return self.graphs.run(key, images, eager)

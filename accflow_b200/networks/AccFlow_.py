@@ -31,10 +31,15 @@ class AccFlow(nn.Module):
         self.hidden_channel = 128
         self.mixed_precision = True
         self.iters = 12          # additive: the reference hard-codes the ofe default (AccFlow_.py:184,188)
+        # additive (the reference README's TODO "Add warmstart mode"): chain the previous step's flows as flow_init of
+        # the next step's estimator calls (raft/raft.py:123-124); warm_iters = iterations of the warm-started calls
+        self.warm_start = False
+        self.warm_iters = None
         ofe_keys = ("ofe.",)
         _tree.populate(self, [e for e in S.accflow_entries("gma" if ofe._GMA else "raft")
                               if not e.name.startswith(ofe_keys)])
-        self._engines = {}
+        self._engines = {}          # shared with DataParallel replicas (shallow __dict__ copy)
+        _tree.register_source(self)
 
     def engine(self, device=None):
         from ..engine import AccFlowEngine
@@ -42,13 +47,13 @@ class AccFlow(nn.Module):
         if device.type != "cuda":
             raise RuntimeError("accflow_b200 runs on CUDA (sm_100a) only; there is no CPU path")
         precision = self.ofe.precision
-        sig = (_tree.signature(self), precision)
+        src = _tree.source_of(self)          # DataParallel replica -> the module it was made from (see _estimator.engine)
+        sig = (_tree.signature(src), precision)
         key = (device, precision)
         hit = self._engines.get(key)
         if hit is None or hit[0] != sig:
-            hit = (sig, AccFlowEngine(dict(self.state_dict()), device, self.ofe._GMA, precision))
-            if not getattr(self, "_is_replica", False):
-                self._engines[key] = hit
+            hit = (sig, AccFlowEngine(dict(src.state_dict()), device, self.ofe._GMA, precision))
+            self._engines[key] = hit
         return hit[1]
 
     @torch.no_grad()
@@ -61,4 +66,5 @@ class AccFlow(nn.Module):
         """[I0, I1, ..., In] -> [F(2->0), F(3->0), ..., F(n->0)] (``test_mode`` is ignored, as in the reference)."""
         images = list(images)
         eng = self.engine(images[0].device if images[0].is_cuda else None)
-        return eng.forward(images, self.iters, graph=self.ofe.use_cuda_graph)
+        return eng.forward(images, self.iters, graph=self.ofe.use_cuda_graph, warm_start=self.warm_start,
+                           warm_iters=self.warm_iters)

@@ -23,7 +23,8 @@ class FlowEstimatorBase(nn.Module):
         if "dropout" not in args:
             args.dropout = 0
         _tree.populate(self, S.gma_entries() if self._GMA else S.raft_entries())
-        self._engines = {}
+        self._engines = {}          # (device, precision) -> (signature, engine); shared with DataParallel replicas
+        _tree.register_source(self)
         # arithmetic of the conv/GEMM kernels (activations are fp32 in HBM in every mode):
         #   "fp16x2" tcgen05, every operand split into fp16 hi + scaled fp16 lo, 3 products: fp32-class
         #            precision inside the fp16 range (the range of the reference's own autocast default)
@@ -58,14 +59,16 @@ class FlowEstimatorBase(nn.Module):
         if device.type != "cuda":
             raise RuntimeError("accflow_b200 runs on CUDA (sm_100a) only; there is no CPU path — move the "
                                "module to a GPU (.cuda()) before calling it")
-        sig = (_tree.signature(self), self.precision)
+        # under nn.DataParallel (test_cvo.py:18,26) every replica of every forward lands here: the engine (packed
+        # weights, workspaces, captured graph) is cached per device on the SOURCE module and validated against the
+        # source's parameter versions, so replicas never rebuild it
+        src = _tree.source_of(self)
+        sig = (_tree.signature(src), self.precision)
         key = (device, self.precision)
         hit = self._engines.get(key)
         if hit is None or hit[0] != sig:
-            sd = {k: v for k, v in self.state_dict().items()}
-            hit = (sig, FlowEstimatorEngine(sd, device, "", self._GMA, self.precision))
-            if not getattr(self, "_is_replica", False):
-                self._engines[key] = hit
+            hit = (sig, FlowEstimatorEngine(dict(src.state_dict()), device, "", self._GMA, self.precision))
+            self._engines[key] = hit
         return hit[1]
 
     @torch.no_grad()

@@ -87,6 +87,29 @@ def populate(root: nn.Module, entries: Iterable[S.Entry]) -> None:
             node.register_parameter(leaf, nn.Parameter(val))
 
 
+# nn.DataParallel re-creates the replicas (fresh broadcast copies of every parameter) on every forward, so a replica
+# cannot validate a cached engine against its own tensors.  A replica's __dict__ is a shallow copy of its source's
+# (Module._replicate_for_data_parallel), so an id stored at construction survives replication and leads back to the
+# source module, whose parameter versions are the truth.
+import weakref
+
+_SOURCES: "weakref.WeakValueDictionary[int, nn.Module]" = weakref.WeakValueDictionary()
+
+
+def register_source(module: nn.Module) -> None:
+    module._src_id = id(module)
+    _SOURCES[module._src_id] = module
+
+
+def source_of(module: nn.Module) -> nn.Module:
+    """The module a DataParallel replica was made from (the module itself when it is not a replica)."""
+    if getattr(module, "_is_replica", False):
+        src = _SOURCES.get(getattr(module, "_src_id", None))
+        if src is not None:
+            return src
+    return module
+
+
 def signature(module: nn.Module):
     """Cheap change detector for packed weights: (data_ptr, _version) of every tensor."""
     return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))

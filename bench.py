@@ -2,12 +2,17 @@
 """Benchmark of the AccFlow hot path (BASELINE.json: long-range flow pairs/sec, 7-frame
 512x512 clips, 12 GRU iterations per pair).
 
-  python bench.py --gpus 1 --steps 10 --warmup 3            # this implementation
-  python bench.py --impl reference --steps 1 --warmup 0     # reference algorithm on host CPU
+  python bench.py --gpus 1 --steps 10 --warmup 3            # this implementation (BASELINE configs[1])
+  python bench.py --ofe gma                                  # configs[2]: AccFlow+GMA
+  python bench.py --total-clips 64                           # configs[3]: fixed 64-clip sweep (strong scaling)
+  python bench.py --size 1024 --iters 32 --precision bf16 --clips 2      # configs[4]
+  python bench.py --impl reference --steps 1 --warmup 0     # reference algorithm on the host CPU cores
+  python bench.py --impl reference-cuda                      # the reference's schedule in eager PyTorch on the GPU
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of AccFlow+RAFT backward accumulation over `--clips` synthetic CVO-shaped
-clips per GPU (5 long-range flows per 7-frame clip).  Prints ONE JSON line on rank 0.
+A "step" is one pass of AccFlow backward accumulation over `--clips` synthetic CVO-shaped clips per GPU
+(5 long-range flows per 7-frame clip); with `--total-clips T` a step is the whole sweep of T clips dealt
+round-robin to the ranks in micro-batches of `--clips`.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -29,6 +34,7 @@ FRAMES = 7
 FLOWS_PER_CLIP = FRAMES - 2
 # conv/GEMM FLOPs (2*MAC) necessary for identical output, B=1, 512x512, 12 iters.
 NECESSARY_GFLOP_PER_CLIP_512 = 3984.5
+FLOW_TOL_PX, EPE_TOL_PX = 1e-3, 1e-4          # north star: fp32-class flows / per-clip EPE
 
 
 def parse():
@@ -36,15 +42,20 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
     ap.add_argument("--clips", type=int, default=9,
-                    help="clips per GPU per step (9 clips = 18/27 pairs fill the 148 SMs with 7.8/11.7 tile rounds)")
+                    help="clips per GPU per (micro-)step (9 clips = 18/27 pairs fill the 148 SMs with 7.8/11.7 tile rounds)")
+    ap.add_argument("--total-clips", type=int, default=0,
+                    help="BASELINE configs[3]: a step is a sweep over this many clips, sharded over the ranks (strong scaling)")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--ofe", default="raft", choices=["raft", "gma"])
-    ap.add_argument("--precision", default=os.environ.get("ACCFLOW_PRECISION", "fp16x2"), choices=["fp32", "bf16x3", "fp16x2", "bf16"],
+    ap.add_argument("--precision", default=os.environ.get("ACCFLOW_PRECISION", "fp16x2"),
+                    choices=["fp32", "bf16x3", "fp16x2", "bf16"],
                     help="conv/GEMM arithmetic: fp16x2 / bf16x3 = tcgen05 split products (fp32-class, parity-gated at 1e-3 px)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--warm-start", action="store_true", help="AccFlow.warm_start (README TODO; raft.py:123-124 flow_init chaining)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (parity + cpu_baseline)")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the eager-PyTorch-CUDA proxy of the reference")
     return ap.parse_args()
 
 
@@ -103,7 +114,25 @@ def make_inputs(clip_ids, size):
     return make_batch(clip_ids, size=size, frames=FRAMES)
 
 
-# ------------------------------------------------------------------------------- reference arm
+def workload_config(args, clips):
+    which = "configs[1]" if args.ofe == "raft" else "configs[2]"
+    if args.total_clips:
+        which = "configs[3]"
+    if args.size == 1024:
+        which = "configs[4]"
+    cfg = {"workload": f"AccFlow+{args.ofe.upper()} backward accumulation, {FRAMES}-frame {args.size}x{args.size} CVO-shaped synthetic clip, "
+                       f"{args.iters} iters/pair (BASELINE {which})",
+           "clips_per_gpu_per_step": clips, "frames": FRAMES, "size": args.size, "iters": args.iters,
+           "weights": "seeded random (accflow_b200.weights, seed 2)",
+           "l2_policy": "working set per step (correlation volumes + activations) exceeds the 126 MB L2"}
+    if args.total_clips:
+        cfg["total_clips_per_step"] = args.total_clips
+    if args.warm_start:
+        cfg["warm_start"] = True
+    return cfg
+
+
+# ------------------------------------------------------------------------------- reference arm (CPU)
 def run_reference(args):
     """The reference algorithm (oracle port of the reference's fp32 CPU path) on host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -140,12 +169,78 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(args, clips):
-    return {"workload": f"AccFlow+{args.ofe.upper()} backward accumulation, {FRAMES}-frame {args.size}x{args.size} CVO-shaped synthetic clip, "
-                        f"{args.iters} iters/pair (BASELINE configs[1])",
-            "clips_per_gpu_per_step": clips, "frames": FRAMES, "size": args.size, "iters": args.iters,
-            "weights": "seeded random (accflow_b200.weights, seed 2)",
-            "l2_policy": "working set per step (correlation volumes + activations) exceeds the 126 MB L2"}
+# ------------------------------------------------------------------------------- reference schedule on the GPU
+def ref_cuda_proxy(args, dev, clips_list=(1, 4, 9, 10), ours_clip0=None, budget_s=75.0):
+    """North-star denominator: the reference's own PyTorch-CUDA path.  The reference (Python) cannot travel to
+    the GPU box, so `oracle/eager_ref.py` restates its execution schedule with the same library calls
+    (tests/test_eager_ref_faithful.py: identical outputs and ATen-op histogram vs the unmodified reference).
+    Timed like test_cvo.py runs it: cudnn.benchmark=True, fp16 autocast default, batch 10 (test_cvo.py:114-115)."""
+    from accflow_b200.weights import make_state_dict
+    from oracle import eager_ref as er
+    sd = {k: v.to(dev) for k, v in make_state_dict(f"acc+{args.ofe}", seed=2).items()}
+    out = {"what": "oracle/eager_ref.py: the reference's schedule (same ATen/cuDNN/torchvision calls, dead work "
+                   "included) in eager PyTorch on this GPU; the reference sources cannot travel to the GPU box",
+           "runs": []}
+    t_begin = time.time()
+    fp32_clip0 = None
+    for mode in ("fp16_autocast", "fp32_tf32off"):
+        er.configure_like_test_cvo(fp32_exact=(mode == "fp32_tf32off"))
+        for b in clips_list:
+            if time.time() - t_begin > budget_s and out["runs"]:
+                break
+            imgs = [t.to(dev) for t in make_inputs(list(range(b)), args.size)["imgs"]]
+            run = lambda: er.accflow_forward(sd, imgs, args.iters, mixed_precision=(mode == "fp16_autocast"))
+            try:
+                for _ in range(2):
+                    flows = run()                                  # cudnn.benchmark autotune + allocator warm-up
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = 2
+                e0.record()
+                for _ in range(n):
+                    flows = run()
+                e1.record()
+                torch.cuda.synchronize()
+            except torch.OutOfMemoryError:
+                out["runs"].append({"mode": mode, "clips": b, "error": "out of memory"})
+                break
+            ms = e0.elapsed_time(e1) / n
+            out["runs"].append({"mode": mode, "clips": b, "ms_per_step": ms, "flows_per_s": FLOWS_PER_CLIP * b / (ms / 1e3)})
+            if mode == "fp32_tf32off" and fp32_clip0 is None:
+                fp32_clip0 = [f[0:1].float().cpu() for f in flows]
+            if mode == "fp16_autocast" and b == clips_list[0]:
+                out["_fp16_clip0"] = [f[0:1].float().cpu() for f in flows]
+            del imgs, flows
+            torch.cuda.empty_cache()
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.allow_tf32 = True
+    best = [r for r in out["runs"] if r.get("mode") == "fp16_autocast" and "flows_per_s" in r]
+    if best:
+        top = max(best, key=lambda r: r["flows_per_s"])
+        out["value"], out["unit"], out["at_clips"] = top["flows_per_s"], "flows/s", top["clips"]
+    fp16_clip0 = out.pop("_fp16_clip0", None)
+    if fp32_clip0 is not None:
+        md = lambda a, b: max(float((x - y).abs().max()) for x, y in zip(a, b))
+        if fp16_clip0 is not None:
+            out["ref_fp16_autocast_vs_ref_fp32_max_px"] = md(fp16_clip0, fp32_clip0)
+        if ours_clip0 is not None:
+            out["ours_vs_ref_fp32_max_px"] = md(ours_clip0, fp32_clip0)
+    return out
+
+
+def run_reference_cuda(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_grad_enabled(False)
+    assert torch.cuda.is_available(), "--impl reference-cuda needs a CUDA device"
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    r = ref_cuda_proxy(args, dev, budget_s=240.0)
+    line = {"impl": "reference-cuda", "metric": "long-range flow pairs/sec", "value": r.get("value"), "unit": "flows/s",
+            "n_gpus": 1, "higher_is_better": True, "dtype": "fp16 autocast (reference default)", "data": "synthetic",
+            "config": workload_config(args, clips=r.get("at_clips")), "ref_cuda": r}
+    print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------- our arm
@@ -173,51 +268,67 @@ def run_b200(args):
     model = model.to(dev).eval()
     model.iters = args.iters
     model.ofe.precision = args.precision
+    model.warm_start = bool(args.warm_start)
     b = args.clips
-    # clip-parallel sharding: the step's world*b clips are dealt round-robin
+    # clip-parallel sharding: the step's clips are dealt round-robin; with --total-clips each rank
+    # sweeps its shard in micro-batches of b (the last one may be ragged)
     from accflow_b200.sharding import gather_clip_metrics, shard_clip_ids
-    n_clips = world * b
-    batch = make_inputs(shard_clip_ids(n_clips, rank, world), args.size)
-    host_imgs = [t.pin_memory() for t in batch["imgs"]]
-    host_out = torch.empty(b, 2, args.size, args.size).pin_memory()
-    dev_imgs = [t.to(dev) for t in batch["imgs"]]
-    bflow, fflow = batch["bflows"][-1].to(dev), batch["fflows"][-1].to(dev)
+    n_clips = args.total_clips if args.total_clips else world * b
+    my_ids = shard_clip_ids(n_clips, rank, world)
+    micro = [my_ids[i:i + b] for i in range(0, len(my_ids), b)]
+    batches = [make_inputs(ids, args.size) for ids in micro]
+    dev_sets = [([t.to(dev) for t in bt["imgs"]], bt["bflows"][-1].to(dev), bt["fflows"][-1].to(dev)) for bt in batches]
+    host_sets = [[t.pin_memory() for t in bt["imgs"]] for bt in batches]
+    host_out = [torch.empty(len(ids), 2, args.size, args.size).pin_memory() for ids in micro]
+    host_epe = torch.empty(len(my_ids), 3).pin_memory()
 
     def step_resident():
-        flows = model(images=dev_imgs, test_mode=False)
-        epe = metrics.clip_epe(flows[-1], bflow, fflow)                       # (b,3): fused occlusion mask + EPE kernel
+        epes = []
+        for imgs, bflow, fflow in dev_sets:
+            flows = model(images=imgs, test_mode=False)
+            epes.append(metrics.clip_epe(flows[-1], bflow, fflow))           # (b,3): fused occlusion mask + EPE kernel
+        epe = epes[0] if len(epes) == 1 else torch.cat(epes)
         return gather_clip_metrics(epe, n_clips, rank, world)                 # the only collective: metric gather
 
-    # End to end: every step copies its frames from pinned host memory and reads its last flow back.  The copy of
-    # step i+1 runs on a copy stream while step i computes (two device input sets); the first step's copy is exposed.
+    # End to end: every (micro-)step copies its frames from pinned host memory, reads its last flow and its EPE
+    # triplets back.  The copy of the next micro-step runs on a copy stream while the current one computes (two
+    # device input sets); the first copy of a timed region is exposed.
     copy_stream = torch.cuda.Stream(device=dev)
-    in_sets = [[torch.empty_like(t, device=dev) for t in host_imgs] for _ in range(2)]
+    bmax = max(len(ids) for ids in micro)
+    in_sets = [[torch.empty(bmax, *t.shape[1:], device=dev) for t in host_sets[0]] for _ in range(2)]
     ev_ready = [torch.cuda.Event() for _ in range(2)]
     ev_used = [torch.cuda.Event() for _ in range(2)]
     e2e_state = {"i": 0, "primed": False}
 
-    def upload(k):
+    def upload(k, j):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_used[k])            # the step that last read this set has consumed it
-            for d, h in zip(in_sets[k], host_imgs):
-                d.copy_(h, non_blocking=True)
+            for d, h in zip(in_sets[k], host_sets[j]):
+                d[: h.shape[0]].copy_(h, non_blocking=True)
             ev_ready[k].record(copy_stream)
 
     def step_e2e(last=False):
-        k = e2e_state["i"] & 1
-        if not e2e_state["primed"]:
-            upload(k)
-            e2e_state["primed"] = True
-        if not last:
-            upload(k ^ 1)                                  # next step's frames, overlapped with this step's kernels
-        cur = torch.cuda.current_stream()
-        cur.wait_event(ev_ready[k])
-        flows = model(images=in_sets[k], test_mode=False)
-        ev_used[k].record(cur)
-        host_out.copy_(flows[-1], non_blocking=True)
-        e2e_state["i"] += 1
-        if last:
-            e2e_state["primed"] = False
+        nm = len(micro)
+        epes = []
+        for j in range(nm):
+            k = e2e_state["i"] & 1
+            if not e2e_state["primed"]:
+                upload(k, j)
+                e2e_state["primed"] = True
+            final = last and j == nm - 1
+            if not final:
+                upload(k ^ 1, (j + 1) % nm)               # next micro-step's frames, overlapped with this one's kernels
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev_ready[k])
+            nb = len(micro[j])
+            flows = model(images=[t[:nb] for t in in_sets[k]], test_mode=False)
+            ev_used[k].record(cur)
+            host_out[j].copy_(flows[-1], non_blocking=True)
+            epes.append(metrics.clip_epe(flows[-1], dev_sets[j][1], dev_sets[j][2]))
+            e2e_state["i"] += 1
+            if final:
+                e2e_state["primed"] = False
+        host_epe.copy_(epes[0] if nm == 1 else torch.cat(epes), non_blocking=True)
         return flows
 
     def timed(fn, steps, warmup, sampler=None, mark_last=False):
@@ -250,12 +361,19 @@ def run_b200(args):
 
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches, clocks = timed(step_resident, args.steps, args.warmup, sampler)
-    flows_total = FLOWS_PER_CLIP * b * world * args.steps
+    flows_total = FLOWS_PER_CLIP * n_clips * args.steps
     value = flows_total / (ms / 1e3)
     ms_e2e, _, _ = timed(step_e2e, args.steps, 1, mark_last=True)
     e2e_value = flows_total / (ms_e2e / 1e3)
-    h2d = sum(t.numel() * 4 for t in host_imgs)
-    d2h = host_out.numel() * 4
+    h2d = sum(t.numel() * 4 for hs in host_sets for t in hs)
+    d2h = sum(t.numel() * 4 for t in host_out) + host_epe.numel() * 4
+
+    # the benched path's own output (CUDA-graph replay, b clips, seed-2 weights) for the parity leg below
+    bench_flows = model(images=dev_sets[0][0], test_mode=False)
+    bench_epe = metrics.clip_epe(bench_flows[-1], dev_sets[0][1], dev_sets[0][2])
+    torch.cuda.synchronize()
+    ours_clip0 = [f[0:1].float().cpu() for f in bench_flows]
+    ours_epe0 = bench_epe[0].float().cpu()
 
     # ---- roofline of the dominant kernel (implicit-GEMM convolution), measured live ----------
     eng = model.engine(dev)
@@ -280,28 +398,23 @@ def run_b200(args):
              "bf16": "conv_tc_kernel (tcgen05 implicit-GEMM conv, bf16 products)"}[args.precision]
     issued = achieved * {"bf16x3": 6, "fp16x2": 3}.get(args.precision, 1)
     traffic, traffic_note = None, None
-    tnew = os.path.join(ROOT, "profiles", f"r1c_conv_tc_zr_{args.precision}_ncu_full.jsonl")
-    if not os.path.exists(tnew):
-        tnew = os.path.join(ROOT, "profiles", f"r1b_conv_tc_zr_{args.precision}_ncu_full.jsonl")
-    tfile = os.path.join(ROOT, "profiles", f"r1_conv_tc_zr_{args.precision}_ncu_full.json")
-    note = ("dram__bytes_read+write of one GRU z|r conv launch (1x5, 384->256, 8 pairs x 64x64; `ncu --set full`) from "
-            "profiles/{}; algorithmic bytes of that launch ~104 MB (operand planes 50 MB + weights 4 MB + h 17 MB "
-            "read, z 17 MB + r*h planes 17 MB written), part of it served by the 126 MB L2")
-    if os.path.exists(tnew):
-        t = json.loads(open(tnew).readline())
-        traffic = (t["dram_read_MB"] + t["dram_write_MB"]) * 1e6
-        traffic_note = note.format(os.path.basename(tnew))
-    elif os.path.exists(tfile):
-        t = json.load(open(tfile))
-        scale_b = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        traffic = sum(float(t[k]["value"]) * scale_b[t[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        traffic_note = note.format(os.path.basename(tfile))
+    for name in (f"r2_conv_tc_zr_{args.precision}_ncu_full.jsonl", f"r1c_conv_tc_zr_{args.precision}_ncu_full.jsonl",
+                 f"r1b_conv_tc_zr_{args.precision}_ncu_full.jsonl"):
+        tfile = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tfile):
+            t = json.loads(open(tfile).readline())
+            traffic = (t["dram_read_MB"] + t["dram_write_MB"]) * 1e6
+            traffic_note = (f"STATIC, not measured in this run: dram__bytes_read+write of one GRU z|r conv launch (1x5, 8 pairs x "
+                            f"64x64; `ncu --set full`) from profiles/{name}")
+            break
     roofline = {"bound": "tensor", "kernel": kname, "issued_mma_tflops": issued, "issued_frac": issued / pk["bf16_tflops_sustained"],
                 "traffic_note": traffic_note,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_kind": f"bf16 dense sustained, {pk_kind}", "launches": len(prof), "ms_in_step": conv_ms,
                 "share_of_step": conv_ms / prof_step_ms,
                 "share_note": "conv launches / whole step, both CUDA-event timed in one eager (non-graph) step",
+                "flop_note": "FLOPs of the convolutions/GEMMs actually launched (2*MAC); the GRU's constant `inp` term is "
+                             "evaluated once per frame, not once per iteration",
                 "traffic": traffic}
 
     # ---- second metric of BASELINE.json: ms per GRU iteration (lookup + update block), graph-replayed ----
@@ -331,49 +444,86 @@ def run_b200(args):
             took[iters] = a.elapsed_time(z) / 5
         return (took[16] - took[4]) / 12.0
 
-    ms_iter = {"pairs_3 (one clip, first accumulation step)": gru_iter_ms(3),
-               f"pairs_{3 * b} (this bench's batch)": gru_iter_ms(3 * b)} if rank == 0 else None
+    ms_iter = None
+    if rank == 0 and args.size <= 512:
+        ms_iter = {"pairs_3 (one clip, first accumulation step)": gru_iter_ms(3),
+                   f"pairs_{3 * b} (this bench's batch)": gru_iter_ms(3 * b)}
 
     line = None
+    ok = True
     if rank == 0:
         line = {"metric": "long-range flow pairs/sec", "value": value, "unit": "flows/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None,
-                "dtype": {"fp32": "f32", "bf16x3": "bf16x3", "fp16x2": "fp16x2", "bf16": "bf16"}[args.precision], "data": "synthetic",
+                "scaling": "strong" if args.total_clips else "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32"}.get(args.precision, args.precision), "data": "synthetic",
                 "config": workload_config(args, b), "clips_per_s": value / FLOWS_PER_CLIP,
                 "pair_evals_per_s": value / FLOWS_PER_CLIP * 11, "ms_per_gru_iter": ms_iter, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "flows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps,
+                        "note": "frames H2D from pinned memory, last flow + per-clip EPE triplets D2H, metric kernel included"},
                 "gpu_launches": int(launches), "roofline": roofline,
-                "necessary_tflops": NECESSARY_GFLOP_PER_CLIP_512 * (args.size / 512) ** 2 * b * world * args.steps / ms}
+                "hbm_peak_bytes": int(torch.cuda.max_memory_allocated(dev)),
+                "necessary_tflops": NECESSARY_GFLOP_PER_CLIP_512 * (args.size / 512) ** 2 * (args.iters / 12)
+                                    * n_clips * args.steps / ms}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args)
+            line["cpu_baseline"], line["parity"] = cpu_leg(args, ours_clip0, ours_epe0, batches[0])
+            fp32_class = args.precision in ("fp32", "bf16x3", "fp16x2")
+            if fp32_class and not args.warm_start:
+                ok = line["parity"]["max_abs_px"] < FLOW_TOL_PX and line["parity"]["epe_delta_px"] < EPE_TOL_PX
+            line["parity"]["pass"] = bool(ok) if fp32_class else None
+        if world == 1 and not args.no_ref_cuda:
+            del dev_sets, in_sets
+            torch.cuda.empty_cache()
+            rc = ref_cuda_proxy(args, dev, ours_clip0=ours_clip0)
+            line["ref_cuda"] = rc
+            if rc.get("value"):
+                line["ref_cuda"]["speedup_resident"] = value / rc["value"]
+                line["ref_cuda"]["speedup_e2e"] = e2e_value / rc["value"]
+                line["ref_cuda"]["north_star_10x"] = "met" if e2e_value / rc["value"] >= 10 else "missed"
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not ok:
+        sys.exit("parity failure: the benched path's flows differ from the oracle beyond the fp32-class bar")
 
 
-def cpu_baseline(args):
-    """Oracle port timed on the host cores of the GPU box, on a bounded sample of the workload."""
+def cpu_leg(args, ours_clip0, ours_epe0, batch0):
+    """Oracle port on the host cores of the GPU box over ONE whole clip (the bounded sample of the workload): its wall time
+    is the cpu_baseline, its flows are what the benched GPU path (graph replay, full batch) is checked against."""
     from accflow_b200.weights import make_state_dict
     from oracle import flow_oracle as fo
+    from oracle import ops
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = make_state_dict(f"acc+{args.ofe}", seed=2)
-    imgs = make_inputs([0], args.size)["imgs"][:3]          # first accumulation step: 3 pair-evals, 1 flow
+    imgs = [t[0:1] for t in batch0["imgs"]]
     t0 = time.time()
-    fo.accflow_forward(sd, imgs, args.iters)
+    if args.warm_start:
+        ref = fo.accflow_forward(sd, imgs, args.iters, warm_start=True)
+    else:
+        ref = fo.accflow_forward(sd, imgs, args.iters)
     t = time.time() - t0
-    # a full 7-frame clip is 11 pair-evals + 5 accumulation steps; this sample is 3 + 1
-    est_clip = t * (11.0 / 3.0)
-    return {"value": FLOWS_PER_CLIP / est_clip, "unit": "flows/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"first accumulation step of one {args.size}x{args.size} clip (3 of 11 pair-evals, {t:.1f}s), scaled x11/3 to a clip"}
+    bflow, fflow = batch0["bflows"][-1][0:1], batch0["fflows"][-1][0:1]
+    occ, _ = ops.calc_occ_mask(bflow, fflow)
+    e_ref = torch.stack(ops.cal_epe(ref[-1], bflow, occ)).reshape(-1)
+    e_ours_cpu = torch.stack(ops.cal_epe(ours_clip0[-1], bflow, occ)).reshape(-1)
+    parity = {"max_abs_px": max(float((a - b).abs().max()) for a, b in zip(ours_clip0, ref)),
+              "epe_delta_px": float((e_ours_cpu - e_ref).abs().max()),
+              "epe_kernel_vs_oracle_px": float((ours_epe0 - e_ref).abs().max()),
+              "clips_checked": 1, "flows_checked": len(ref), "flow_max_px": float(max(r.abs().max() for r in ref)),
+              "what": "clip 0 of the benched batch: CUDA-graph-replayed flows F(2->0)..F(6->0) vs the CPU oracle (fp32)",
+              "tolerance": {"max_abs_px": FLOW_TOL_PX, "epe_delta_px": EPE_TOL_PX}}
+    base = {"value": FLOWS_PER_CLIP / t, "unit": "flows/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"one whole {FRAMES}-frame {args.size}x{args.size} clip (11 pair-evals, 5 accumulation steps), {t:.1f}s"}
+    return base, parity
 
 
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "reference-cuda":
+        run_reference_cuda(a)
     else:
         run_b200(a)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ACCFLOW_ABI_VERSION 2
+#define ACCFLOW_ABI_VERSION 3
 #if defined(__GNUC__)
 #define ACCFLOW_API __attribute__((visibility("default")))
 #else
@@ -82,6 +82,11 @@ typedef struct accflow_conv_desc {
   float* h;    int h_ld;    /* GRU hidden state (read for ZR, read+written for Q) */
   float* z;    int z_ld;    /* GRU update gate buffer (written by ZR, read by Q) */
   int pool_w;               /* ACCFLOW_EPI_STORE_POOL: width of the target map (multiple of 32) */
+  /* Optional NHWC slice added to acc*alpha*scale + shift BEFORE the activation / gate math (all epilogues).
+   * The GRU convolutions read cat[h, inp, mf] (raft/update.py:45-60) where `inp` is constant over the 12
+   * iterations of raft/raft.py:127: its contribution conv(inp) is evaluated once and passed here, the
+   * per-iteration convolution then contracts over [h, mf] only.  Needs cout % 4 == 0, 16B alignment. */
+  const float* pre_add; int pre_ld;
 } accflow_conv_desc;
 
 ACCFLOW_API int accflow_abi_version(void);

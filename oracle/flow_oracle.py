@@ -190,14 +190,17 @@ def flow_head_generic(sd: SD, pfx: str, x):
     return _conv(sd, pfx + "2", torch.relu(_conv(sd, pfx + "0", x, pad=1)), pad=1)
 
 
-def acc_iter(sd: SD, i1, i2, i_n, f2n, iters: int = 12, trace: Optional[dict] = None):
-    """AccFlow.iter, AccFlow_.py:177-201."""
+def acc_iter(sd: SD, i1, i2, i_n, f2n, iters: int = 12, trace: Optional[dict] = None, flow_init=None):
+    """AccFlow.iter, AccFlow_.py:177-201.  ``flow_init`` (not in the reference's iter; the estimators' own argument,
+    raft/raft.py:123-124) feeds the warm-start mode of accflow_forward."""
     if f2n is None:
         flows = flow_estimator(sd, torch.cat([i1, i1, i2]), torch.cat([i2, i_n, i_n]), iters, pfx="ofe.")
         dflow, flow_ini, f2n = ops.downflow8(flows).chunk(3)
     else:
-        flows = flow_estimator(sd, torch.cat([i1, i1]), torch.cat([i2, i_n]), iters, pfx="ofe.")
+        flows = flow_estimator(sd, torch.cat([i1, i1]), torch.cat([i2, i_n]), iters, flow_init, pfx="ofe.")
         dflow, flow_ini = ops.downflow8(flows).chunk(2)
+    if trace is not None:
+        trace["dflow_small"] = dflow
     b = i1.shape[0]
     enc = flow_encoder(sd, torch.cat([flow_ini, dflow, f2n], 0))
     f_ini, df, f = enc[:b], enc[b:2 * b], enc[2 * b:]
@@ -213,11 +216,23 @@ def acc_iter(sd: SD, i1, i2, i_n, f2n, iters: int = 12, trace: Optional[dict] = 
     return flow_decoder(sd, f_fuse)
 
 
-def accflow_forward(sd: SD, images: List[torch.Tensor], iters: int = 12) -> List[torch.Tensor]:
-    """AccFlow.forward, AccFlow_.py:157-175: [F(2->0), F(3->0), ..., F(n-1->0)]."""
+def accflow_forward(sd: SD, images: List[torch.Tensor], iters: int = 12, warm_start: bool = False,
+                    warm_iters: Optional[int] = None) -> List[torch.Tensor]:
+    """AccFlow.forward, AccFlow_.py:157-175: [F(2->0), F(3->0), ..., F(n-1->0)].
+
+    ``warm_start`` is the mode the reference lists as a TODO (README.md:11) and this repo defines:
+    from the second step on the estimator starts pair (i -> i-1) from the previous step's F(i-1 -> i-2) and pair
+    (i -> 0) from the previous accumulated F(i-1 -> 0), both at 1/8 resolution, for ``warm_iters`` iterations."""
     flow = None
     outs = []
+    prev_dflow = None
     for i in range(2, len(images)):
-        flow, flow_up = acc_iter(sd, images[i], images[i - 1], images[0], flow, iters)
+        tr = {}
+        if warm_start and flow is not None:
+            flow, flow_up = acc_iter(sd, images[i], images[i - 1], images[0], flow, warm_iters or iters, tr,
+                                     flow_init=torch.cat([prev_dflow, flow]))
+        else:
+            flow, flow_up = acc_iter(sd, images[i], images[i - 1], images[0], flow, iters, tr)
+        prev_dflow = tr["dflow_small"]
         outs.append(flow_up)
     return outs
