@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("ACCFLOW_LIB") or os.path.join(HERE, "libaccflow_b200.
 MAX_SRC = 4
 ABI_VERSION = 3
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
-EPI_STORE, EPI_GRU_ZR, EPI_GRU_Q, EPI_STORE_POOL = 0, 1, 2, 3
+EPI_STORE, EPI_GRU_ZR, EPI_GRU_Q, EPI_STORE_POOL, EPI_ROWSTATS, EPI_STORE_T = 0, 1, 2, 3, 4, 5
 
 fp = C.c_void_p  # device pointers travel as integers
 
@@ -31,13 +31,13 @@ class ConvDesc(C.Structure):
         ("residual", fp), ("res_ld", C.c_int), ("post_relu", C.c_int), ("epilogue", C.c_int),
         ("out", fp), ("out_ld", C.c_int), ("out2", fp), ("out2_ld", C.c_int),
         ("h", fp), ("h_ld", C.c_int), ("z", fp), ("z_ld", C.c_int), ("pool_w", C.c_int),
-        ("pre_add", fp), ("pre_ld", C.c_int),
+        ("pre_add", fp), ("pre_ld", C.c_int), ("row_stats", fp),
     ]
 
 
 class TcWeights(C.Structure):
     _fields_ = [("planes", fp), ("nplanes", C.c_int), ("rows", C.c_int), ("k", C.c_int), ("k_pitch", C.c_int),
-                ("t", C.c_int)]
+                ("t", C.c_int), ("plane_stride", C.c_longlong)]
 
 
 class TcIO(C.Structure):
@@ -57,6 +57,8 @@ SIGNATURES = {
     "accflow_conv2d_f32": [C.POINTER(ConvDesc), fp],
     "accflow_conv2d_tc": [C.POINTER(ConvDesc), C.POINTER(TcIO), C.POINTER(TcWeights), i, fp],
     "accflow_tc_debug_trace": [fp, i],
+    "accflow_tc_rowstat_parts": [i, i],
+    "accflow_softmax_stats_finalize": [fp, ll, i, fp, fp],
     "accflow_split_bf16_planes": [fp, ll, i, i, i, i, ll, i, fp, fp],
     "accflow_conv_smallc_f32": [fp, i, i, i, i, i, fp, fp, fp, i, i, i, i, fp, i, fp, i, ll, i, fp],
     "accflow_instnorm_chunks": [i],
@@ -82,7 +84,7 @@ SIGNATURES = {
 }
 _RESTYPE = {"accflow_launch_count": ll, "accflow_launch_count_add": ll}
 _NO_CHECK = {"accflow_abi_version", "accflow_last_error", "accflow_launch_count", "accflow_launch_count_add",
-             "accflow_instnorm_chunks"}
+             "accflow_instnorm_chunks", "accflow_tc_rowstat_parts"}
 
 _lib = None
 

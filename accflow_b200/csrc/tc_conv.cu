@@ -67,6 +67,7 @@ struct Params {
   const float* residual;
   int res_ld, post_relu, epilogue, out_vec;
   const float* pre_add; int pre_ld;         // added before the activation / gate math (hoisted GRU `inp` term)
+  const float* row_stats; float sm_alpha;   // softmax emit pass: value = exp(acc*sm_alpha - max) * inv_sum per row
   float* out; int out_ld;
   float* out2; int out2_ld;
   float* h; int h_ld;
@@ -574,6 +575,62 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       tc_fence_after();
       asm volatile("bar.sync 3, 256;" ::: "memory");             // staged affine visible to both warp sets
       const uint32_t lane_addr = tmem_base + slot * acc_cols + ((uint32_t)(32 * (warp & 3)) << 16);
+      // this thread's own output row (TMEM lane), mode 0 tiles: used by the row-wise epilogues below
+      const int own_oy = oy0 + (trow >> p.tw_shift), own_ox = ox0 + (trow & (p.tw - 1));
+      const bool own_in = own_oy < p.out_h && own_ox < p.out_w;
+      const long long own_pix = ((long long)sample * p.out_h + own_oy) * p.out_w + own_ox;
+      if (p.epilogue == ACCFLOW_EPI_ROWSTATS || p.epilogue == ACCFLOW_EPI_STORE_T) {
+        // Row-wise epilogues straight from registers (no staging panel): softmax partial statistics of
+        // s = acc*alpha over this half tile (gma/modules.py:66-74), or the transposed operand-plane store.
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int c = cbeg; c < cend; c += 16) {
+          float acc[16];
+          if (p.nprod == 1) tmem_ld16(lane_addr + c, acc);
+          if (p.nprod > 1) {
+            float corr[16];
+            tmem_ld16x2(lane_addr + c, lane_addr + BN + c, acc, corr);
+            const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
+          }
+          if (c + 16 >= cend) {                                  // last TMEM read of this tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
+          }
+          if (p.epilogue == ACCFLOW_EPI_ROWSTATS) {
+            float sv[16], mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              sv[j] = (n0 + c + j < p.cout) ? acc[j] * p.alpha : -INFINITY;
+              mx = fmaxf(mx, sv[j]);
+            }
+            if (mx > -INFINITY) {
+              const float m_new = fmaxf(m_run, mx);
+              float sum = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) sum += expf(sv[j] - m_new);
+              l_run = l_run * expf(m_run - m_new) + sum;
+              m_run = m_new;
+            }
+          } else if (own_in) {
+            const long long col0 = (long long)sample * p.cout;
+            const long long pin = (long long)own_oy * p.out_w + own_ox;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = n0 + c + j;
+              if (n < p.cout)
+                store_planes(p.out_pl.ptr + (col0 + n) * p.out_pl.pitch + pin, p.out_pl.plane_stride, NPL,
+                             fmaf(acc[j], s_scale[lt & 1][c + j], s_shift[lt & 1][c + j]));
+            }
+          }
+        }
+        if (p.epilogue == ACCFLOW_EPI_ROWSTATS && own_in)
+          *reinterpret_cast<float2*>(p.out + own_pix * p.out_ld + 2 * (2 * n_tile + half)) = make_float2(m_run, l_run);
+        continue;
+      }
+      float2 sm_stats = make_float2(0.f, 0.f);                    // softmax emit pass: (max, 1/sum) of this thread's row
+      if (p.row_stats && own_in) sm_stats = __ldg(reinterpret_cast<const float2*>(p.row_stats) + own_pix);
       if (p.epilogue == ACCFLOW_EPI_STORE_POOL) {
         // Correlation volume + first pyramid level (raft/corr.py:47-55 and :20-22).  The N axis of the tile is a
         // (BN / w) x w piece of the target map; this warp set owns the x range [half*w/2, (half+1)*w/2) of every
@@ -654,6 +711,10 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;   // fp16x2: lo planes carry 2^11
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
+          }
+          if (p.row_stats) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = expf(fmaf(acc[j], p.sm_alpha, -sm_stats.x)) * sm_stats.y;
           }
           float4* d4 = reinterpret_cast<float4*>(stg + trow * PITCH);
 #pragma unroll
@@ -808,6 +869,22 @@ __global__ void split_planes_vec8_kernel(const float* __restrict__ x, long long 
   }
 }
 
+// partial [rows][parts][2] = (m_k, sum_j exp(s_j - m_k)) -> stats [rows][2] = (max, 1 / sum_j exp(s_j - max))
+__global__ void softmax_stats_finalize_kernel(const float* __restrict__ partial, long long rows, int parts,
+                                              float* __restrict__ stats) {
+  const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (r >= rows) return;
+  const float2* pp = reinterpret_cast<const float2*>(partial) + r * parts;
+  float m = -INFINITY;
+  for (int k = 0; k < parts; ++k) m = fmaxf(m, __ldg(pp + k).x);
+  float l = 0.f;
+  for (int k = 0; k < parts; ++k) {
+    const float2 v = __ldg(pp + k);
+    l += v.y * expf(v.x - m);
+  }
+  reinterpret_cast<float2*>(stats)[r] = make_float2(m, 1.f / l);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -836,6 +913,23 @@ using namespace accflow;
 extern "C" int accflow_tc_debug_trace(long long* host, int n) {
   if (!host || n <= 0 || n > 3 * 1024) return -1;
   return (int)cudaMemcpyFromSymbol(host, tc::g_tc_trace, sizeof(long long) * n);
+}
+
+static int tc_bn_for(int cout, int nprod) {
+  const int bn_cap = nprod == 1 ? 256 : 128;
+  const int ntiles = cdiv(cout, bn_cap);
+  return cdiv(cdiv(cout, ntiles), 32) * 32;
+}
+
+extern "C" int accflow_tc_rowstat_parts(int cout, int nprod) {
+  if (cout <= 0) return 0;
+  return 2 * cdiv(cout, tc_bn_for(cout, nprod));
+}
+
+extern "C" int accflow_softmax_stats_finalize(const float* partial, long long rows, int parts, float* stats, void* stream) {
+  ACCFLOW_REQUIRE(partial && stats && rows > 0 && parts > 0, "softmax_stats_finalize: bad arguments");
+  tc::softmax_stats_finalize_kernel<<<cdiv(rows, 256), 256, 0, (cudaStream_t)stream>>>(partial, rows, parts, stats);
+  return launched("softmax_stats_finalize");
 }
 
 extern "C" int accflow_split_bf16_planes(const float* x, long long rows, int k, int ld, int k_fill, int pitch,
@@ -916,9 +1010,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   p.msub = 1;
   if (const char* e = getenv("ACCFLOW_TC_DEBUG")) p.debug = atoi(e);
   // N tile: multiple of 32; the split modes keep two accumulators (MAIN | CORR) x two TMEM slots (BN <= 128).
-  const int bn_cap = nprod == 1 ? 256 : 128;
-  int ntiles = cdiv(d.cout, bn_cap);
-  int bn = cdiv(cdiv(d.cout, ntiles), 32) * 32;
+  const int bn = tc_bn_for(d.cout, nprod);
   p.bn = bn;
   p.n_tiles = cdiv(d.cout, bn);
   // Narrow N tiles in the shift modes: two 128-pixel sub-tiles per CTA tile share every weight tile (the
@@ -981,8 +1073,23 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
                     "conv2d_tc: STORE_POOL needs a per-sample GEMM whose N tile (%d) covers whole row pairs of the "
                     "pool_w=%d wide map, pool_w %% 32 == 0, 16B-aligned outputs", bn, d.pool_w);
     p.pool_w = d.pool_w;
+  } else if (d.epilogue == ACCFLOW_EPI_ROWSTATS) {
+    ACCFLOW_REQUIRE(p.mode == 0 && d.stride == 1 && d.kh * d.kw == 1 && d.out && (reinterpret_cast<uintptr_t>(d.out) & 7u) == 0 &&
+                        d.out_ld == 2 * accflow_tc_rowstat_parts(d.cout, nprod) && !d.pre_add && !d.residual,
+                    "conv2d_tc: ROWSTATS needs a 1x1 / per-sample GEMM and out_ld == 2 * accflow_tc_rowstat_parts(cout)");
+  } else if (d.epilogue == ACCFLOW_EPI_STORE_T) {
+    ACCFLOW_REQUIRE(p.mode == 0 && d.stride == 1 && d.kh * d.kw == 1 && io.out_planes && !d.out && !d.pre_add && !d.residual &&
+                        d.act == ACCFLOW_ACT_NONE && d.act_split == 0 && io.out_pitch >= p.out_h * p.out_w,
+                    "conv2d_tc: STORE_T needs a 1x1 conv / GEMM, out_planes with pitch >= pixels per sample, no fp32 output");
   } else {
     return fail(-1, "conv2d_tc: unknown epilogue %d", d.epilogue);
+  }
+  if (d.row_stats) {
+    ACCFLOW_REQUIRE(d.epilogue == ACCFLOW_EPI_STORE && p.mode == 0 && d.stride == 1 && d.kh * d.kw == 1 && !d.scale && !d.shift &&
+                        d.act == ACCFLOW_ACT_NONE && d.act_split == 0 && !d.residual && !d.pre_add &&
+                        (reinterpret_cast<uintptr_t>(d.row_stats) & 7u) == 0,
+                    "conv2d_tc: row_stats (softmax emit) needs a plain 1x1 / per-sample GEMM store epilogue");
+    p.row_stats = d.row_stats; p.sm_alpha = d.alpha; p.alpha = 1.0f;
   }
   p.out_vec = d.epilogue == ACCFLOW_EPI_STORE && d.act_split == 0 && aligned16(d.out) && (!d.out || d.out_ld % 4 == 0) &&
               (!d.residual || (aligned16(d.residual) && d.res_ld % 4 == 0));
@@ -1004,7 +1111,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   {
     const cuuint64_t gdim[4] = {(cuuint64_t)w.k, (cuuint64_t)w.rows, (cuuint64_t)w.t, (cuuint64_t)w.nplanes};
     const cuuint64_t gstr[3] = {(cuuint64_t)w.k_pitch * 2, (cuuint64_t)w.k_pitch * 2 * w.rows,
-                                (cuuint64_t)w.k_pitch * 2 * w.rows * w.t};
+                                w.plane_stride ? (cuuint64_t)w.plane_stride * 2 : (cuuint64_t)w.k_pitch * 2 * w.rows * w.t};
     const cuuint32_t box[4] = {(cuuint32_t)tc::KC, (cuuint32_t)bn, 1, (cuuint32_t)nplanes};   // all planes in one op
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult cr = enc(&maps.w, nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w.planes), gdim, gstr, box, estr,

@@ -257,7 +257,8 @@ class Kernels:
              post_relu=False, epilogue=L.EPI_STORE, h: Optional[View] = None, z: Optional[View] = None,
              weight_ptr: Optional[int] = None, weight_batch_stride=0, cout=None, cout_pad=None,
              use_affine=True, tc_b: Optional["L.TcWeights"] = None, tc_src_planes=None, planes_only=False,
-             emit_planes=True, pool_w=0, pre_add: Optional[View] = None):
+             emit_planes=True, pool_w=0, pre_add: Optional[View] = None, row_stats: Optional[torch.Tensor] = None,
+             tc_out_planes=None):
         """``planes_only``: the output (``out``; ``out2`` for the GRU z|r epilogue) is read by tensor-core
         convolutions only, so in the tensor-core modes its fp32 copy is not written (half the store bytes).
         ``emit_planes=False``: the next reader is not a tensor-core conv (InstanceNorm), so no planes are written.
@@ -296,13 +297,15 @@ class Kernels:
         if pre_add is not None:
             assert pre_add.c == d.cout and pre_add.b == s0.b
             d.pre_add, d.pre_ld = pre_add.ptr, pre_add.ld
+        if row_stats is not None:
+            d.row_stats = row_stats.data_ptr()
         if tc:
             io = L.TcIO()
             for k, sv in enumerate(srcs):
                 io.src_planes[k], io.src_pitch[k], io.src_plane_stride[k] = (
                     tc_src_planes[k] if tc_src_planes is not None else self.ensure_planes(sv))
             written = []
-            if epilogue == L.EPI_STORE_POOL:
+            if epilogue in (L.EPI_STORE_POOL, L.EPI_ROWSTATS, L.EPI_STORE_T):
                 targets = ()
             elif epilogue == L.EPI_STORE:
                 targets = (("out", out), ("out2", out2 if act_split else None))
@@ -326,6 +329,8 @@ class Kernels:
                     d.out = None
                 elif epilogue == L.EPI_GRU_ZR and written[0] is out2:
                     d.out2 = None
+            if tc_out_planes is not None:          # caller-owned destination planes (no fp32 twin tensor)
+                io.out_planes, io.out_pitch, io.out_plane_stride = tc_out_planes
             tw = tc_b if tc_b is not None else pc.tc_weights(self.precision == "fp16x2")
             args = ("accflow_conv2d_tc", C.byref(d), C.byref(io), C.byref(tw), self.NPROD[self.precision], _stream())
         else:
@@ -775,16 +780,63 @@ class FlowEstimatorEngine:
         return lv
 
     def attention(self, inp: View, tag: str):
-        """Attention.forward (gma/modules.py:54-76), heads=1, content only."""
+        """Attention.forward (gma/modules.py:54-76), heads=1, content only -> softmax(q k^T * scale).
+
+        Tensor-core modes: the logits are never materialised.  Pass 1 runs q k^T and keeps only per-row running
+        (max, sum exp) partials (EPI_ROWSTATS); pass 2 re-runs the GEMM (K = 128: cheaper than one more pass over
+        the P x P matrix) and writes exp(s - max) / sum straight into 16-bit operand planes — the A operand of the
+        per-iteration aggregation.  No fp32 matrix, no softmax pass, no plane-split pass.  Returns
+        ("planes", ptr, pitch, plane_stride); the exact-fp32 mode returns ("f32", tensor)."""
         k = self.k
         B, h, w = inp.b, inp.h, inp.w
         P = h * w
         qk = k.view(tag + ".qk", B, h, w, 256)
-        k.conv(self.to_qk, [inp], qk)
-        attn = k.buf(tag + ".attn", B, P, P)
-        k.gemm_nt(tag + ".att", qk.ch(0, 128), qk.ch(128, 256), View(attn.view(B, h, w, P)), alpha=self.qk_scale)
-        k.softmax_rows(attn, B * P, P)
-        return attn
+        if not k.tc:
+            k.conv(self.to_qk, [inp], qk)
+            attn = k.buf(tag + ".attn", B, P, P)
+            k.gemm_nt(tag + ".att", qk.ch(0, 128), qk.ch(128, 256), View(attn.view(B, h, w, P)), alpha=self.qk_scale)
+            k.softmax_rows(attn, B * P, P)
+            return ("f32", attn)
+        k.planes_ptr(qk, create=True)
+        k.conv(self.to_qk, [inp], qk, planes_only=True)                  # q | k feed the GEMM only
+        qp, cp, pstride = k.planes_ptr(qk, create=False)
+        npl = k.nplanes
+        kw = L.TcWeights(qp + 2 * 128, npl, P, 128, cp, B, pstride)      # B operand = the k half of the same planes
+        qsrc = [(qp, cp, pstride)]
+        parts = L.call("accflow_tc_rowstat_parts", P, k.NPROD[k.precision])
+        partial = k.buf(tag + ".att_part", B * P, 2 * parts)
+        stats = k.buf(tag + ".att_stats", B * P, 2)
+        g = _Gemm(128, P, P)
+        k.conv(g, [PlanesOnly(B, h, w, 128, cp)], View(partial.view(B, h, w, 2 * parts)), alpha=self.qk_scale,
+               weight_batch_stride=1, use_affine=False, tc_b=kw, tc_src_planes=qsrc, epilogue=L.EPI_ROWSTATS, cout=P)
+        L.call("accflow_softmax_stats_finalize", partial.data_ptr(), B * P, parts, stats.data_ptr(), _stream())
+        Pp = (P + 7) // 8 * 8
+        attn_pl = k.buf16(tag + ".attn_pl", npl, B, P, Pp)
+        dst = (attn_pl.data_ptr(), Pp, B * P * Pp)
+        k.conv(g, [PlanesOnly(B, h, w, 128, cp)], None, alpha=self.qk_scale, weight_batch_stride=1, use_affine=False,
+               tc_b=kw, tc_src_planes=qsrc, row_stats=stats, tc_out_planes=dst)
+        return ("planes",) + dst
+
+    def aggregate(self, attn, mf: View, mfg: View, tag: str):
+        """Aggregate.forward (gma/modules.py:102-115): mfg = mf + gamma * (attn @ to_v(mf)).  Tensor-core modes: the
+        to_v conv writes v transposed into operand planes (EPI_STORE_T), the aggregation GEMM reads the attention
+        planes of ``attention`` through TMA and adds the gamma-scaled result onto ``mf`` in its epilogue."""
+        k = self.k
+        B, h, w = mf.b, mf.h, mf.w
+        P = h * w
+        if attn[0] == "f32":
+            vbuf = k.view(tag + ".v", B, h, w, 128)
+            k.conv(self.to_v, [mf], vbuf)
+            k.gemm_nn(tag + ".agg", View(attn[1].view(B, h, w, P)), vbuf, mfg, alpha=self.gamma, residual=mf)
+            return
+        _, ap, apitch, astride = attn
+        npl = k.nplanes
+        Pp = (P + 7) // 8 * 8
+        vt = k.buf16(tag + ".vT", npl, B, 128, Pp)
+        k.conv(self.to_v, [mf], None, epilogue=L.EPI_STORE_T, tc_out_planes=(vt.data_ptr(), Pp, B * 128 * Pp))
+        tw = L.TcWeights(vt.data_ptr(), npl, 128, P, Pp, B, 0)
+        k.conv(_Gemm(P, 128, 128), [PlanesOnly(B, h, w, P, apitch)], mfg, alpha=self.gamma, weight_batch_stride=1,
+               residual=mf, use_affine=False, tc_b=tw, tc_src_planes=[(ap, apitch, astride)], planes_only=True)
 
     def iterate(self, st, iters: int, flow_init: Optional[torch.Tensor], tag="fe") -> torch.Tensor:
         """The GRU refinement loop + final convex upsample (raft/raft.py:121-146)."""
@@ -806,7 +858,6 @@ class FlowEstimatorEngine:
         delta = k.view(tag + ".delta", B, h, w, 2)
         x_srcs = [mf]                      # `inp` enters through st["gru_pre"]
         if self.gma:
-            vbuf = k.view(tag + ".v", B, h, w, 128)
             mfg = k.view(tag + ".mfg", B, h, w, 128)
             x_srcs = [mf, mfg]
         if flow_init is not None:
@@ -822,9 +873,7 @@ class FlowEstimatorEngine:
             k.conv(self.convf2, [flo1], cf.ch(192, 256), act=L.ACT_RELU, planes_only=True)
             k.conv(self.convm, [cf], mf.ch(0, 126), act=L.ACT_RELU, planes_only=not self.gma)
             if self.gma:
-                # Aggregate.forward (gma/modules.py:102-115): mf + gamma * (attn @ to_v(mf))
-                k.conv(self.to_v, [mf], vbuf)
-                k.gemm_nn(tag + ".agg", View(st["attn"].view(B, h, w, P)), vbuf, mfg, alpha=self.gamma, residual=mf)
+                self.aggregate(st["attn"], mf, mfg, tag)
             for (zr, q), (pre_zr, pre_q) in zip(self.gru, st["gru_pre"]):
                 k.conv(zr, [hid] + x_srcs, epilogue=L.EPI_GRU_ZR, h=hid, z=z, out2=rh, planes_only=True, pre_add=pre_zr)
                 k.conv(q, [rh] + x_srcs, epilogue=L.EPI_GRU_Q, h=hid, z=z, pre_add=pre_q)

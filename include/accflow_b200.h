@@ -45,7 +45,17 @@ enum {
   /* tensor-core per-sample GEMM only: out = acc*alpha (the correlation volume, raft/corr.py:47-55) and
    * out2 = 2x2 mean over the N axis viewed as a row-major map of width pool_w (first avg_pool2d of the
    * pyramid, raft/corr.py:20-22); out2 row stride = out2_ld. */
-  ACCFLOW_EPI_STORE_POOL = 3
+  ACCFLOW_EPI_STORE_POOL = 3,
+  /* tensor-core kernel only.  Softmax over the N axis without materialising the logits (GMA Attention.forward,
+   * gma/modules.py:66-74): per output row and per (N tile, half tile) the running maximum m and sum exp(s - m) of
+   * s = acc*alpha go to out[row*out_ld + 2*part .. +1]; out_ld = 2 * accflow_tc_rowstat_parts(cout, nprod).
+   * accflow_softmax_stats_finalize merges the parts into (max, 1/sum) per row; a second launch of the same GEMM with
+   * EPI_STORE and `row_stats` set then writes softmax(s) = exp(s - max) / sum straight into operand planes. */
+  ACCFLOW_EPI_ROWSTATS = 4,
+  /* tensor-core kernel only, 1x1 / per-sample GEMM: the result is written TRANSPOSED into operand planes
+   * out_planes[plane][(sample*cout + n)*pitch + pixel] (K-major B operand of a following per-sample GEMM whose K axis
+   * is the pixel index: v of Aggregate.forward, gma/modules.py:105-108).  No fp32 output. */
+  ACCFLOW_EPI_STORE_T = 5
 };
 
 #define ACCFLOW_MAX_SRC 4
@@ -87,6 +97,9 @@ typedef struct accflow_conv_desc {
    * iterations of raft/raft.py:127: its contribution conv(inp) is evaluated once and passed here, the
    * per-iteration convolution then contracts over [h, mf] only.  Needs cout % 4 == 0, 16B alignment. */
   const float* pre_add; int pre_ld;
+  /* EPI_STORE on the tensor-core kernel: per-row (max, 1/sum) pairs [batch*out_h*out_w][2]; when set the stored value
+   * is exp(acc*alpha - max) * (1/sum) (softmax emit pass, see ACCFLOW_EPI_ROWSTATS); scale/shift/act must be unset. */
+  const float* row_stats;
 } accflow_conv_desc;
 
 ACCFLOW_API int accflow_abi_version(void);
@@ -111,6 +124,7 @@ typedef struct accflow_tc_weights {
   int k;              /* logical K per t (sum of source channels) */
   int k_pitch;        /* elements between rows, multiple of 8 */
   int t;              /* taps or samples */
+  long long plane_stride; /* elements between planes; 0 = dense (t*rows*k_pitch) */
 } accflow_tc_weights;
 
 /* bf16 planes that travel next to the fp32 activations (x = p0 + p1 + p2): element (plane, pixel,
@@ -136,6 +150,11 @@ typedef struct accflow_tc_io {
  * operands inside the fp16 range). */
 ACCFLOW_API int accflow_conv2d_tc(const accflow_conv_desc* d, const accflow_tc_io* io, const accflow_tc_weights* w,
                                   int nprod, void* stream);
+
+/* Number of (N tile, half tile) partial results per row that ACCFLOW_EPI_ROWSTATS writes for `cout` columns. */
+ACCFLOW_API int accflow_tc_rowstat_parts(int cout, int nprod);
+/* partial [rows][parts][2] (m, sum exp(s-m)) -> stats [rows][2] = (max, 1/sum) (softmax over the whole row). */
+ACCFLOW_API int accflow_softmax_stats_finalize(const float* partial, long long rows, int parts, float* stats, void* stream);
 
 /* Perf experiments: with ACCFLOW_TC_DEBUG bit 4 set, accflow_conv2d_tc records clock64 stamps of CTA 0's MMA-issuing
  * thread (3 per weight tile: barriers passed, last MMA issued, commit issued; first 1024 tiles); this copies n of them. */

@@ -299,6 +299,54 @@ def test_corr_volume_with_fused_first_level(hw):
             assert maxdiff(lv[l].reshape(ref[l].shape), ref[l]) < tol * 4, (prec, l)
 
 
+@pytest.mark.parametrize("hw", [(16, 16), (17, 16), (24, 40)])
+def test_gma_attention_and_aggregate(KP, hw):
+    """Attention.forward + Aggregate.forward (gma/modules.py:54-76, 102-115) at kernel level, every arithmetic mode:
+    tensor-core modes take the fused path (row statistics pass, softmax written once as operand planes, transposed
+    v planes, aggregation GEMM with the gamma-residual epilogue); ragged P (17x16 = 272 columns) covers the masked
+    tail of the last N tile."""
+    K, tol = KP
+    from accflow_b200.engine import FlowEstimatorEngine, PackedConv, View
+    from oracle import flow_oracle as fo
+    h, w = hw
+    B = 2
+    g = torch.Generator().manual_seed(51)
+    inp = torch.relu(torch.randn(B, 128, h, w, generator=g))
+    mf = torch.randn(B, 128, h, w, generator=g)
+    sd = {"att.to_qk.weight": torch.randn(256, 128, 1, 1, generator=g) * 0.35,
+          "agg.to_v.weight": torch.randn(128, 128, 1, 1, generator=g) * 0.1, "agg.gamma": torch.tensor([0.5])}
+    attn_ref = fo.gma_attention(sd, "att.", inp)
+    ref = fo.gma_aggregate(sd, "agg.", attn_ref, mf)
+    assert float(attn_ref.max()) > 0.05                      # a peaked softmax, not a uniform one
+    eng = FlowEstimatorEngine.__new__(FlowEstimatorEngine)
+    eng.k, eng.gma = K, True
+    eng.to_qk = PackedConv([dev(sd["att.to_qk.weight"])], [None], 1, (0, 0))
+    eng.to_v = PackedConv([dev(sd["agg.to_v.weight"])], [None], 1, (0, 0))
+    eng.gamma, eng.qk_scale = 0.5, 128 ** -0.5
+    inpv, mfv = View(dev(nhwc(inp))), View(dev(nhwc(mf)))
+    out = View(torch.zeros(B, h, w, 128, device="cuda"))
+    for _ in range(2):                                       # second pass: plane buffers exist (planes-only outputs)
+        attn = eng.attention(inpv, f"tatt{h}x{w}")
+        eng.aggregate(attn, mfv, out, f"tatt{h}x{w}")
+    torch.cuda.synchronize()
+    P = h * w
+    if attn[0] == "planes":
+        _, ptr, pitch, pstride = attn
+        pl = K._ws[(f"tatt{h}x{w}.attn_pl", "bf16", K.nplanes, B, P, (P + 7) // 8 * 8)]
+        if K.precision == "fp16x2":
+            got = pl.view(torch.float16)[0].float() + pl.view(torch.float16)[1].float() / 2048.0
+        else:
+            got = pl.float().sum(0)
+        assert maxdiff(got[:, :, :P], attn_ref) < tol
+        got_out = K._planes[out.t.data_ptr()]
+        rec = (got_out.view(torch.float16)[0].float() + got_out.view(torch.float16)[1].float() / 2048.0
+               if K.precision == "fp16x2" else got_out.float().sum(0))
+        assert maxdiff(rec[..., :128].permute(0, 3, 1, 2), ref) < tol * 4
+    else:
+        assert maxdiff(attn[1], attn_ref) < tol
+        assert maxdiff(out.t.permute(0, 3, 1, 2), ref) < tol * 4
+
+
 def test_convex_upsample(golden):
     from accflow_b200 import ops as P
     g, _ = golden
