@@ -69,6 +69,7 @@ __device__ __forceinline__ float grid_roundtrip(float x, int size) {
 // 16-bit operand planes written next to an fp32 value for the tensor-core convolutions.
 //   nplanes = 1 : bf16(x)                                   ("bf16" mode)
 //   nplanes = 3 : bf16 p0 + p1 + p2 = x (24 mantissa bits)   ("bf16x3" mode, 6 products)
+//   nplanes = 4 : ONE plane fp16(x) ("fp16" mode: single fp16 products, the reference's autocast class)
 //   nplanes = 2 : fp16 hi = fp16(x), lo = fp16((x - hi) * 2^11)  ("fp16x2" mode, 3 products);
 //                 the lo plane is pre-scaled so it never underflows; the kernel multiplies the
 //                 cross-term accumulator by 2^-11.
@@ -76,8 +77,15 @@ __device__ __forceinline__ float grid_roundtrip(float x, int size) {
 //                 degrades to a clipped value instead of hi = inf, lo = -inf -> NaN through the whole recurrence.
 #define ACCFLOW_FP16X2_SCALE 2048.0f
 #define ACCFLOW_FP16_MAX 65504.0f
+#define ACCFLOW_PLANES_FP16 4   /* plane-format code: one fp16 plane */
+inline bool valid_plane_fmt(int n) { return n >= 1 && n <= 4; }
+inline int plane_count(int fmt) { return fmt == ACCFLOW_PLANES_FP16 ? 1 : fmt; }
 __device__ __forceinline__ float sat_fp16(float v) { return fminf(fmaxf(v, -ACCFLOW_FP16_MAX), ACCFLOW_FP16_MAX); }
 __device__ __forceinline__ void store_planes(__nv_bfloat16* dst, long long plane_stride, int nplanes, float v) {
+  if (nplanes == ACCFLOW_PLANES_FP16) {
+    *reinterpret_cast<__half*>(dst) = __float2half_rn(sat_fp16(v));
+    return;
+  }
   if (nplanes == 2) {
     v = sat_fp16(v);
     __half* d = reinterpret_cast<__half*>(dst);
@@ -102,6 +110,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 // 4 consecutive channels (8-byte aligned destination) into the operand planes: one 8-byte store per plane.
 __device__ __forceinline__ void store_planes4_at(__nv_bfloat16* base, long long plane_stride, int nplanes, const float* yin) {
+  if (nplanes == ACCFLOW_PLANES_FP16) {
+    const __half2 h01 = __floats2half2_rn(sat_fp16(yin[0]), sat_fp16(yin[1])), h23 = __floats2half2_rn(sat_fp16(yin[2]), sat_fp16(yin[3]));
+    *reinterpret_cast<uint2*>(base) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    return;
+  }
   if (nplanes == 2) {   // fp16 hi + pre-scaled fp16 lo
     const float y[4] = {sat_fp16(yin[0]), sat_fp16(yin[1]), sat_fp16(yin[2]), sat_fp16(yin[3])};
     const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);

@@ -472,7 +472,14 @@ __global__ void __launch_bounds__(256) stem_patch_kernel(const float* __restrict
   }
   __nv_bfloat16* dst = out_pl + pix * pitch + k0;
   uint32_t p0[4], p1[4], p2[4];
-  if (nplanes == 2) {
+  if (nplanes == ACCFLOW_PLANES_FP16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 hi = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+      p0[e] = *reinterpret_cast<const uint32_t*>(&hi);
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+  } else if (nplanes == 2) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const __half2 hi = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
@@ -718,8 +725,8 @@ extern "C" int accflow_flow_patch_f32(const float* flow, int batch, int h, int w
                                       int pl_pitch, long long pl_stride, int nplanes, void* stream) {
   ACCFLOW_REQUIRE(flow && (out || out_planes) && batch > 0 && h > 0 && w > 0 && out_ld >= 98 && out_ld % 2 == 0,
                   "flow_patch: bad arguments (out_ld even and >= 98; fp32 out and/or planes)");
-  ACCFLOW_REQUIRE(!out_planes || (nplanes >= 1 && nplanes <= 3 && pl_pitch % 2 == 0 && pl_stride % 2 == 0),
-                  "flow_patch: nplanes must be 1, 2 or 3, even plane pitch");
+  ACCFLOW_REQUIRE(!out_planes || (valid_plane_fmt(nplanes) && pl_pitch % 2 == 0 && pl_stride % 2 == 0),
+                  "flow_patch: bad plane format, or odd plane pitch");
   const long long total = (long long)batch * h * w * (out_ld / 2);
   flow_patch_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(flow, batch, h, w, out, out_ld,
                                                                         reinterpret_cast<__nv_bfloat16*>(out_planes),
@@ -730,7 +737,7 @@ extern "C" int accflow_flow_patch_f32(const float* flow, int batch, int h, int w
 extern "C" int accflow_stem_patch_planes(const float* img_nchw, int batch, int H, int W, void* out_planes, int pitch,
                                          long long pl_stride, int nplanes, void* stream) {
   ACCFLOW_REQUIRE(img_nchw && out_planes && batch > 0 && H > 0 && W > 0, "stem_patch: bad arguments");
-  ACCFLOW_REQUIRE(pitch >= 148 && pitch % 8 == 0 && pl_stride % 8 == 0 && nplanes >= 1 && nplanes <= 3 &&
+  ACCFLOW_REQUIRE(pitch >= 148 && pitch % 8 == 0 && pl_stride % 8 == 0 && valid_plane_fmt(nplanes) &&
                       aligned16(out_planes), "stem_patch: pitch must be >= 148 and a multiple of 8, planes 16B aligned");
   const long long total = (long long)batch * ((H + 1) / 2) * ((W + 1) / 2) * (pitch / 8);
   stem_patch_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(img_nchw, batch, H, W,

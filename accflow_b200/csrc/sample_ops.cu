@@ -695,7 +695,7 @@ extern "C" int accflow_instnorm_planes_f32(const float* x, int batch, int hw, in
                                            float* stats, void* out_planes, int pl_pitch, long long pl_stride, int nplanes,
                                            void* stream) {
   ACCFLOW_REQUIRE(x && (out || out_planes) && partial && stats, "instnorm: null pointer");
-  ACCFLOW_REQUIRE(!out_planes || (nplanes >= 1 && nplanes <= 3 && pl_pitch % 4 == 0 && pl_pitch >= c && pl_stride % 4 == 0 &&
+  ACCFLOW_REQUIRE(!out_planes || (valid_plane_fmt(nplanes) && pl_pitch % 4 == 0 && pl_pitch >= c && pl_stride % 4 == 0 &&
                                   (reinterpret_cast<uintptr_t>(out_planes) & 7u) == 0),
                   "instnorm: planes must be 8B aligned, pitch %% 4 == 0, nplanes 1..3");
   ACCFLOW_REQUIRE(batch > 0 && hw > 0 && c > 0 && c <= 256 && c % 4 == 0, "instnorm: bad shape b=%d hw=%d c=%d", batch, hw, c);
@@ -753,7 +753,7 @@ extern "C" int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, con
   for (int l = 0; l < 4; ++l) { p.lh[l] = hh; p.lw[l] = ww; hh >>= 1; ww >>= 1; }
   p.batch = batch; p.h = h; p.w = w; p.radius = radius; p.coords = coords;
   p.out = out; p.out_ld = out_ld; p.flow_out = flow_out; p.mf_tail = mf_tail; p.mf_ld = mf_ld;
-  ACCFLOW_REQUIRE((!out_planes && !tail_planes) || (nplanes >= 1 && nplanes <= 3), "corr_lookup: nplanes must be 1, 2 or 3");
+  ACCFLOW_REQUIRE((!out_planes && !tail_planes) || valid_plane_fmt(nplanes), "corr_lookup: bad plane format");
   p.out_pl = reinterpret_cast<__nv_bfloat16*>(out_planes); p.pl_pitch = pl_pitch; p.pl_stride = pl_stride; p.nplanes = nplanes;
   p.tail_pl = reinterpret_cast<__nv_bfloat16*>(tail_planes); p.tail_pitch = tail_pitch; p.tail_stride = tail_stride;
   if (radius == 4) corr_lookup_fast_kernel<4><<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(p);     // RAFT / GMA

@@ -48,6 +48,7 @@ struct Params {
   int n_tiles;                              // cout tiles
   int per_sample;                           // weights' T coordinate = sample instead of tap
   int cout, bn, nplanes, nprod, stages;
+  int plane_fmt, fp16;                      // format code of emitted planes (common.cuh); fp16 operands (else bf16)
   // Operand rings of conv_tc_kernel.  A (activations) and W (weights) are staged independently so one
   // activation box can serve several filter taps ("shift" modes):
   //   mode 0: one box per tap (strided convs, 1x1, per-sample GEMMs), pixels row-major in the tile.
@@ -239,6 +240,12 @@ __device__ __forceinline__ void store_planes1(const PlaneOut& po, int nplanes, l
   store_planes(po.ptr + pix * po.pitch + n, po.plane_stride, nplanes, y);
 }
 
+// Gate math of the GRU epilogues (raft/update.py:47-58): sigmoid / tanh through ex2.approx + rcp (about 8 instructions
+// instead of ~40 for expf + IEEE division / tanhf).  Absolute error <= ~3e-7 for |x| <= 20 (the multiply by log2(e)
+// rounds the exponent argument to ~1e-6 relative; d(sigmoid)/dx <= 1/4), saturating correctly at +-inf.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - 2.f * __frcp_rn(1.f + __expf(2.f * x)); }
+
 // ---------------------------------------------------------------------------------- MMA issue loop
 // One thread issues every tcgen05.mma of the CTA, so its instruction count per weight tile is on the
 // critical path (measured: with TMA and epilogue disabled the old loop still ran at 2.2x the tensor time).
@@ -247,7 +254,7 @@ __device__ __forceinline__ void store_planes1(const PlaneOut& po, int nplanes, l
 // products share one instruction: the weight planes w0 | w1 are contiguous in shared memory and the
 // MAIN | CORR accumulators are contiguous in TMEM, so  a0 x [w0; w1]  is a single N = 2*BN MMA.
 struct MmaCtx {
-  int total_tiles, stride_tiles, first_tile, nchunks, n_inner, SA, SB, BN, a_stage, b_stage, debug, msub, sub_cols;
+  int total_tiles, stride_tiles, first_tile, nchunks, n_inner, SA, SB, BN, a_stage, b_stage, debug, msub, sub_cols, fp16;
   uint32_t a_plane16, w_plane16, smem_a, smem_b, tmem_base, acc_cols;
   uint64_t *afull, *afree, *bfull, *bfree, *acc_full, *acc_empty;
 };
@@ -262,8 +269,8 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0
 
 template <int NPROD, int MSUB>
 __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
-  const uint32_t idesc1 = make_idesc(BM, c.BN, NPROD == 3);
-  const uint32_t idesc2 = make_idesc(BM, 2 * c.BN, NPROD == 3);      // a0 x [w0; w1] -> MAIN | CORR
+  const uint32_t idesc1 = make_idesc(BM, c.BN, c.fp16 != 0);
+  const uint32_t idesc2 = make_idesc(BM, 2 * c.BN, c.fp16 != 0);      // a0 x [w0; w1] -> MAIN | CORR
   const bool comb = c.n_inner == 1;        // operands share the weight ring's barriers (SA == SB, slots advance together)
   int sa = 0, sb = 0, ntr = 0;
   bool next_ready = false, a_ready = false;
@@ -537,6 +544,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       c.a_stage = a_stage; c.b_stage = b_stage; c.a_plane16 = a_plane_bytes >> 4; c.w_plane16 = w_plane_bytes >> 4;
       c.smem_a = smem_u32(smem); c.smem_b = smem_u32(smem_b);
       c.tmem_base = tmem_base; c.acc_cols = acc_cols; c.debug = p.debug; c.msub = p.msub; c.sub_cols = sub_cols;
+      c.fp16 = p.fp16;
       c.afull = bar_afull; c.afree = bar_afree; c.bfull = bar_bfull; c.bfree = bar_bfree;
       c.acc_full = bar_acc_full; c.acc_empty = bar_acc_empty;
       if (p.nprod == 3) { if (p.msub == 2) mma_issue_loop<3, 2>(c); else mma_issue_loop<3, 1>(c); }
@@ -620,7 +628,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             for (int j = 0; j < 16; ++j) {
               const int n = n0 + c + j;
               if (n < p.cout)
-                store_planes(p.out_pl.ptr + (col0 + n) * p.out_pl.pitch + pin, p.out_pl.plane_stride, NPL,
+                store_planes(p.out_pl.ptr + (col0 + n) * p.out_pl.pitch + pin, p.out_pl.plane_stride, p.plane_fmt,
                              fmaf(acc[j], s_scale[lt & 1][c + j], s_shift[lt & 1][c + j]));
             }
           }
@@ -697,112 +705,137 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         }
         continue;
       }
-      for (int sub = 0; sub < p.msub; ++sub)
-      for (int c = cbeg; c < cend; c += 16) {
-        {
-          float acc[16];
-          if (p.debug & 8) {
+      for (int sub = 0; sub < p.msub; ++sub) {
+        // the four output rows this thread finishes per 16-column step (phase 2): fixed over the steps of a sub-tile
+        long long pix4[4];
+        bool rok[4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-          } else if (p.nprod == 1) tmem_ld16(lane_addr + sub * sub_cols + c, acc);
-          if (p.nprod > 1 && !(p.debug & 8)) {
-            float corr[16];
-            tmem_ld16x2(lane_addr + sub * sub_cols + c, lane_addr + sub * sub_cols + BN + c, acc, corr);
-            const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;   // fp16x2: lo planes carry 2^11
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
-          }
-          if (p.row_stats) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = expf(fmaf(acc[j], p.sm_alpha, -sm_stats.x)) * sm_stats.y;
-          }
-          float4* d4 = reinterpret_cast<float4*>(stg + trow * PITCH);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) d4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        for (int itr = 0; itr < 4; ++itr) {
+          const int row = 32 * (warp & 3) + itr * 8 + (lane >> 2);
+          const int r_slow = (row >> p.tw_shift) + 16 * sub, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
+          const int oy = oy0 + (p.mode == 2 ? r_fast : r_slow), ox = ox0 + (p.mode == 2 ? r_slow : r_fast);
+          rok[itr] = oy < p.out_h && ox < p.out_w;
+          pix4[itr] = ((long long)sample * p.out_h + oy) * p.out_w + ox;
         }
-        if (c + 16 >= cend && sub == p.msub - 1) {   // last TMEM read of this tile: hand the slot back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
-        }
-        __syncwarp();                         // the panel rows this warp reads back are the ones it staged
-        const int nb = n0 + c + pc4 * 4;
-        if (nb < p.cout && !(p.debug & 4)) {
-          const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
-          const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[lt & 1][c + pc4 * 4]);
-          const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+        for (int c = cbeg; c < cend; c += 16) {
+          const int nb = n0 + c + pc4 * 4;
+          const bool active = nb < p.cout && !(p.debug & 4);
           const bool vec4 = nb + 3 < p.cout;
-#pragma unroll 2
+          // Global reads of this step (hoisted GRU term, h, z, residual) are issued BEFORE the TMEM load / staging /
+          // warp sync below, all four rows at once: their latency overlaps phase 1 instead of being paid once per row
+          // inside the math (the GRU epilogues were bound by exactly that: 2 exposed L2/DRAM round trips per step).
+          float4 ga[4], gb[4], gc[4];
+          const int hd = p.cout >> 1;
+          const bool want_pre = active && p.pre_add != nullptr;
+          const bool zr_r = p.epilogue == ACCFLOW_EPI_GRU_ZR && nb >= hd;
+          const bool want_b = active && (zr_r || p.epilogue == ACCFLOW_EPI_GRU_Q ||
+                                         (p.epilogue == ACCFLOW_EPI_STORE && p.residual && p.out_vec && vec4));
+          const bool want_c = active && p.epilogue == ACCFLOW_EPI_GRU_Q;
+#pragma unroll
           for (int itr = 0; itr < 4; ++itr) {
-            const int row = 32 * (warp & 3) + itr * 8 + (lane >> 2);
-            const int r_slow = (row >> p.tw_shift) + 16 * sub, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
-            const int oy = oy0 + (p.mode == 2 ? r_fast : r_slow), ox = ox0 + (p.mode == 2 ? r_slow : r_fast);
-            if (oy >= p.out_h || ox >= p.out_w) continue;
-            const long long pix = ((long long)sample * p.out_h + oy) * p.out_w + ox;
-            const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
-            float y[4] = {fmaf(a4.x, sc[0], sh[0]), fmaf(a4.y, sc[1], sh[1]), fmaf(a4.z, sc[2], sh[2]), fmaf(a4.w, sc[3], sh[3])};
-            if (p.pre_add) {
-              const float4 pa = __ldg(reinterpret_cast<const float4*>(p.pre_add + pix * p.pre_ld + nb));
-              y[0] += pa.x; y[1] += pa.y; y[2] += pa.z; y[3] += pa.w;
+            ga[itr] = gb[itr] = gc[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!rok[itr]) continue;
+            if (want_pre) ga[itr] = __ldg(reinterpret_cast<const float4*>(p.pre_add + pix4[itr] * p.pre_ld + nb));
+            if (want_b) {
+              const float* src = p.epilogue == ACCFLOW_EPI_STORE ? p.residual + pix4[itr] * p.res_ld + nb
+                                 : p.h + pix4[itr] * p.h_ld + (zr_r ? nb - hd : nb);
+              gb[itr] = *reinterpret_cast<const float4*>(src);
             }
-            if (p.epilogue == ACCFLOW_EPI_STORE) {
-              if (p.out_vec && vec4) {
+            if (want_c) gc[itr] = __ldg(reinterpret_cast<const float4*>(p.z + pix4[itr] * p.z_ld + nb));
+          }
+          {
+            float acc[16];
+            if (p.debug & 8) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) y[j] = act_apply(y[j], p.act);
-                if (p.residual) {
-                  const float4 r = *reinterpret_cast<const float4*>(p.residual + pix * p.res_ld + nb);
-                  y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
-                }
-                if (p.post_relu) {
+              for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+            } else if (p.nprod == 1) tmem_ld16(lane_addr + sub * sub_cols + c, acc);
+            if (p.nprod > 1 && !(p.debug & 8)) {
+              float corr[16];
+              tmem_ld16x2(lane_addr + sub * sub_cols + c, lane_addr + sub * sub_cols + BN + c, acc, corr);
+              const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;   // fp16x2: lo planes carry 2^11
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
-                }
-                if (p.out) *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
-                if (p.out_pl.ptr) store_planes4(p.out_pl, NPL, pix, nb, y);
-              } else {
+              for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
+            }
+            if (p.row_stats) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int n = nb + j;
-                  if (n < p.cout) {
-                    const bool second = p.act_split > 0 && n >= p.act_split;
-                    float o = act_apply(y[j], second ? p.act2 : p.act);
-                    if (p.residual) o += p.residual[pix * p.res_ld + n];
-                    if (p.post_relu) o = fmaxf(o, 0.f);
-                    if (second && p.out2) {
-                      p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
-                      if (p.out2_pl.ptr) store_planes1(p.out2_pl, NPL, pix, n - p.act_split, o);
-                    } else {
-                      if (p.out) p.out[pix * p.out_ld + n] = o;
-                      if (p.out_pl.ptr) store_planes1(p.out_pl, NPL, pix, n, o);
+              for (int j = 0; j < 16; ++j) acc[j] = expf(fmaf(acc[j], p.sm_alpha, -sm_stats.x)) * sm_stats.y;
+            }
+            float4* d4 = reinterpret_cast<float4*>(stg + trow * PITCH);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          }
+          if (c + 16 >= cend && sub == p.msub - 1) {   // last TMEM read of this tile: hand the slot back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
+          }
+          __syncwarp();                         // the panel rows this warp reads back are the ones it staged
+          if (active) {
+            const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
+            const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[lt & 1][c + pc4 * 4]);
+            const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+#pragma unroll
+            for (int itr = 0; itr < 4; ++itr) {
+              if (!rok[itr]) continue;
+              const int row = 32 * (warp & 3) + itr * 8 + (lane >> 2);
+              const long long pix = pix4[itr];
+              const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
+              float y[4] = {fmaf(a4.x, sc[0], sh[0]) + ga[itr].x, fmaf(a4.y, sc[1], sh[1]) + ga[itr].y,
+                            fmaf(a4.z, sc[2], sh[2]) + ga[itr].z, fmaf(a4.w, sc[3], sh[3]) + ga[itr].w};
+              if (p.epilogue == ACCFLOW_EPI_STORE) {
+                if (p.out_vec && vec4) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) y[j] = act_apply(y[j], p.act);
+                  if (p.residual) { y[0] += gb[itr].x; y[1] += gb[itr].y; y[2] += gb[itr].z; y[3] += gb[itr].w; }
+                  if (p.post_relu) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
+                  }
+                  if (p.out) *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
+                  if (p.out_pl.ptr) store_planes4(p.out_pl, p.plane_fmt, pix, nb, y);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const int n = nb + j;
+                    if (n < p.cout) {
+                      const bool second = p.act_split > 0 && n >= p.act_split;
+                      float o = act_apply(y[j], second ? p.act2 : p.act);
+                      if (p.residual) o += p.residual[pix * p.res_ld + n];
+                      if (p.post_relu) o = fmaxf(o, 0.f);
+                      if (second && p.out2) {
+                        p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
+                        if (p.out2_pl.ptr) store_planes1(p.out2_pl, p.plane_fmt, pix, n - p.act_split, o);
+                      } else {
+                        if (p.out) p.out[pix * p.out_ld + n] = o;
+                        if (p.out_pl.ptr) store_planes1(p.out_pl, p.plane_fmt, pix, n, o);
+                      }
                     }
                   }
                 }
-              }
-            } else if (p.epilogue == ACCFLOW_EPI_GRU_ZR) {
-              const int hd = p.cout >> 1;   // multiple of 4 (checked on the host): a group never straddles z | r
-              float g4[4];
+              } else if (p.epilogue == ACCFLOW_EPI_GRU_ZR) {
+                // hd is a multiple of 4 (checked on the host): a group never straddles z | r
+                float g4[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) g4[j] = 1.f / (1.f + expf(-y[j]));
-              if (nb < hd) {
-                *reinterpret_cast<float4*>(p.z + pix * p.z_ld + nb) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+                for (int j = 0; j < 4; ++j) g4[j] = sigmoid_fast(y[j]);
+                if (nb < hd) {
+                  *reinterpret_cast<float4*>(p.z + pix * p.z_ld + nb) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+                } else {
+                  const int n = nb - hd;
+                  float o[4] = {g4[0] * gb[itr].x, g4[1] * gb[itr].y, g4[2] * gb[itr].z, g4[3] * gb[itr].w};
+                  if (p.out2) *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
+                  if (p.out2_pl.ptr) store_planes4(p.out2_pl, p.plane_fmt, pix, n, o);
+                }
               } else {
-                const int n = nb - hd;
-                const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + n);
-                float o[4] = {g4[0] * hh.x, g4[1] * hh.y, g4[2] * hh.z, g4[3] * hh.w};
-                if (p.out2) *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
-                if (p.out2_pl.ptr) store_planes4(p.out2_pl, NPL, pix, n, o);
+                const float4 zz = gc[itr], hh = gb[itr];
+                float o[4] = {fmaf(zz.x, tanh_fast(y[0]) - hh.x, hh.x), fmaf(zz.y, tanh_fast(y[1]) - hh.y, hh.y),
+                              fmaf(zz.z, tanh_fast(y[2]) - hh.z, hh.z), fmaf(zz.w, tanh_fast(y[3]) - hh.w, hh.w)};
+                *reinterpret_cast<float4*>(p.h + pix * p.h_ld + nb) = make_float4(o[0], o[1], o[2], o[3]);
+                if (p.h_pl.ptr) store_planes4(p.h_pl, p.plane_fmt, pix, nb, o);
               }
-            } else {
-              const float4 zz = *reinterpret_cast<const float4*>(p.z + pix * p.z_ld + nb);
-              const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + nb);
-              float o[4] = {(1.f - zz.x) * hh.x + zz.x * tanhf(y[0]), (1.f - zz.y) * hh.y + zz.y * tanhf(y[1]),
-                            (1.f - zz.z) * hh.z + zz.z * tanhf(y[2]), (1.f - zz.w) * hh.w + zz.w * tanhf(y[3])};
-              *reinterpret_cast<float4*>(p.h + pix * p.h_ld + nb) = make_float4(o[0], o[1], o[2], o[3]);
-              if (p.h_pl.ptr) store_planes4(p.h_pl, NPL, pix, nb, o);
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   }
@@ -837,6 +870,15 @@ __global__ void split_planes_vec8_kernel(const float* __restrict__ x, long long 
   float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
   __nv_bfloat16* dst = out + r * pitch + c;
   uint32_t p0[4], p1[4], p2[4];
+  if (nplanes == ACCFLOW_PLANES_FP16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 hi = __floats2half2_rn(sat_fp16(v[2 * e]), sat_fp16(v[2 * e + 1]));
+      p0[e] = *reinterpret_cast<const uint32_t*>(&hi);
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+    return;
+  }
   if (nplanes == 2) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = sat_fp16(v[e]);
@@ -916,7 +958,7 @@ extern "C" int accflow_tc_debug_trace(long long* host, int n) {
 }
 
 static int tc_bn_for(int cout, int nprod) {
-  const int bn_cap = nprod == 1 ? 256 : 128;
+  const int bn_cap = nprod <= 2 ? 256 : 128;          // single-product modes (1 = bf16, 2 = fp16): one accumulator
   const int ntiles = cdiv(cout, bn_cap);
   return cdiv(cdiv(cout, ntiles), 32) * 32;
 }
@@ -936,7 +978,7 @@ extern "C" int accflow_split_bf16_planes(const float* x, long long rows, int k, 
                                          long long plane_stride, int nplanes, void* out_planes, void* stream) {
   ACCFLOW_REQUIRE(x && out_planes && rows > 0 && k > 0 && ld >= k && k_fill >= k && pitch >= k_fill,
                   "split_bf16_planes: bad arguments");
-  ACCFLOW_REQUIRE(nplanes >= 1 && nplanes <= 3, "split_bf16_planes: nplanes must be 1 (bf16), 2 (fp16x2) or 3 (bf16x3)");
+  ACCFLOW_REQUIRE(valid_plane_fmt(nplanes), "split_bf16_planes: plane format must be 1 (bf16), 2 (fp16x2), 3 (bf16x3) or 4 (fp16)");
   if (k == k_fill && k % 8 == 0 && ld % 4 == 0 && pitch % 8 == 0 && plane_stride % 8 == 0 && aligned16(x) &&
       aligned16(out_planes)) {
     tc::split_planes_vec8_kernel<<<cdiv(rows * (k / 8), 256), 256, 0, (cudaStream_t)stream>>>(
@@ -949,12 +991,17 @@ extern "C" int accflow_split_bf16_planes(const float* x, long long rows, int k, 
 }
 
 extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_io* iop, const accflow_tc_weights* wp,
-                                 int nprod, void* stream) {
+                                 int nprod_in, void* stream) {
+  int nprod = nprod_in;
   ACCFLOW_REQUIRE(dp && wp && iop, "conv2d_tc: null descriptor");
   const accflow_conv_desc& d = *dp;
   const accflow_tc_weights& w = *wp;
   const accflow_tc_io& io = *iop;
-  ACCFLOW_REQUIRE(nprod == 1 || nprod == 3 || nprod == 6, "conv2d_tc: nprod must be 1 (bf16), 3 (fp16x2 split) or 6 (bf16x3 split)");
+  ACCFLOW_REQUIRE(nprod == 1 || nprod == 2 || nprod == 3 || nprod == 6,
+                  "conv2d_tc: nprod must be 1 (bf16), 2 (fp16), 3 (fp16x2 split) or 6 (bf16x3 split)");
+  const bool fp16_single = nprod == 2;      // one fp16 product per MAC: same instruction stream as bf16, fp16 operands
+  const bool fp16_ops = nprod == 2 || nprod == 3;
+  if (fp16_single) nprod = 1;
   ACCFLOW_REQUIRE(w.planes && aligned16(w.planes) && w.nplanes >= (nprod == 1 ? 1 : nprod == 3 ? 2 : 3), "conv2d_tc: weight planes missing");
   ACCFLOW_REQUIRE(w.k_pitch % 8 == 0 && w.k_pitch >= w.k && w.rows > 0 && w.t > 0, "conv2d_tc: bad weight geometry");
   ACCFLOW_REQUIRE(d.nsrc >= 1 && d.nsrc <= ACCFLOW_MAX_SRC, "conv2d_tc: nsrc=%d out of range", d.nsrc);
@@ -990,6 +1037,8 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   p.cout = d.cout;
   p.nprod = nprod;
   p.nplanes = nplanes;
+  p.plane_fmt = fp16_single ? ACCFLOW_PLANES_FP16 : nplanes;
+  p.fp16 = fp16_ops;
   const int m_tiles_all = p.tiles_x * p.tiles_y * d.batch;
   // Shift modes (see Params): stride-1 multi-tap convs load each activation box once per K block and
   // serve kh (mode 1) or kw (mode 2) taps from it.  ACCFLOW_TC_SHIFT=0 forces one box per tap.
@@ -1114,7 +1163,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
                                 w.plane_stride ? (cuuint64_t)w.plane_stride * 2 : (cuuint64_t)w.k_pitch * 2 * w.rows * w.t};
     const cuuint32_t box[4] = {(cuuint32_t)tc::KC, (cuuint32_t)bn, 1, (cuuint32_t)nplanes};   // all planes in one op
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult cr = enc(&maps.w, nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w.planes), gdim, gstr, box, estr,
+    CUresult cr = enc(&maps.w, fp16_ops ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w.planes), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ACCFLOW_REQUIRE(cr == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(weights) failed (%d)", (int)cr);
@@ -1132,12 +1181,12 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
       gstr[0] = pitchb * d.in_w; gstr[1] = pitchb;
     }
     const cuuint32_t estr[5] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1, 1};
-    CUresult cr = enc(&maps.a[s], nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(io.src_planes[s]), gdim, gstr, box,
+    CUresult cr = enc(&maps.a[s], fp16_ops ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(io.src_planes[s]), gdim, gstr, box,
                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS && p.mode == 2) {   // driver refuses the permuted strides: horizontal convs go one box per tap
       tc::mode2_rejected = true;
-      return accflow_conv2d_tc(dp, iop, wp, nprod, stream);
+      return accflow_conv2d_tc(dp, iop, wp, fp16_single ? 2 : nprod, stream);
     }
     ACCFLOW_REQUIRE(cr == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(source %d) failed (%d)", s, (int)cr);
   }

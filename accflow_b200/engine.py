@@ -122,8 +122,9 @@ class PackedConv:
             self._astaps = pc
         return self._astaps
 
-    def tc_weights(self, fp16x2: bool = False) -> "L.TcWeights":
-        """16-bit operand planes [planes][taps][cout][k_pitch] for accflow_conv2d_tc."""
+    def tc_weights(self, fp16x2=False) -> "L.TcWeights":
+        """16-bit operand planes [planes][taps][cout][k_pitch] for accflow_conv2d_tc; ``fp16x2``: False = bf16 planes,
+        True = fp16 hi + scaled lo, "fp16" = one fp16 plane."""
         if self._tc is None:
             self._tc = {}
         if fp16x2 not in self._tc:
@@ -140,6 +141,8 @@ class PackedConv:
 def split_planes_torch(x: torch.Tensor, fp16x2: bool = False) -> torch.Tensor:
     """x (fp32) -> stacked 16-bit planes (one-off weight packing): bf16 p0, p1, p2 with x ~= p0 + p1 + p2,
     or fp16 (hi, lo * 2^11) when ``fp16x2``."""
+    if fp16x2 == "fp16":
+        return x.clamp(-65504.0, 65504.0).to(torch.float16)[None].contiguous()
     if fp16x2:
         x = x.clamp(-65504.0, 65504.0)           # same saturation as the device-side split (common.cuh sat_fp16)
         hi = x.to(torch.float16)
@@ -155,9 +158,10 @@ def split_planes_torch(x: torch.Tensor, fp16x2: bool = False) -> torch.Tensor:
 class Kernels:
     """Thin typed wrappers over the C ABI.  One instance per device."""
 
-    MODES = ("fp32", "bf16x3", "fp16x2", "bf16")
-    NPROD = {"bf16x3": 6, "fp16x2": 3, "bf16": 1}
-    NPLANES = {"bf16x3": 3, "fp16x2": 2, "bf16": 1, "fp32": 0}
+    MODES = ("fp32", "bf16x3", "fp16x2", "bf16", "fp16")
+    NPROD = {"bf16x3": 6, "fp16x2": 3, "bf16": 1, "fp16": 2}           # accflow_conv2d_tc's nprod codes
+    NPLANES = {"bf16x3": 3, "fp16x2": 2, "bf16": 1, "fp16": 1, "fp32": 0}
+    PLANE_FMT = {"bf16x3": 3, "fp16x2": 2, "bf16": 1, "fp16": 4, "fp32": 0}     # format codes of include/accflow_b200.h
 
     def __init__(self, device: torch.device, precision: str = "fp32"):
         assert precision in self.MODES, precision
@@ -191,7 +195,13 @@ class Kernels:
 
     @property
     def nplanes(self) -> int:
+        """Number of 16-bit planes per operand (allocation, strides)."""
         return self.NPLANES[self.precision]
+
+    @property
+    def plane_fmt(self) -> int:
+        """Plane format code handed to every kernel that writes operand planes."""
+        return self.PLANE_FMT[self.precision]
 
     def wrote(self, v: Optional[View]):
         """A non-tensor-core kernel wrote ``v``: its planes (if any exist) are stale."""
@@ -239,7 +249,7 @@ class Kernels:
             r0, r1 = rng
             rows = v.t.shape[0] * v.h * v.w
             L.call("accflow_split_bf16_planes", v.t.data_ptr() + 4 * r0, rows, r1 - r0, v.ld, r1 - r0, cp, stride,
-                   self.nplanes, self._planes[key].data_ptr() + 2 * r0, _stream())
+                   self.plane_fmt, self._planes[key].data_ptr() + 2 * r0, _stream())
             st.remove(rng)
         return ptr, cp, stride
 
@@ -331,7 +341,8 @@ class Kernels:
                     d.out2 = None
             if tc_out_planes is not None:          # caller-owned destination planes (no fp32 twin tensor)
                 io.out_planes, io.out_pitch, io.out_plane_stride = tc_out_planes
-            tw = tc_b if tc_b is not None else pc.tc_weights(self.precision == "fp16x2")
+            tw = tc_b if tc_b is not None else pc.tc_weights(
+                {"fp16x2": True, "fp16": "fp16"}.get(self.precision, False))
             args = ("accflow_conv2d_tc", C.byref(d), C.byref(io), C.byref(tw), self.NPROD[self.precision], _stream())
         else:
             args = ("accflow_conv2d_f32", C.byref(d), _stream())
@@ -364,7 +375,7 @@ class Kernels:
         pl = self._out_planes(out)
         L.call("accflow_conv_smallc_f32", x_ptr, int(nchw), batch, cin, h, w, pc.w.data_ptr(),
                None if pc.scale is None else pc.scale.data_ptr(), pc.shift.data_ptr(), pc.kh, pc.stride, pc.cout,
-               act, out.ptr, out.ld, pl[0], pl[1], pl[2], self.nplanes, _stream())
+               act, out.ptr, out.ld, pl[0], pl[1], pl[2], self.plane_fmt, _stream())
         self._done(out, pl[0] is not None)
 
     def flow_conv7(self, tag: str, flow: torch.Tensor, batch: int, h: int, w: int, pc: PackedConv, out: View,
@@ -376,7 +387,7 @@ class Kernels:
         patch = self.view(tag + ".fpatch", batch, h, w, 104)
         pl = self.planes_ptr(patch, create=True)
         L.call("accflow_flow_patch_f32", flow.data_ptr(), batch, h, w, None, patch.ld, pl[0], pl[1], pl[2],
-               self.nplanes, _stream())          # planes only: nothing reads the fp32 patch
+               self.plane_fmt, _stream())          # planes only: nothing reads the fp32 patch
         self._stale[patch.t.data_ptr()] = []
         self.conv(pc.as_1x1(), [patch.ch(0, 98)], out, act=L.ACT_RELU, planes_only=planes_only)
 
@@ -408,7 +419,7 @@ class Kernels:
         out_f32 = None if (planes_only and pl[0] is not None) else out.ptr      # convc1 reads the planes only
         L.call("accflow_corr_lookup_f32", lv[0].data_ptr(), lv[1].data_ptr(), lv[2].data_ptr(), lv[3].data_ptr(),
                out.b, out.h, out.w, radius, coords.data_ptr(), out_f32, out.ld, flow.data_ptr(), mf_tail.ptr, mf_tail.ld,
-               pl[0], pl[1], pl[2], tl[0], tl[1], tl[2], self.nplanes, _stream())
+               pl[0], pl[1], pl[2], tl[0], tl[1], tl[2], self.plane_fmt, _stream())
         self._done(out, pl[0] is not None)
         self._done(mf_tail, tl[0] is not None)
 
@@ -431,7 +442,7 @@ class Kernels:
             return
         L.call("accflow_instnorm_planes_f32", x.ptr, x.b, hw, x.c, eps, int(relu),
                None if residual is None else residual.ptr, int(post_relu), None if planes_only else out.ptr,
-               partial.data_ptr(), stats.data_ptr(), pl[0], pl[1], pl[2], self.nplanes, _stream())
+               partial.data_ptr(), stats.data_ptr(), pl[0], pl[1], pl[2], self.plane_fmt, _stream())
         self._fresh(out)
 
     def gemm_nt(self, tag: str, a: View, b: View, out: View, alpha=1.0, pool_out: Optional[torch.Tensor] = None,
@@ -450,7 +461,7 @@ class Kernels:
         npl = self.nplanes
         pitch = (K + 7) // 8 * 8
         planes = self.buf16(tag + ".bpl", npl, B, N, pitch)
-        L.call("accflow_split_bf16_planes", b.ptr, B * N, K, b.ld, K, pitch, B * N * pitch, npl, planes.data_ptr(),
+        L.call("accflow_split_bf16_planes", b.ptr, B * N, K, b.ld, K, pitch, B * N * pitch, self.plane_fmt, planes.data_ptr(),
                _stream())
         tw = L.TcWeights(planes.data_ptr(), npl, N, K, pitch, B)
         if pool_out is not None:      # fused first pyramid level (ACCFLOW_EPI_STORE_POOL)
@@ -474,7 +485,7 @@ class Kernels:
         bt = self.buf(tag + ".bt", B, N, Kp, zero=True)
         self.transpose(b, bt, Kp)
         planes = self.buf16(tag + ".bpl", npl, B, N, Kp)
-        L.call("accflow_split_bf16_planes", bt.data_ptr(), B * N, K, Kp, K, Kp, B * N * Kp, npl, planes.data_ptr(),
+        L.call("accflow_split_bf16_planes", bt.data_ptr(), B * N, K, Kp, K, Kp, B * N * Kp, self.plane_fmt, planes.data_ptr(),
                _stream())
         tw = L.TcWeights(planes.data_ptr(), npl, N, K, Kp, B)
         self.conv(_Gemm(K, N, N), [a], out, alpha=alpha, weight_batch_stride=1, residual=residual, use_affine=False,
@@ -589,7 +600,7 @@ class EncoderPlan:
             assert im.dtype == F32 and im.is_contiguous() and im.shape[1] == 3
             nb = int(im.shape[0])
             L.call("accflow_stem_patch_planes", im.data_ptr(), nb, H, W,
-                   patches.data_ptr() + 2 * b0 * h2 * w2 * pitch, pitch, stride_pl, k.nplanes, _stream())
+                   patches.data_ptr() + 2 * b0 * h2 * w2 * pitch, pitch, stride_pl, k.plane_fmt, _stream())
             b0 += nb
         return patches.data_ptr(), pitch, stride_pl, 2 * h2 * w2 * pitch
 

@@ -59,7 +59,7 @@ def main(argv: Optional[Sequence[str]] = None):
     ap.add_argument("--size", type=int, default=None, help="synthetic clip size (default ACCFLOW_CVO_SIZE or 512)")
     ap.add_argument("--clips", type=int, default=None, help="number of synthetic clips (default ACCFLOW_CVO_CLIPS or 20)")
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--precision", default=None, choices=["fp32", "bf16x3", "fp16x2", "bf16"])
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16x3", "fp16x2", "bf16", "fp16"])
     ap.add_argument("--warm-start", action="store_true")
     ap.add_argument("--out-dir", default=".")
     args = ap.parse_args(argv)

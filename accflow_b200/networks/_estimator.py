@@ -29,7 +29,8 @@ class FlowEstimatorBase(nn.Module):
         #   "fp16x2" tcgen05, every operand split into fp16 hi + scaled fp16 lo, 3 products: fp32-class
         #            precision inside the fp16 range (the range of the reference's own autocast default)
         #   "bf16x3" tcgen05, three bf16 planes, 6 products: fp32-class precision, fp32 range
-        #   "fp32"   FFMA kernels, exact;   "bf16" tcgen05, plain bf16 products (autocast class)
+        #   "fp32"   FFMA kernels, exact;   "bf16" / "fp16" tcgen05, one bf16 / fp16 product per MAC (the latter is the
+        #            arithmetic class of the reference's default, fp16 autocast)
         self.precision = os.environ.get("ACCFLOW_PRECISION", "fp16x2")
         # replay whole forwards as CUDA graphs (captured on the third call per input shape)
         self.use_cuda_graph = os.environ.get("ACCFLOW_GRAPH", "1") != "0"

@@ -127,6 +127,8 @@ typedef struct accflow_tc_weights {
   long long plane_stride; /* elements between planes; 0 = dense (t*rows*k_pitch) */
 } accflow_tc_weights;
 
+/* Plane FORMAT codes (the `nplanes` argument of every function that writes operand planes):
+ *   1 = one bf16 plane; 2 = fp16 hi + fp16 lo*2^11 (two planes); 3 = three bf16 planes; 4 = one fp16 plane. */
 /* bf16 planes that travel next to the fp32 activations (x = p0 + p1 + p2): element (plane, pixel,
  * channel) of a slice lives at planes[plane*plane_stride + pixel*pitch + channel].  Sources are
  * mandatory (the tensor cores read only planes); the planes of the outputs are optional and
@@ -145,7 +147,8 @@ typedef struct accflow_tc_io {
 /* Same contract as accflow_conv2d_f32 (the descriptor's fp32 `src` pointers, `weight` and
  * `cout_pad` are ignored) on the 5th-gen tensor cores: tcgen05.mma with TMEM accumulators, both
  * operands by TMA (im2col boxes with zero fill for the activations).
- * nprod = 1: bf16 products (1 plane); nprod = 6: bf16x3 split products (3 bf16 planes, fp32-class);
+ * nprod = 1: bf16 products (1 plane); nprod = 2: fp16 products (1 fp16 plane: the arithmetic class of the reference's
+ * fp16 autocast default, networks/__init__.py:8); nprod = 6: bf16x3 split products (3 bf16 planes, fp32-class);
  * nprod = 3: fp16x2 split products (2 fp16 planes: hi, and lo pre-scaled by 2^11; fp32-class for
  * operands inside the fp16 range). */
 ACCFLOW_API int accflow_conv2d_tc(const accflow_conv_desc* d, const accflow_tc_io* io, const accflow_tc_weights* w,
