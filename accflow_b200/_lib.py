@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
         ("residual", fp), ("res_ld", C.c_int), ("post_relu", C.c_int), ("epilogue", C.c_int),
         ("out", fp), ("out_ld", C.c_int), ("out2", fp), ("out2_ld", C.c_int),
         ("h", fp), ("h_ld", C.c_int), ("z", fp), ("z_ld", C.c_int), ("pool_w", C.c_int),
-        ("pre_add", fp), ("pre_ld", C.c_int), ("row_stats", fp),
+        ("pre_add", fp), ("pre_ld", C.c_int), ("row_stats", fp), ("out_h", C.c_int), ("out_w", C.c_int),
     ]
 
 
@@ -68,6 +68,7 @@ SIGNATURES = {
     "accflow_corr_pool_f32": [fp, ll, i, i, fp, fp, fp, fp],
     "accflow_corr_lookup_f32": [fp, fp, fp, fp, i, i, i, i, fp, fp, i, fp, fp, i, fp, i, ll, fp, i, ll, i, fp],
     "accflow_stem_patch_planes": [fp, i, i, i, fp, i, ll, i, fp],
+    "accflow_stem_rows_planes": [fp, i, i, i, fp, i, ll, i, fp],
     "accflow_flow_patch_f32": [fp, i, i, i, fp, i, fp, i, ll, i, fp],
     "accflow_conv3x3_smallcout_f32": [fp, i, i, i, i, i, fp, fp, fp, i, i, fp, i, fp],
     "accflow_coords_init_f32": [fp, i, i, i, fp, fp],

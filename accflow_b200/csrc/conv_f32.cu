@@ -440,37 +440,8 @@ __global__ void __launch_bounds__(256) stem7x7_kernel(const float* __restrict__ 
   }
 }
 
-// ---- 7x7 / stride-2 stem patches: NCHW image [N,3,H,W] -> operand planes [planes][N][H/2][W/2][pitch] with
-// channel k = (ky*7+kx)*3 + c = image(c, 2y-3+ky, 2x-3+kx) (zero outside, zero for k >= 147).  The stem conv
-// (raft/extractor.py:163-167) then runs as a K=147 1x1 conv on the tensor-core kernel.  Planes only (no fp32
-// copy): one thread writes two consecutive channels (32-bit stores).
-__global__ void __launch_bounds__(256) stem_patch_kernel(const float* __restrict__ img, int batch, int H, int W,
-                                                         __nv_bfloat16* __restrict__ out_pl, int pitch,
-                                                         long long pl_stride, int nplanes) {
-  const int oh = (H + 1) / 2, ow = (W + 1) / 2;
-  const int kg = pitch >> 3;                                    // 8-channel groups per pixel (19 for pitch 152)
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long total = (long long)batch * oh * ow * kg;
-  if (i >= total) return;
-  const long long pix = i / kg;
-  const int k0 = (int)(i - pix * kg) * 8;
-  const int b = (int)(pix / ((long long)oh * ow));
-  const int r = (int)(pix - (long long)b * oh * ow);
-  const int oy = r / ow, ox = r - oy * ow;
-  const float* ib = img + (long long)b * 3 * H * W;
-  float v[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int k = k0 + e;
-    v[e] = 0.f;
-    if (k < 147) {
-      const int tap = k / 3, c = k - tap * 3;
-      const int ky = tap / 7, kx = tap - ky * 7;
-      const int iy = 2 * oy - 3 + ky, ix = 2 * ox - 3 + kx;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[e] = __ldg(ib + ((long long)c * H + iy) * W + ix);
-    }
-  }
-  __nv_bfloat16* dst = out_pl + pix * pitch + k0;
+// 8 consecutive channels (16-byte aligned destination) of one pixel into the operand planes (format codes: common.cuh).
+__device__ __forceinline__ void write8_planes(__nv_bfloat16* dst, long long pl_stride, int nplanes, const float* v) {
   uint32_t p0[4], p1[4], p2[4];
   if (nplanes == ACCFLOW_PLANES_FP16) {
 #pragma unroll
@@ -507,6 +478,69 @@ __global__ void __launch_bounds__(256) stem_patch_kernel(const float* __restrict
       *reinterpret_cast<uint4*>(dst + 2 * pl_stride) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
     }
   }
+}
+
+// ---- 7x7 / stride-2 stem as a 4-tap vertical convolution.  With u = ky + 1 = 2*ty + dy and v = kx + 1 = 2*tx + dx
+// (u = 0 / v = 0 are zero taps) the stem conv of raft/extractor.py:163-167 reads x[c][2*(Y + ty - 2) + dy][2*(X + tx - 2) + dx]:
+// a 4x4 stride-1 filter over the 2x2 space-to-depth image.  The four x taps are folded into channels here,
+//   out[n][Y][X][tx*12 + c*4 + dy*2 + dx] = x[n][c][2*Y + dy][2*(X + tx - 2) + dx]      (48 channels, zero outside),
+// and the four y taps are served from one activation box by the tensor-core kernel's shift mode (kh = 4, pad 2, output
+// clipped to H/2 rows).  96 B per pixel and plane instead of the 304 B of the full 147-channel im2col.
+__global__ void __launch_bounds__(256) stem_rows_kernel(const float* __restrict__ img, int batch, int H, int W,
+                                                        __nv_bfloat16* __restrict__ out_pl, int pitch, long long pl_stride,
+                                                        int nplanes) {
+  const int oh = H / 2, ow = W / 2;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)batch * oh * ow * 6;      // 6 groups of 8 channels per pixel
+  if (i >= total) return;
+  const long long pix = i / 6;
+  const int g = (int)(i - pix * 6);
+  const int b = (int)(pix / ((long long)oh * ow));
+  const int r = (int)(pix - (long long)b * oh * ow);
+  const int oy = r / ow, ox = r - oy * ow;
+  const float* ib = img + (long long)b * 3 * H * W;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = 8 * g + e;                                   // k = tx*12 + c*4 + dy*2 + dx
+    const int tx = k / 12, rem = k - tx * 12, c = rem >> 2, dy = (rem >> 1) & 1, dx = rem & 1;
+    const int iy = 2 * oy + dy, ix = 2 * (ox + tx - 2) + dx;
+    v[e] = (ix >= 0 && ix < W) ? __ldg(ib + ((long long)c * H + iy) * W + ix) : 0.f;
+  }
+  write8_planes(out_pl + pix * pitch + 8 * g, pl_stride, nplanes, v);
+}
+
+// ---- 7x7 / stride-2 stem patches: NCHW image [N,3,H,W] -> operand planes [planes][N][H/2][W/2][pitch] with
+// channel k = (ky*7+kx)*3 + c = image(c, 2y-3+ky, 2x-3+kx) (zero outside, zero for k >= 147).  The stem conv
+// (raft/extractor.py:163-167) then runs as a K=147 1x1 conv on the tensor-core kernel.  Planes only (no fp32
+// copy): one thread writes two consecutive channels (32-bit stores).
+__global__ void __launch_bounds__(256) stem_patch_kernel(const float* __restrict__ img, int batch, int H, int W,
+                                                         __nv_bfloat16* __restrict__ out_pl, int pitch,
+                                                         long long pl_stride, int nplanes) {
+  const int oh = (H + 1) / 2, ow = (W + 1) / 2;
+  const int kg = pitch >> 3;                                    // 8-channel groups per pixel (19 for pitch 152)
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)batch * oh * ow * kg;
+  if (i >= total) return;
+  const long long pix = i / kg;
+  const int k0 = (int)(i - pix * kg) * 8;
+  const int b = (int)(pix / ((long long)oh * ow));
+  const int r = (int)(pix - (long long)b * oh * ow);
+  const int oy = r / ow, ox = r - oy * ow;
+  const float* ib = img + (long long)b * 3 * H * W;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = k0 + e;
+    v[e] = 0.f;
+    if (k < 147) {
+      const int tap = k / 3, c = k - tap * 3;
+      const int ky = tap / 7, kx = tap - ky * 7;
+      const int iy = 2 * oy - 3 + ky, ix = 2 * ox - 3 + kx;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[e] = __ldg(ib + ((long long)c * H + iy) * W + ix);
+    }
+  }
+  write8_planes(out_pl + pix * pitch + k0, pl_stride, nplanes, v);
 }
 
 // ---- 7x7 flow patches: flow [B,h,w,2] -> [B,h,w,ld] with channel (ky*7+kx)*2 + c = flow(y+ky-3, x+kx-3, c),
@@ -732,6 +766,18 @@ extern "C" int accflow_flow_patch_f32(const float* flow, int batch, int h, int w
                                                                         reinterpret_cast<__nv_bfloat16*>(out_planes),
                                                                         pl_pitch, pl_stride, nplanes);
   return launched("flow_patch");
+}
+
+extern "C" int accflow_stem_rows_planes(const float* img_nchw, int batch, int H, int W, void* out_planes, int pitch,
+                                        long long pl_stride, int nplanes, void* stream) {
+  ACCFLOW_REQUIRE(img_nchw && out_planes && batch > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "stem_rows: bad arguments");
+  ACCFLOW_REQUIRE(pitch >= 48 && pitch % 8 == 0 && pl_stride % 8 == 0 && valid_plane_fmt(nplanes) && aligned16(out_planes),
+                  "stem_rows: pitch must be >= 48 and a multiple of 8, planes 16B aligned");
+  const long long total = (long long)batch * (H / 2) * (W / 2) * 6;
+  stem_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(img_nchw, batch, H, W,
+                                                                       reinterpret_cast<__nv_bfloat16*>(out_planes), pitch,
+                                                                       pl_stride, nplanes);
+  return launched("stem_rows");
 }
 
 extern "C" int accflow_stem_patch_planes(const float* img_nchw, int batch, int H, int W, void* out_planes, int pitch,

@@ -351,6 +351,10 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
 // Persistent: grid = min(#tiles, #SMs); CTA c walks tiles c, c+grid, ... (tiles are N-major so that
 // neighbouring CTAs share one weight tile in L2).  Two TMEM accumulator slots let the epilogue of
 // tile i overlap the TMA/MMA main loop of tile i+1; the smem operand ring runs across tiles.
+// GRU = true: the instantiation for the GRU gate epilogues (its phase 2 issues all global reads of a 16-column step - the
+// hoisted input term, h, z - before the TMEM load; 48 more live registers, which the plain-store instantiation must
+// not pay: at 10 warps the allocator's ceiling is 168 registers per thread).
+template <bool GRU>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPack maps) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -587,7 +591,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       const int own_oy = oy0 + (trow >> p.tw_shift), own_ox = ox0 + (trow & (p.tw - 1));
       const bool own_in = own_oy < p.out_h && own_ox < p.out_w;
       const long long own_pix = ((long long)sample * p.out_h + own_oy) * p.out_w + own_ox;
-      if (p.epilogue == ACCFLOW_EPI_ROWSTATS || p.epilogue == ACCFLOW_EPI_STORE_T) {
+      if (!GRU && (p.epilogue == ACCFLOW_EPI_ROWSTATS || p.epilogue == ACCFLOW_EPI_STORE_T)) {
         // Row-wise epilogues straight from registers (no staging panel): softmax partial statistics of
         // s = acc*alpha over this half tile (gma/modules.py:66-74), or the transposed operand-plane store.
         float m_run = -INFINITY, l_run = 0.f;
@@ -639,7 +643,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       }
       float2 sm_stats = make_float2(0.f, 0.f);                    // softmax emit pass: (max, 1/sum) of this thread's row
       if (p.row_stats && own_in) sm_stats = __ldg(reinterpret_cast<const float2*>(p.row_stats) + own_pix);
-      if (p.epilogue == ACCFLOW_EPI_STORE_POOL) {
+      if (!GRU && p.epilogue == ACCFLOW_EPI_STORE_POOL) {
         // Correlation volume + first pyramid level (raft/corr.py:47-55 and :20-22).  The N axis of the tile is a
         // (BN / w) x w piece of the target map; this warp set owns the x range [half*w/2, (half+1)*w/2) of every
         // row, so a thread holds the two vertically adjacent 16-column runs of a row pair in registers: the 2x2
@@ -705,6 +709,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         }
         continue;
       }
+      if constexpr (GRU) {
       for (int sub = 0; sub < p.msub; ++sub) {
         // the four output rows this thread finishes per 16-column step (phase 2): fixed over the steps of a sub-tile
         long long pix4[4];
@@ -720,7 +725,6 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         for (int c = cbeg; c < cend; c += 16) {
           const int nb = n0 + c + pc4 * 4;
           const bool active = nb < p.cout && !(p.debug & 4);
-          const bool vec4 = nb + 3 < p.cout;
           // Global reads of this step (hoisted GRU term, h, z, residual) are issued BEFORE the TMEM load / staging /
           // warp sync below, all four rows at once: their latency overlaps phase 1 instead of being paid once per row
           // inside the math (the GRU epilogues were bound by exactly that: 2 exposed L2/DRAM round trips per step).
@@ -728,8 +732,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           const int hd = p.cout >> 1;
           const bool want_pre = active && p.pre_add != nullptr;
           const bool zr_r = p.epilogue == ACCFLOW_EPI_GRU_ZR && nb >= hd;
-          const bool want_b = active && (zr_r || p.epilogue == ACCFLOW_EPI_GRU_Q ||
-                                         (p.epilogue == ACCFLOW_EPI_STORE && p.residual && p.out_vec && vec4));
+          const bool want_b = active && (zr_r || p.epilogue == ACCFLOW_EPI_GRU_Q);
           const bool want_c = active && p.epilogue == ACCFLOW_EPI_GRU_Q;
 #pragma unroll
           for (int itr = 0; itr < 4; ++itr) {
@@ -737,9 +740,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             if (!rok[itr]) continue;
             if (want_pre) ga[itr] = __ldg(reinterpret_cast<const float4*>(p.pre_add + pix4[itr] * p.pre_ld + nb));
             if (want_b) {
-              const float* src = p.epilogue == ACCFLOW_EPI_STORE ? p.residual + pix4[itr] * p.res_ld + nb
-                                 : p.h + pix4[itr] * p.h_ld + (zr_r ? nb - hd : nb);
-              gb[itr] = *reinterpret_cast<const float4*>(src);
+              gb[itr] = *reinterpret_cast<const float4*>(p.h + pix4[itr] * p.h_ld + (zr_r ? nb - hd : nb));
             }
             if (want_c) gc[itr] = __ldg(reinterpret_cast<const float4*>(p.z + pix4[itr] * p.z_ld + nb));
           }
@@ -755,10 +756,6 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
               const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;   // fp16x2: lo planes carry 2^11
 #pragma unroll
               for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
-            }
-            if (p.row_stats) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) acc[j] = expf(fmaf(acc[j], p.sm_alpha, -sm_stats.x)) * sm_stats.y;
             }
             float4* d4 = reinterpret_cast<float4*>(stg + trow * PITCH);
 #pragma unroll
@@ -782,37 +779,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
               const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
               float y[4] = {fmaf(a4.x, sc[0], sh[0]) + ga[itr].x, fmaf(a4.y, sc[1], sh[1]) + ga[itr].y,
                             fmaf(a4.z, sc[2], sh[2]) + ga[itr].z, fmaf(a4.w, sc[3], sh[3]) + ga[itr].w};
-              if (p.epilogue == ACCFLOW_EPI_STORE) {
-                if (p.out_vec && vec4) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) y[j] = act_apply(y[j], p.act);
-                  if (p.residual) { y[0] += gb[itr].x; y[1] += gb[itr].y; y[2] += gb[itr].z; y[3] += gb[itr].w; }
-                  if (p.post_relu) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
-                  }
-                  if (p.out) *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
-                  if (p.out_pl.ptr) store_planes4(p.out_pl, p.plane_fmt, pix, nb, y);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const int n = nb + j;
-                    if (n < p.cout) {
-                      const bool second = p.act_split > 0 && n >= p.act_split;
-                      float o = act_apply(y[j], second ? p.act2 : p.act);
-                      if (p.residual) o += p.residual[pix * p.res_ld + n];
-                      if (p.post_relu) o = fmaxf(o, 0.f);
-                      if (second && p.out2) {
-                        p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
-                        if (p.out2_pl.ptr) store_planes1(p.out2_pl, p.plane_fmt, pix, n - p.act_split, o);
-                      } else {
-                        if (p.out) p.out[pix * p.out_ld + n] = o;
-                        if (p.out_pl.ptr) store_planes1(p.out_pl, p.plane_fmt, pix, n, o);
-                      }
-                    }
-                  }
-                }
-              } else if (p.epilogue == ACCFLOW_EPI_GRU_ZR) {
+              if (p.epilogue == ACCFLOW_EPI_GRU_ZR) {
                 // hd is a multiple of 4 (checked on the host): a group never straddles z | r
                 float g4[4];
 #pragma unroll
@@ -836,6 +803,115 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           }
           __syncwarp();
         }
+      }
+      } else {
+      for (int sub = 0; sub < p.msub; ++sub)
+      for (int c = cbeg; c < cend; c += 16) {
+        {
+          float acc[16];
+          if (p.debug & 8) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+          } else if (p.nprod == 1) tmem_ld16(lane_addr + sub * sub_cols + c, acc);
+          if (p.nprod > 1 && !(p.debug & 8)) {
+            float corr[16];
+            tmem_ld16x2(lane_addr + sub * sub_cols + c, lane_addr + sub * sub_cols + BN + c, acc, corr);
+            const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;   // fp16x2: lo planes carry 2^11
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
+          }
+          if (p.row_stats) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = expf(fmaf(acc[j], p.sm_alpha, -sm_stats.x)) * sm_stats.y;
+          }
+          float4* d4 = reinterpret_cast<float4*>(stg + trow * PITCH);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
+        if (c + 16 >= cend && sub == p.msub - 1) {   // last TMEM read of this tile: hand the slot back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
+        }
+        __syncwarp();                         // the panel rows this warp reads back are the ones it staged
+        const int nb = n0 + c + pc4 * 4;
+        if (nb < p.cout && !(p.debug & 4)) {
+          const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
+          const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[lt & 1][c + pc4 * 4]);
+          const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+          const bool vec4 = nb + 3 < p.cout;
+#pragma unroll 2
+          for (int itr = 0; itr < 4; ++itr) {
+            const int row = 32 * (warp & 3) + itr * 8 + (lane >> 2);
+            const int r_slow = (row >> p.tw_shift) + 16 * sub, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
+            const int oy = oy0 + (p.mode == 2 ? r_fast : r_slow), ox = ox0 + (p.mode == 2 ? r_slow : r_fast);
+            if (oy >= p.out_h || ox >= p.out_w) continue;
+            const long long pix = ((long long)sample * p.out_h + oy) * p.out_w + ox;
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
+            float y[4] = {fmaf(a4.x, sc[0], sh[0]), fmaf(a4.y, sc[1], sh[1]), fmaf(a4.z, sc[2], sh[2]), fmaf(a4.w, sc[3], sh[3])};
+            if (p.pre_add) {
+              const float4 pa = __ldg(reinterpret_cast<const float4*>(p.pre_add + pix * p.pre_ld + nb));
+              y[0] += pa.x; y[1] += pa.y; y[2] += pa.z; y[3] += pa.w;
+            }
+            if (p.epilogue == ACCFLOW_EPI_STORE) {
+              if (p.out_vec && vec4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) y[j] = act_apply(y[j], p.act);
+                if (p.residual) {
+                  const float4 r = *reinterpret_cast<const float4*>(p.residual + pix * p.res_ld + nb);
+                  y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
+                }
+                if (p.post_relu) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
+                }
+                if (p.out) *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
+                if (p.out_pl.ptr) store_planes4(p.out_pl, p.plane_fmt, pix, nb, y);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int n = nb + j;
+                  if (n < p.cout) {
+                    const bool second = p.act_split > 0 && n >= p.act_split;
+                    float o = act_apply(y[j], second ? p.act2 : p.act);
+                    if (p.residual) o += p.residual[pix * p.res_ld + n];
+                    if (p.post_relu) o = fmaxf(o, 0.f);
+                    if (second && p.out2) {
+                      p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
+                      if (p.out2_pl.ptr) store_planes1(p.out2_pl, p.plane_fmt, pix, n - p.act_split, o);
+                    } else {
+                      if (p.out) p.out[pix * p.out_ld + n] = o;
+                      if (p.out_pl.ptr) store_planes1(p.out_pl, p.plane_fmt, pix, n, o);
+                    }
+                  }
+                }
+              }
+            } else if (p.epilogue == ACCFLOW_EPI_GRU_ZR) {
+              const int hd = p.cout >> 1;   // multiple of 4 (checked on the host): a group never straddles z | r
+              float g4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) g4[j] = 1.f / (1.f + expf(-y[j]));
+              if (nb < hd) {
+                *reinterpret_cast<float4*>(p.z + pix * p.z_ld + nb) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+              } else {
+                const int n = nb - hd;
+                const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + n);
+                float o[4] = {g4[0] * hh.x, g4[1] * hh.y, g4[2] * hh.z, g4[3] * hh.w};
+                if (p.out2) *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
+                if (p.out2_pl.ptr) store_planes4(p.out2_pl, p.plane_fmt, pix, n, o);
+              }
+            } else {
+              const float4 zz = *reinterpret_cast<const float4*>(p.z + pix * p.z_ld + nb);
+              const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + nb);
+              float o[4] = {(1.f - zz.x) * hh.x + zz.x * tanhf(y[0]), (1.f - zz.y) * hh.y + zz.y * tanhf(y[1]),
+                            (1.f - zz.z) * hh.z + zz.z * tanhf(y[2]), (1.f - zz.w) * hh.w + zz.w * tanhf(y[3])};
+              *reinterpret_cast<float4*>(p.h + pix * p.h_ld + nb) = make_float4(o[0], o[1], o[2], o[3]);
+              if (p.h_pl.ptr) store_planes4(p.h_pl, p.plane_fmt, pix, nb, o);
+            }
+          }
+        }
+        __syncwarp();
+      }
       }
     }
   }
@@ -1028,6 +1104,9 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   p.out_h = (d.in_h + 2 * d.pad_h - d.kh) / d.stride + 1;
   p.out_w = (d.in_w + 2 * d.pad_w - d.kw) / d.stride + 1;
   ACCFLOW_REQUIRE(p.out_h > 0 && p.out_w > 0, "conv2d_tc: empty output");
+  ACCFLOW_REQUIRE(d.out_h >= 0 && d.out_h <= p.out_h && d.out_w >= 0 && d.out_w <= p.out_w, "conv2d_tc: out_h / out_w exceed the output map");
+  if (d.out_h) p.out_h = d.out_h;
+  if (d.out_w) p.out_w = d.out_w;
   int tw = 8, sh = 3;
   while (tw < p.out_w && tw < 128) { tw <<= 1; ++sh; }
   p.tw = tw; p.tw_shift = sh; p.th = tc::BM / tw;
@@ -1196,7 +1275,8 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   int dev = 0;
   cudaGetDevice(&dev);
   if (cfg_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
     if (e != cudaSuccess) return fail((int)e, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
     cfg_dev = dev;
   }
@@ -1204,6 +1284,9 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
   const int total_tiles = p.tiles_x * p.tiles_y * d.batch * p.n_tiles;
   dim3 grid(total_tiles < sm_count ? total_tiles : sm_count, 1, 1);
-  tc::conv_tc_kernel<<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
+  if (d.epilogue == ACCFLOW_EPI_GRU_ZR || d.epilogue == ACCFLOW_EPI_GRU_Q)
+    tc::conv_tc_kernel<true><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
+  else
+    tc::conv_tc_kernel<false><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
   return launched("conv2d_tc");
 }

@@ -268,7 +268,7 @@ class Kernels:
              weight_ptr: Optional[int] = None, weight_batch_stride=0, cout=None, cout_pad=None,
              use_affine=True, tc_b: Optional["L.TcWeights"] = None, tc_src_planes=None, planes_only=False,
              emit_planes=True, pool_w=0, pre_add: Optional[View] = None, row_stats: Optional[torch.Tensor] = None,
-             tc_out_planes=None):
+             tc_out_planes=None, out_h: int = 0):
         """``planes_only``: the output (``out``; ``out2`` for the GRU z|r epilogue) is read by tensor-core
         convolutions only, so in the tensor-core modes its fp32 copy is not written (half the store bytes).
         ``emit_planes=False``: the next reader is not a tensor-core conv (InstanceNorm), so no planes are written.
@@ -309,6 +309,7 @@ class Kernels:
             d.pre_add, d.pre_ld = pre_add.ptr, pre_add.ld
         if row_stats is not None:
             d.row_stats = row_stats.data_ptr()
+        d.out_h = out_h
         if tc:
             io = L.TcIO()
             for k, sv in enumerate(srcs):
@@ -351,12 +352,13 @@ class Kernels:
             L.call(*args)
         else:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            oh = (s0.h + 2 * pc.pad_h - pc.kh) // pc.stride + 1
+            oh = out_h or (s0.h + 2 * pc.pad_h - pc.kh) // pc.stride + 1
             ow = (s0.w + 2 * pc.pad_w - pc.kw) // pc.stride + 1
             e0.record()
             L.call(*args)
             e1.record()
-            self.profile.append((e0, e1, 2.0 * s0.b * oh * ow * d.cout * cin * pc.kh * pc.kw))
+            macs = getattr(pc, "algo_macs_per_pixel", None) or d.cout * cin * pc.kh * pc.kw     # algorithmic, not padded
+            self.profile.append((e0, e1, 2.0 * s0.b * oh * ow * macs))
         for tv in written:
             self._fresh(tv)
 
@@ -574,6 +576,14 @@ class EncoderPlan:
         w = sd[pfx + "conv1.weight"]                       # (64,3,7,7) -> [(ky*7+kx)*3 + c][64]
         self.stem = pc(pfx + "conv1", 2, 3, pfx + "norm1")
         self.stem.w = w.detach().to(F32).permute(2, 3, 1, 0).reshape(147, 64).contiguous()
+        # tensor-core form (accflow_stem_rows_planes): 4 vertical taps over 48 channels k = tx*12 + c*4 + dy*2 + dx,
+        # filter value w[o][c][2*ty + dy - 1][2*tx + dx - 1] (zero where an index is -1)
+        w8 = torch.zeros(w.shape[0], 3, 8, 8, device=w.device, dtype=F32)
+        w8[:, :, 1:, 1:] = w.detach().to(F32)
+        w4 = w8.view(w.shape[0], 3, 4, 2, 4, 2).permute(0, 2, 4, 1, 3, 5).reshape(w.shape[0], 4, 48)   # [o][ty][tx,c,dy,dx]
+        self.stem4 = PackedConv([w4.permute(0, 2, 1).reshape(w.shape[0], 48, 4, 1).contiguous()], [sd[pfx + "conv1.bias"]],
+                                1, (2, 0), bn(pfx + "norm1"))
+        self.stem4.algo_macs_per_pixel = w.shape[0] * 147          # the zero taps of the 8x8 embedding are not work
         self.blocks = []
         for stage, stride in ((1, 1), (2, 2), (3, 2)):
             for blk in (0, 1):
@@ -586,20 +596,20 @@ class EncoderPlan:
 
     @staticmethod
     def stem_patches(k: Kernels, images: Sequence[torch.Tensor]):
-        """im2col of the 7x7/s2 stem (K = 147, raft/extractor.py:163) straight into operand planes.  The patches
-        depend on the image only, so one gather serves every encoder that reads the same frames
-        -> (base pointer, pitch, plane stride in elements, bytes per image)."""
+        """Operand planes of the 7x7/s2 stem (raft/extractor.py:163) in its 4-vertical-tap form: 48 channels per
+        half-resolution pixel (accflow_stem_rows_planes).  They depend on the image only, so one gather serves every
+        encoder that reads the same frames -> (base pointer, pitch, plane stride in elements, bytes per image)."""
         n = sum(int(im.shape[0]) for im in images)
         H, W = int(images[0].shape[-2]), int(images[0].shape[-1])
-        h2, w2 = (H + 1) // 2, (W + 1) // 2
-        pitch = 152
-        patches = k.buf16("stem.patches", k.nplanes, n, h2, w2, pitch)
+        h2, w2 = H // 2, W // 2
+        pitch = 48
+        patches = k.buf16("stem.rows", k.nplanes, n, h2, w2, pitch)
         stride_pl = n * h2 * w2 * pitch
         b0 = 0
         for im in images:
             assert im.dtype == F32 and im.is_contiguous() and im.shape[1] == 3
             nb = int(im.shape[0])
-            L.call("accflow_stem_patch_planes", im.data_ptr(), nb, H, W,
+            L.call("accflow_stem_rows_planes", im.data_ptr(), nb, H, W,
                    patches.data_ptr() + 2 * b0 * h2 * w2 * pitch, pitch, stride_pl, k.plane_fmt, _stream())
             b0 += nb
         return patches.data_ptr(), pitch, stride_pl, 2 * h2 * w2 * pitch
@@ -616,12 +626,12 @@ class EncoderPlan:
         x = k.view(tag + ".stem", n, h2, w2, 64)
         b0 = 0
         if k.tc:
-            # im2col (7x7/s2, K=147) straight into operand planes, then a 1x1 conv on the tensor cores
+            # x taps folded into 48 channels (operand planes), the 4 y taps served by the conv kernel's shift mode
             if patches is None:
                 patches, patch_image0 = self.stem_patches(k, images), 0
             pptr, pitch, stride_pl, img_bytes = patches
-            k.conv(self.stem.as_1x1(), [PlanesOnly(n, h2, w2, 147, pitch)], x, act=relu,
-                   tc_src_planes=[(pptr + patch_image0 * img_bytes, pitch, stride_pl)], emit_planes=not inst)
+            k.conv(self.stem4, [PlanesOnly(n, h2, w2, 48, pitch)], x, act=relu,
+                   tc_src_planes=[(pptr + patch_image0 * img_bytes, pitch, stride_pl)], emit_planes=not inst, out_h=h2)
         else:
             for im in images:
                 assert im.dtype == F32 and im.is_contiguous() and im.shape[1] == 3

@@ -100,6 +100,9 @@ typedef struct accflow_conv_desc {
   /* EPI_STORE on the tensor-core kernel: per-row (max, 1/sum) pairs [batch*out_h*out_w][2]; when set the stored value
    * is exp(acc*alpha - max) * (1/sum) (softmax emit pass, see ACCFLOW_EPI_ROWSTATS); scale/shift/act must be unset. */
   const float* row_stats;
+  /* tensor-core kernel: evaluate only the first out_h rows / out_w columns of the output map (0 = all, i.e.
+   * (in + 2*pad - k)/stride + 1).  Expresses asymmetric padding: the stem's 4-tap form pads 2 above and 1 below. */
+  int out_h, out_w;
 } accflow_conv_desc;
 
 ACCFLOW_API int accflow_abi_version(void);
@@ -191,6 +194,12 @@ ACCFLOW_API int accflow_flow_patch_f32(const float* flow, int batch, int h, int 
  * 209) then runs as a K=147 1x1 conv on the tensor-core kernel. */
 ACCFLOW_API int accflow_stem_patch_planes(const float* img_nchw, int batch, int H, int W, void* out_planes, int pitch,
                                           long long pl_plane_stride, int nplanes, void* stream);
+
+/* The same stem as a 4-tap vertical convolution: the four x taps of the 4x4 filter over the 2x2 space-to-depth image are
+ * folded into 48 channels, out[n][Y][X][tx*12 + c*4 + dy*2 + dx] = img[n][c][2Y + dy][2(X + tx - 2) + dx] (zero outside);
+ * the tensor-core kernel then runs kh = 4, kw = 1, pad_h = 2 with accflow_conv_desc.out_h = H/2 (raft/extractor.py:163-167). */
+ACCFLOW_API int accflow_stem_rows_planes(const float* img_nchw, int batch, int H, int W, void* out_planes, int pitch,
+                                         long long pl_plane_stride, int nplanes, void* stream);
 
 /* 3x3 / stride 1 / pad 1 convolution with cout <= 4 (FlowHead.conv2 raft/update.py:10,
  * FlowDecoder.flow[2] AccFlow_.py:19, Blending.mask[2] AccFlow_.py:118), fused affine + activation.

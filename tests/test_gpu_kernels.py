@@ -275,6 +275,33 @@ def test_corr_pyramid_and_lookup(KP, golden):
     assert maxdiff(flow.view(B, h, w, 2).permute(0, 3, 1, 2), coords - ops.coords_grid(B, h, w)) < 1e-6
 
 
+@pytest.mark.parametrize("hw", [(16, 32), (64, 64), (24, 96)])
+def test_corr_lookup_16byte_gather_path(hw):
+    """CorrBlock.__call__ (raft/corr.py:24-45) on maps whose widths are multiples of 32 (512x512 / 1024x1024
+    configurations): the 16-byte-gather kernel vs the oracle, coordinates far outside the map included."""
+    from accflow_b200 import _lib as L
+    from oracle import ops
+    h, w = hw
+    B = 2
+    g = torch.Generator().manual_seed(61)
+    f1 = torch.randn(B, 32, h, w, generator=g)
+    f2 = torch.randn(B, 32, h, w, generator=g)
+    pyr = ops.corr_pyramid(f1, f2)
+    coords = ops.coords_grid(B, h, w) + torch.randn(B, 2, h, w, generator=g) * 12.0
+    coords[0, :, 0, 0] = torch.tensor([-7.3, 2.2])               # far outside: all taps of level 0 are zero padding
+    coords[1, :, h - 1, w - 1] = torch.tensor([w + 30.5, h + 9.25])
+    coords[0, :, 1, 1] = torch.tensor([3.0, 4.0])                # integer coordinates (weights exactly 1 / 0)
+    ref = ops.corr_lookup(pyr, coords)
+    lv = [t.reshape(B * h * w, -1).cuda().contiguous() for t in pyr]
+    out = torch.empty(B, h, w, 324, device="cuda")
+    flow = torch.empty(B, h * w, 2, device="cuda")
+    c = dev(coords.permute(0, 2, 3, 1).reshape(B, h * w, 2).contiguous())
+    L.call("accflow_corr_lookup_f32", lv[0].data_ptr(), lv[1].data_ptr(), lv[2].data_ptr(), lv[3].data_ptr(), B, h, w, 4,
+           c.data_ptr(), out.data_ptr(), 324, flow.data_ptr(), None, 0, None, 0, 0, None, 0, 0, 1, None)
+    torch.cuda.synchronize()
+    assert maxdiff(out.permute(0, 3, 1, 2), ref) < 2e-5
+
+
 @pytest.mark.parametrize("hw", [(32, 32), (16, 64), (64, 64)])
 def test_corr_volume_with_fused_first_level(hw):
     """CorrBlock.__init__ (raft/corr.py:8-22, 47-55) through the engine path whose GEMM epilogue emits level 1:
@@ -325,7 +352,9 @@ def test_gma_attention_and_aggregate(KP, hw):
     eng.gamma, eng.qk_scale = 0.5, 128 ** -0.5
     inpv, mfv = View(dev(nhwc(inp))), View(dev(nhwc(mf)))
     out = View(torch.zeros(B, h, w, 128, device="cuda"))
-    for _ in range(2):                                       # second pass: plane buffers exist (planes-only outputs)
+    if K.tc:
+        K.planes_ptr(out, create=True)                       # as in the engine: the GRU convs read mf_global's planes only
+    for _ in range(2):
         attn = eng.attention(inpv, f"tatt{h}x{w}")
         eng.aggregate(attn, mfv, out, f"tatt{h}x{w}")
     torch.cuda.synchronize()
