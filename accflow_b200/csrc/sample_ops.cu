@@ -863,7 +863,8 @@ extern "C" int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, con
   ACCFLOW_REQUIRE((!out_planes && !tail_planes) || valid_plane_fmt(nplanes), "corr_lookup: bad plane format");
   p.out_pl = reinterpret_cast<__nv_bfloat16*>(out_planes); p.pl_pitch = pl_pitch; p.pl_stride = pl_stride; p.nplanes = nplanes;
   p.tail_pl = reinterpret_cast<__nv_bfloat16*>(tail_planes); p.tail_pitch = tail_pitch; p.tail_stride = tail_stride;
-  static const bool vec_off = getenv("ACCFLOW_LOOKUP_VEC") && atoi(getenv("ACCFLOW_LOOKUP_VEC")) == 0;
+  const char* vec_env = getenv("ACCFLOW_LOOKUP_VEC");      // read per call: A/B experiments toggle it in-process
+  const bool vec_off = vec_env && atoi(vec_env) == 0;
   const bool vec_ok = !vec_off && w % 32 == 0 && aligned16(lvl0) && aligned16(lvl1) && aligned16(lvl2) && aligned16(lvl3);
   if (radius == 4 && vec_ok) corr_lookup_vec_kernel<4><<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(p);   // 16-byte gathers
   else if (radius == 4) corr_lookup_fast_kernel<4><<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(p);     // RAFT / GMA
