@@ -275,6 +275,8 @@ def run_b200(args):
     from accflow_b200.sharding import gather_clip_metrics, shard_clip_ids
     n_clips = args.total_clips if args.total_clips else world * b
     my_ids = shard_clip_ids(n_clips, rank, world)
+    n_micro = -(-len(my_ids) // b)
+    b = -(-len(my_ids) // n_micro)                      # even micro-steps (64 clips, --clips 9 -> 8 x 8, not 7 x 9 + 1)
     micro = [my_ids[i:i + b] for i in range(0, len(my_ids), b)]
     batches = [make_inputs(ids, args.size) for ids in micro]
     dev_sets = [([t.to(dev) for t in bt["imgs"]], bt["bflows"][-1].to(dev), bt["fflows"][-1].to(dev)) for bt in batches]
