@@ -97,6 +97,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
+#pragma unroll 1                       // (unrolled x4 at every call site it was 1 500 of the kernel's 12 500 instructions)
   for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
     asm volatile(
         "{\n"
@@ -213,61 +214,6 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n, bool fp16) {
 }
 
 
-// ---------------------------------------------------------------------------------- CTA-pair helpers (cta_group::2)
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of the same shared variable in CTA rank 0 (the MMA leader) of the cluster
-__device__ __forceinline__ uint32_t mapa_rank0(uint32_t local_addr) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local_addr));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma2_load_4d(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
-                                             int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma2_load_5d(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
-                                             int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {     // arrives on `bar` in BOTH CTAs of the pair
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 // Perf-experiment trace (ACCFLOW_TC_DEBUG bit 4 = 16): clock64 stamps of CTA 0's MMA-issuing thread, three per weight
 // tile (barriers passed, last MMA issued, commit issued); read back with accflow_tc_debug_trace.
 __device__ long long g_tc_trace[3 * 1024];
@@ -322,18 +268,10 @@ __device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) {
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 
-// PAIR (cta_group::2): the leader CTA's thread issues M = 256 instructions over both CTAs' activation boxes; each CTA
-// holds HALF of the weight tile's rows, so the fused N = 2*BN product is not expressible (its halves would land in
-// non-adjacent TMEM columns) and the split mode issues three N = BN products instead; commits are multicast to both
-// CTAs' barriers.
-template <int NPROD, int MSUB, bool PAIR>
+template <int NPROD, int MSUB>
 __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
-  const uint32_t idesc1 = make_idesc(PAIR ? 2 * BM : BM, c.BN, c.fp16 != 0);
-  const uint32_t idesc2 = make_idesc(BM, 2 * c.BN, c.fp16 != 0);      // a0 x [w0; w1] -> MAIN | CORR (single CTA only)
-  auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-    if (PAIR) umma2_bf16(d, a, b, idesc, acc); else umma_bf16(d, a, b, idesc, acc);
-  };
-  auto commit = [](uint64_t* bar) { if (PAIR) umma2_commit_mc(bar); else umma_commit(bar); };
+  const uint32_t idesc1 = make_idesc(BM, c.BN, c.fp16 != 0);
+  const uint32_t idesc2 = make_idesc(BM, 2 * c.BN, c.fp16 != 0);      // a0 x [w0; w1] -> MAIN | CORR
   const bool comb = c.n_inner == 1;        // operands share the weight ring's barriers (SA == SB, slots advance together)
   int sa = 0, sb = 0, ntr = 0;
   bool next_ready = false, a_ready = false;
@@ -378,13 +316,7 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
               const uint64_t a0 = desc_from_lo(as_lo + 2 * k4), w0 = desc_from_lo(w_lo + 2 * k4);
               const uint32_t acc = first | (uint32_t)k4;
               if (NPROD == 1) {
-                mma(sm_main, a0, w0, idesc1, acc);
-              } else if (PAIR) {
-                const uint64_t a1 = desc_from_lo(as_lo + c.a_plane16 + 2 * k4);
-                const uint64_t w1 = desc_from_lo(w_lo + c.w_plane16 + 2 * k4);
-                mma(sm_main, a0, w0, idesc1, acc);                   // MAIN += a0 w0
-                mma(sm_corr, a0, w1, idesc1, acc);                   // CORR += a0 w1
-                mma(sm_corr, a1, w0, idesc1, 1);                     // CORR += a1 w0
+                umma_bf16(sm_main, a0, w0, idesc1, acc);
               } else {
                 const uint64_t a1 = desc_from_lo(as_lo + c.a_plane16 + 2 * k4);
                 umma_bf16(sm_main, a0, w0, idesc2, acc);             // MAIN += a0 w0 ; CORR += a0 w1
@@ -403,17 +335,17 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
         }
         first = 1;
         if (tr) g_tc_trace[3 * ntr + 1] = clock64();
-        commit(&c.bfree[sb]);                                        // weight tile reusable once these MMAs retire
+        umma_commit(&c.bfree[sb]);                                   // weight tile reusable once these MMAs retire
         if (tr) { g_tc_trace[3 * ntr + 2] = clock64(); ++ntr; }
         a_lo += 1024 >> 4;                                           // shift modes: next tap = 8 pixel rows further
         w_slot += c.b_stage;
         if (++sb == c.SB) { sb = 0; pb ^= 1; w_slot = c.smem_b; }
       }
-      if (!comb) commit(&c.afree[sa]);                               // ... and so is the activation box
+      if (!comb) umma_commit(&c.afree[sa]);                          // ... and so is the activation box
       a_slot += c.a_stage;
       if (++sa == c.SA) { sa = 0; pa ^= 1; a_slot = c.smem_a; }
     }
-    commit(&c.acc_full[slot]);
+    umma_commit(&c.acc_full[slot]);
   }
 }
 
@@ -423,14 +355,7 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
 // GRU = true: the instantiation for the GRU gate epilogues (its phase 2 issues all global reads of a 16-column step - the
 // hoisted input term, h, z - before the TMEM load; 48 more live registers, which the plain-store instantiation must
 // not pay: at 10 warps the allocator's ceiling is 168 registers per thread).
-// PAIR = true: launched as clusters of two CTAs (tcgen05 cta_group::2).  A pair computes 256 pixels x BN: each CTA stages
-// its own 128-pixel activation boxes and HALF of every weight tile, the leader (cluster rank 0) issues M = 256 MMAs that
-// read both CTAs' shared memory, each CTA's accumulator lives in its own TMEM and is drained by its own epilogue warps.
-// Weight bytes per SM halve: the single-CTA kernel needs ~52 B/clk/SM of operands in the split mode against the
-// ~42 B/clk/SM the L2 delivers chip-wide (profiles/r2b_gru_probe.jsonl, B300_MICROARCH: 6300 B/clk), the pair ~31.
-// Barriers: both CTAs' TMA bytes complete on the LEADER's full barriers; tcgen05.commit multicasts the free / acc_full
-// arrivals to both CTAs; both CTAs' epilogue warps arrive on the leader's acc_empty.
-template <bool GRU, bool PAIR>
+template <bool GRU>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPack maps) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -443,7 +368,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = p.bn, SA = p.stages, SB = p.stages_b, NPL = p.nplanes;
   const int n_outer = p.n_outer, n_inner = p.n_inner;          // A boxes per K block / taps served by one box
-  const int w_plane_bytes = (PAIR ? BN / 2 : BN) * KC * 2;     // pair: this CTA's half of the weight tile's rows
+  const int w_plane_bytes = BN * KC * 2;
   const int a_plane_bytes = p.a_plane_bytes;                    // (128 + 8 * halo rows) pixels x 128 B
   const int a_stage = NPL * a_plane_bytes, b_stage = NPL * w_plane_bytes;
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms): [A ring][W ring] then the epilogue panels
@@ -460,14 +385,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
   const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
-  // tile walk: single CTA: tile = n_tile * m_tiles + m; pair: tile = n_tile * m_pairs + mp, this CTA's m = 2*mp + rank
-  // (m >= m_tiles is the phantom half of an odd last pair: its sample index is out of range, TMA zero-fills, no stores)
-  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
-  const bool leader = crank == 0;
-  const int m_div = PAIR ? (m_tiles + 1) >> 1 : m_tiles;
-  const int total_tiles = m_div * p.n_tiles;
-  const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tile_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total_tiles = m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < SA; ++s) {
@@ -480,29 +398,17 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
     }
     for (int j = 0; j < 2; ++j) {
       mbar_init(&bar_acc_full[j], 1);
-      mbar_init(&bar_acc_empty[j], PAIR ? 16 : 8);      // one arrival per epilogue warp (pair: of both CTAs, leader's copy)
+      mbar_init(&bar_acc_empty[j], 8);      // one arrival per epilogue warp
     }
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
     for (int s = 0; s < p.nsrc; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
   }
-  if (warp == 1) { if (PAIR) tmem_alloc2(&tmem_slot, tmem_cols); else tmem_alloc(&tmem_slot, tmem_cols); }
+  if (warp == 1) tmem_alloc(&tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();           // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  // operand loads: the pair variants complete on the leader's barrier (shared::cluster address); only the leader
-  // posts the expected byte count, for both CTAs
-  auto ld_a = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
-    if (PAIR) tma2_load_5d(dst, m, mapa_rank0(smem_u32(bar)), c0, c1, c2, c3, c4); else tma_load_5d(dst, m, bar, c0, c1, c2, c3, c4);
-  };
-  auto ld_w = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    if (PAIR) tma2_load_4d(dst, m, mapa_rank0(smem_u32(bar)), c0, c1 + (int)crank * (BN / 2), c2, c3); else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
-  };
-  auto expect = [&](uint64_t* bar, uint32_t bytes) {
-    if (!PAIR) mbar_expect_tx(bar, bytes); else if (leader) mbar_expect_tx(bar, 2u * bytes);
-  };
 
   if (warp == 0) {
     // ================================ TMA producer ============================================
@@ -510,10 +416,9 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       const bool comb = n_inner == 1;
       int sa = 0, sb = 0;                                    // ring positions (A boxes, weight tiles)
       uint32_t pa = 1, pb = 1;                               // parity of the "free" phase to wait for (first lap passes)
-      for (int tile = tile_first; tile < total_tiles; tile += tile_stride) {
-        const int n_tile = tile / m_div;
-        int t = tile - n_tile * m_div;
-        if (PAIR) t = 2 * t + (int)crank;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile / m_tiles;
+        int t = tile - n_tile * m_tiles;
         const int tile_x = t % p.tiles_x; t /= p.tiles_x;
         const int tile_y = t % p.tiles_y;
         const int sample = t / p.tiles_y;
@@ -526,10 +431,10 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           uint8_t* adst = smem + (size_t)(comb ? sb : sa) * a_stage;
           if (comb) {
             mbar_wait(&bar_bfree[sb], pb);
-            expect(abar, (p.debug & 1) ? 0u : (uint32_t)(a_stage + b_stage));
+            mbar_expect_tx(abar, (p.debug & 1) ? 0u : (uint32_t)(a_stage + b_stage));
           } else {
             mbar_wait(&bar_afree[sa], pa);
-            expect(abar, (p.debug & 1) ? 0u : (uint32_t)a_stage);
+            mbar_expect_tx(abar, (p.debug & 1) ? 0u : (uint32_t)a_stage);
           }
           int c1, c2;                                        // box origin along tensor-map dims 1, 2
           if (p.mode == 0) {
@@ -541,16 +446,16 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             c1 = oy0 + ck.tap - p.pad_h; c2 = ox0 - p.pad_w;
           }
           // one TMA op brings all operand planes (the plane index is the box's outermost dimension)
-          if (!(p.debug & 1)) ld_a(adst, &maps.a[ck.s], abar, ck.c0, c1, c2, sample, 0);
+          if (!(p.debug & 1)) tma_load_5d(adst, &maps.a[ck.s], abar, ck.c0, c1, c2, sample, 0);
           const int kcoord = p.src_off[ck.s] + ck.c0;
           for (int j = 0; j < n_inner; ++j) {
             uint8_t* wdst = smem_b + (size_t)sb * b_stage;
             if (!comb) {
               mbar_wait(&bar_bfree[sb], pb);
-              expect(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)b_stage);
+              mbar_expect_tx(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)b_stage);
             }
             const int tap = p.per_sample ? sample : p.mode == 0 ? ck.tap : p.mode == 1 ? j * p.kw + ck.tap : ck.tap * p.kw + j;
-            if (!(p.debug & 1)) ld_w(wdst, &maps.w, &bar_bfull[sb], kcoord, n0, tap, 0);
+            if (!(p.debug & 1)) tma_load_4d(wdst, &maps.w, &bar_bfull[sb], kcoord, n0, tap, 0);
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
           if (++sa == SA) { sa = 0; pa ^= 1; }
@@ -571,9 +476,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         Chunk ck;
       };
       auto decode = [&](Cur& c) {
-        const int n_tile = c.tile / m_div;
-        int t = c.tile - n_tile * m_div;
-        if (PAIR) t = 2 * t + (int)crank;
+        const int n_tile = c.tile / m_tiles;
+        int t = c.tile - n_tile * m_tiles;
         const int tile_x = t % p.tiles_x; t /= p.tiles_x;
         const int tile_y = t % p.tiles_y;
         c.sample = t / p.tiles_y;
@@ -583,7 +487,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       auto advance = [&](Cur& c) {
         c.ck.next(p, n_outer);
         if (++c.i == nchunks) {
-          c.tile += tile_stride;
+          c.tile += gridDim.x;
           if (c.tile < total_tiles) decode(c);
         }
       };
@@ -597,16 +501,16 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         } else {                                             // dims (C, H, W): outer tap = ky, halo along x
           c1 = c.oy0 + c.ck.tap - p.pad_h; c2 = c.ox0 - p.pad_w;
         }
-        if (!(p.debug & 1)) ld_a(adst, &maps.a[c.ck.s], abar, c.ck.c0, c1, c2, c.sample, 0);
+        if (!(p.debug & 1)) tma_load_5d(adst, &maps.a[c.ck.s], abar, c.ck.c0, c1, c2, c.sample, 0);
       };
       auto issue_a_ring = [&](const Cur& c) {               // shift modes: the box goes to the activation ring
         mbar_wait(&bar_afree[sa], pa);
-        expect(&bar_afull[sa], (p.debug & 1) ? 0u : (uint32_t)a_stage);
+        mbar_expect_tx(&bar_afull[sa], (p.debug & 1) ? 0u : (uint32_t)a_stage);
         issue_a(c, &bar_afull[sa], smem + (size_t)sa * a_stage);
         if (++sa == SA) { sa = 0; pa ^= 1; }
       };
       Cur cb;
-      cb.tile = tile_first;
+      cb.tile = blockIdx.x;
       if (cb.tile < total_tiles) decode(cb);
       Cur ca = cb;
       const int ja = SB - 1;                                 // weight tile after which the next box is requested
@@ -619,17 +523,17 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           // n_inner == 1 (one weight tile per activation box): both operands share the weight ring's
           // barriers and slot index, i.e. one handshake per K step instead of two.
           mbar_wait(&bar_bfree[sb], pb);
-          expect(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)(a_stage + b_stage));
+          mbar_expect_tx(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)(a_stage + b_stage));
           issue_a(cb, &bar_bfull[sb], smem + (size_t)sb * a_stage);
         }
         for (int j = 0; j < n_inner; ++j) {
           uint8_t* wdst = smem_b + (size_t)sb * b_stage;
           if (!comb) {
             mbar_wait(&bar_bfree[sb], pb);
-            expect(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)b_stage);
+            mbar_expect_tx(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)b_stage);
           }
           const int tap = p.per_sample ? cb.sample : p.mode == 0 ? cb.ck.tap : p.mode == 1 ? j * p.kw + cb.ck.tap : cb.ck.tap * p.kw + j;
-          if (!(p.debug & 1)) ld_w(wdst, &maps.w, &bar_bfull[sb], kcoord, cb.n0, tap, 0);
+          if (!(p.debug & 1)) tma_load_4d(wdst, &maps.w, &bar_bfull[sb], kcoord, cb.n0, tap, 0);
           if (++sb == SB) { sb = 0; pb ^= 1; }
           if (ahead && j == ja && ca.tile < total_tiles) { issue_a_ring(ca); advance(ca); }
         }
@@ -638,9 +542,9 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==============================================
-    if (lane == 0 && leader) {
+    if (lane == 0) {
       MmaCtx c;
-      c.total_tiles = total_tiles; c.stride_tiles = tile_stride; c.first_tile = tile_first;
+      c.total_tiles = total_tiles; c.stride_tiles = gridDim.x; c.first_tile = blockIdx.x;
       c.nchunks = nchunks; c.n_inner = n_inner; c.SA = SA; c.SB = SB; c.BN = BN;
       c.a_stage = a_stage; c.b_stage = b_stage; c.a_plane16 = a_plane_bytes >> 4; c.w_plane16 = w_plane_bytes >> 4;
       c.smem_a = smem_u32(smem); c.smem_b = smem_u32(smem_b);
@@ -648,9 +552,9 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       c.fp16 = p.fp16;
       c.afull = bar_afull; c.afree = bar_afree; c.bfull = bar_bfull; c.bfree = bar_bfree;
       c.acc_full = bar_acc_full; c.acc_empty = bar_acc_empty;
-      if (p.nprod == 3) { if (p.msub == 2) mma_issue_loop<3, 2, PAIR>(c); else mma_issue_loop<3, 1, PAIR>(c); }
-      else if (p.nprod == 1) { if (p.msub == 2) mma_issue_loop<1, 2, PAIR>(c); else mma_issue_loop<1, 1, PAIR>(c); }
-      else if (!PAIR) mma_issue_loop<6, 1, false>(c);
+      if (p.nprod == 3) { if (p.msub == 2) mma_issue_loop<3, 2>(c); else mma_issue_loop<3, 1>(c); }
+      else if (p.nprod == 1) { if (p.msub == 2) mma_issue_loop<1, 2>(c); else mma_issue_loop<1, 1>(c); }
+      else mma_issue_loop<6, 1>(c);
     }
   } else {
     // ================================ epilogue ================================================
@@ -663,18 +567,12 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
     const int pc4 = st & 3;                                     // float4 group inside the 16-column panel
     const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
     int lt = 0;
-    const uint32_t empty_bar0 = PAIR ? mapa_rank0(smem_u32(&bar_acc_empty[0])) : 0u;     // the leader's acc_empty[0]
-    auto release_slot = [&](int slot) {       // TMEM slot drained by this warp: tell the MMA thread (pair: the leader's)
-      if (PAIR) mbar_arrive_remote(empty_bar0 + 8u * (uint32_t)slot); else mbar_arrive(&bar_acc_empty[slot]);
-    };
-    for (int tile = tile_first; tile < total_tiles; tile += tile_stride, ++lt) {
-      const int n_tile = tile / m_div;
-      int t = tile - n_tile * m_div;
-      if (PAIR) t = 2 * t + (int)crank;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int n_tile = tile / m_tiles;
+      int t = tile - n_tile * m_tiles;
       const int tile_x = t % p.tiles_x; t /= p.tiles_x;
       const int tile_y = t % p.tiles_y;
       const int sample = t / p.tiles_y;
-      const bool phantom = PAIR && sample >= p.batch;            // odd last pair: nothing to store
       const int ox0 = tile_x * p.tile_w, oy0 = tile_y * p.tile_h, n0 = n_tile * BN;
       const int slot = lt & 1, use = lt >> 1;
       {  // stage this tile's scale / shift (global-load latency off the per-panel critical path)
@@ -692,7 +590,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       const uint32_t lane_addr = tmem_base + slot * acc_cols + ((uint32_t)(32 * (warp & 3)) << 16);
       // this thread's own output row (TMEM lane), mode 0 tiles: used by the row-wise epilogues below
       const int own_oy = oy0 + (trow >> p.tw_shift), own_ox = ox0 + (trow & (p.tw - 1));
-      const bool own_in = own_oy < p.out_h && own_ox < p.out_w && !phantom;
+      const bool own_in = own_oy < p.out_h && own_ox < p.out_w;
       const long long own_pix = ((long long)sample * p.out_h + own_oy) * p.out_w + own_ox;
       if (!GRU && (p.epilogue == ACCFLOW_EPI_ROWSTATS || p.epilogue == ACCFLOW_EPI_STORE_T)) {
         // Row-wise epilogues straight from registers (no staging panel): softmax partial statistics of
@@ -711,7 +609,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           if (c + 16 >= cend) {                                  // last TMEM read of this tile
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) release_slot(slot);
+            if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
           }
           if (p.epilogue == ACCFLOW_EPI_ROWSTATS) {
             float sv[16], mx = -INFINITY;
@@ -780,7 +678,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             if (pr == npairs - 1 && xs == nsteps - 1) {            // last TMEM read of this tile
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) release_slot(slot);
+              if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
             }
             if (my_in) {
               float pl[8];
@@ -822,7 +720,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           const int row = 32 * (warp & 3) + itr * 8 + (lane >> 2);
           const int r_slow = (row >> p.tw_shift) + 16 * sub, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
           const int oy = oy0 + (p.mode == 2 ? r_fast : r_slow), ox = ox0 + (p.mode == 2 ? r_slow : r_fast);
-          rok[itr] = oy < p.out_h && ox < p.out_w && !phantom;
+          rok[itr] = oy < p.out_h && ox < p.out_w;
           pix4[itr] = ((long long)sample * p.out_h + oy) * p.out_w + ox;
         }
         for (int c = cbeg; c < cend; c += 16) {
@@ -867,7 +765,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           if (c + 16 >= cend && sub == p.msub - 1) {   // last TMEM read of this tile: hand the slot back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) release_slot(slot);
+            if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
           }
           __syncwarp();                         // the panel rows this warp reads back are the ones it staged
           if (active) {
@@ -934,7 +832,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         if (c + 16 >= cend && sub == p.msub - 1) {   // last TMEM read of this tile: hand the slot back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) release_slot(slot);
+          if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
         }
         __syncwarp();                         // the panel rows this warp reads back are the ones it staged
         const int nb = n0 + c + pc4 * 4;
@@ -948,7 +846,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             const int row = 32 * (warp & 3) + itr * 8 + (lane >> 2);
             const int r_slow = (row >> p.tw_shift) + 16 * sub, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
             const int oy = oy0 + (p.mode == 2 ? r_fast : r_slow), ox = ox0 + (p.mode == 2 ? r_slow : r_fast);
-            if (oy >= p.out_h || ox >= p.out_w || phantom) continue;
+            if (oy >= p.out_h || ox >= p.out_w) continue;
             const long long pix = ((long long)sample * p.out_h + oy) * p.out_w + ox;
             const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
             float y[4] = {fmaf(a4.x, sc[0], sh[0]), fmaf(a4.y, sc[1], sh[1]), fmaf(a4.z, sc[2], sh[2]), fmaf(a4.w, sc[3], sh[3])};
@@ -1019,11 +917,10 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
     }
   }
   __syncthreads();
-  if (PAIR) cluster_sync_all();          // nobody leaves while the peer may still read its smem / signal its barriers
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    if (PAIR) tmem_dealloc2(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -1222,6 +1119,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   p.nplanes = nplanes;
   p.plane_fmt = fp16_single ? ACCFLOW_PLANES_FP16 : nplanes;
   p.fp16 = fp16_ops;
+  const int m_tiles_all = p.tiles_x * p.tiles_y * d.batch;
   // Shift modes (see Params): stride-1 multi-tap convs load each activation box once per K block and
   // serve kh (mode 1) or kw (mode 2) taps from it.  ACCFLOW_TC_SHIFT=0 forces one box per tap.
   static bool shift_env_read = false, shift_enabled = true;
@@ -1243,14 +1141,6 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   // N tile: multiple of 32; the split modes keep two accumulators (MAIN | CORR) x two TMEM slots (BN <= 128).
   const int bn = tc_bn_for(d.cout, nprod);
   p.bn = bn;
-  // CTA pairs (cta_group::2): each CTA of a 2-CTA cluster stages half of every weight tile.  Chosen for the layers whose
-  // operand delivery exceeds what the L2 can feed a single CTA: wide N tiles (the weight tile dominates the bytes per
-  // MMA-clock).  ACCFLOW_TC_PAIR: 0 = never, 1 = heuristic (default), 2 = whenever the shape allows it.
-  int pair_mode = 1;
-  if (const char* e = getenv("ACCFLOW_TC_PAIR")) pair_mode = atoi(e);      // read per call: tests / A-B runs toggle it
-  const int m_tiles_all = p.tiles_x * p.tiles_y * d.batch;
-  const bool pair_ok = !per_sample && nprod != 6 && m_tiles_all >= 2 && bn % 32 == 0 && d.epilogue != ACCFLOW_EPI_STORE_POOL;
-  const bool pair = pair_ok && (pair_mode == 2 || (pair_mode == 1 && bn >= 96 && m_tiles_all >= 296));
   p.n_tiles = cdiv(d.cout, bn);
   // Narrow N tiles in the shift modes: two 128-pixel sub-tiles per CTA tile share every weight tile (the
   // small-channel encoder layers were bound by re-fetching the whole filter from L2 for every 128 pixels).
@@ -1260,13 +1150,13 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     if (!msub_env_read) { if (const char* e = getenv("ACCFLOW_TC_MSUB")) msub_enabled = atoi(e) != 0; msub_env_read = true; }
     const int sub_cols = (nprod > 1 ? 2 : 1) * bn;
     const int slow_extent = p.mode == 1 ? p.out_h : p.out_w;
-    if (msub_enabled && p.mode != 0 && 2 * 2 * sub_cols <= 512 && slow_extent > 16 && m_tiles_all >= 4 * 148) {   // (pairs too)
+    if (msub_enabled && p.mode != 0 && 2 * 2 * sub_cols <= 512 && slow_extent > 16 && m_tiles_all >= 4 * 148) {
       p.msub = 2;
       if (p.mode == 1) { p.tile_h = 32; p.tiles_y = cdiv(p.out_h, 32); } else { p.tile_w = 32; p.tiles_x = cdiv(p.out_w, 32); }
     }
   }
   p.a_plane_bytes = (tc::BM * p.msub + 8 * (p.n_inner - 1)) * tc::KC * 2;
-  const int a_stage = nplanes * p.a_plane_bytes, b_stage = nplanes * (pair ? bn / 2 : bn) * tc::KC * 2;
+  const int a_stage = nplanes * p.a_plane_bytes, b_stage = nplanes * bn * tc::KC * 2;
   const int stage_bytes = a_stage + b_stage;
   const int epi_bytes = 2 * tc::BM * 20 * 4;                 // two 128 x (16+4)-float epilogue panels
   const int ring_bytes = 222 * 1024 - 1024 - epi_bytes;
@@ -1351,7 +1241,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     const cuuint64_t gdim[4] = {(cuuint64_t)w.k, (cuuint64_t)w.rows, (cuuint64_t)w.t, (cuuint64_t)w.nplanes};
     const cuuint64_t gstr[3] = {(cuuint64_t)w.k_pitch * 2, (cuuint64_t)w.k_pitch * 2 * w.rows,
                                 w.plane_stride ? (cuuint64_t)w.plane_stride * 2 : (cuuint64_t)w.k_pitch * 2 * w.rows * w.t};
-    const cuuint32_t box[4] = {(cuuint32_t)tc::KC, (cuuint32_t)(pair ? bn / 2 : bn), 1, (cuuint32_t)nplanes};   // all planes in one op
+    const cuuint32_t box[4] = {(cuuint32_t)tc::KC, (cuuint32_t)bn, 1, (cuuint32_t)nplanes};   // all planes in one op
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult cr = enc(&maps.w, fp16_ops ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w.planes), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
@@ -1386,43 +1276,18 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   int dev = 0;
   cudaGetDevice(&dev);
   if (cfg_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
     if (e != cudaSuccess) return fail((int)e, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
     cfg_dev = dev;
   }
   static thread_local int sm_count = 0;
   if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
-  const bool gru = d.epilogue == ACCFLOW_EPI_GRU_ZR || d.epilogue == ACCFLOW_EPI_GRU_Q;
-  if (pair) {
-    const int m_all = p.tiles_x * p.tiles_y * d.batch;            // (msub may have changed the tile counts)
-    const int pair_tiles = ((m_all + 1) / 2) * p.n_tiles;
-    const int nclusters = pair_tiles < sm_count / 2 ? pair_tiles : sm_count / 2;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * nclusters, 1, 1);
-    cfg.blockDim = dim3(tc::NTHREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = gru ? cudaLaunchKernelEx(&cfg, tc::conv_tc_kernel<true, true>, p, maps)
-                        : cudaLaunchKernelEx(&cfg, tc::conv_tc_kernel<false, true>, p, maps);
-    if (e != cudaSuccess) return fail((int)e, "conv2d_tc: cluster launch failed: %s", cudaGetErrorString(e));
-    return launched("conv2d_tc_pair");
-  }
   const int total_tiles = p.tiles_x * p.tiles_y * d.batch * p.n_tiles;
   dim3 grid(total_tiles < sm_count ? total_tiles : sm_count, 1, 1);
-  if (gru)
-    tc::conv_tc_kernel<true, false><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
+  if (d.epilogue == ACCFLOW_EPI_GRU_ZR || d.epilogue == ACCFLOW_EPI_GRU_Q)
+    tc::conv_tc_kernel<true><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
   else
-    tc::conv_tc_kernel<false, false><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
+    tc::conv_tc_kernel<false><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
   return launched("conv2d_tc");
 }

@@ -145,50 +145,6 @@ def test_gru_epilogues(KP):
     assert maxdiff(hv.t.permute(0, 3, 1, 2), ref) < tol
 
 
-@pytest.mark.parametrize("precision", ["fp16x2", "fp16", "bf16"])
-def test_cta_pair_variant_matches_torch(precision, monkeypatch):
-    """conv_tc_kernel<.., PAIR> (tcgen05 cta_group::2: M = 256 over a 2-CTA cluster, each CTA stages half of every weight
-    tile): forced on (ACCFLOW_TC_PAIR=2) for shift-mode and 1x1 shapes, odd tile counts (phantom half pair), multi-source
-    K, two sub-tiles, and the GRU gate epilogues with the hoisted input term."""
-    from accflow_b200 import _lib as L
-    from accflow_b200.engine import Kernels, PackedConv, View
-    monkeypatch.setenv("ACCFLOW_TC_PAIR", "2")
-    Kp = Kernels(torch.device("cuda:0"), precision)
-    tol = PRECISIONS[precision]
-    g = torch.Generator().manual_seed(21)
-    for (B, cins, H, W, cout, kh, kw) in ((3, [128, 128], 24, 16, 256, 1, 5), (1, [256], 17, 19, 192, 3, 3), (2, [324], 20, 18, 256, 1, 1),
-                                          (1, [128, 128, 128], 40, 24, 128, 5, 1), (2, [64], 200, 200, 64, 3, 3)):
-        xs = [torch.randn(B, c, H, W, generator=g) for c in cins]
-        w = torch.randn(cout, sum(cins), kh, kw, generator=g) / math.sqrt(sum(cins) * kh * kw)
-        b = torch.randn(cout, generator=g)
-        ref = torch.relu(F.conv2d(torch.cat(xs, 1), w, b, padding=(kh // 2, kw // 2)))
-        out = torch.empty(B, H, W, cout, device="cuda")
-        Kp.conv(PackedConv([dev(w)], [dev(b)], 1, (kh // 2, kw // 2)), [View(dev(nhwc(x))) for x in xs], View(out),
-                act=L.ACT_RELU)
-        torch.cuda.synchronize()
-        assert maxdiff(out.permute(0, 3, 1, 2), ref) < tol, (cins, cout, kh, kw)
-    # GRU half-step with the hoisted term through the pair kernel
-    B, H, W = 3, 20, 12
-    h = torch.tanh(torch.randn(B, 128, H, W, generator=g))
-    mf = torch.randn(B, 128, H, W, generator=g)
-    pre_zr_t, pre_q_t = torch.randn(B, 256, H, W, generator=g) * 0.3, torch.randn(B, 128, H, W, generator=g) * 0.3
-    ws = [torch.randn(128, 256, 5, 1, generator=g) * 0.03 for _ in range(3)]
-    bs = [torch.randn(128, generator=g) * 0.1 for _ in range(3)]
-    hx = torch.cat([h, mf], 1)
-    z = torch.sigmoid(F.conv2d(hx, ws[0], bs[0], padding=(2, 0)) + pre_zr_t[:, :128])
-    r = torch.sigmoid(F.conv2d(hx, ws[1], bs[1], padding=(2, 0)) + pre_zr_t[:, 128:])
-    q = torch.tanh(F.conv2d(torch.cat([r * h, mf], 1), ws[2], bs[2], padding=(2, 0)) + pre_q_t)
-    ref = (1 - z) * h + z * q
-    zr = PackedConv([dev(ws[0]), dev(ws[1])], [dev(bs[0]), dev(bs[1])], 1, (2, 0))
-    qc = PackedConv([dev(ws[2])], [dev(bs[2])], 1, (2, 0))
-    hv, mv = View(dev(nhwc(h))), View(dev(nhwc(mf)))
-    zb, rh = View(torch.empty(B, H, W, 128, device="cuda")), View(torch.empty(B, H, W, 128, device="cuda"))
-    Kp.conv(zr, [hv, mv], epilogue=L.EPI_GRU_ZR, h=hv, z=zb, out2=rh, pre_add=View(dev(nhwc(pre_zr_t))))
-    Kp.conv(qc, [rh, mv], epilogue=L.EPI_GRU_Q, h=hv, z=zb, pre_add=View(dev(nhwc(pre_q_t))))
-    torch.cuda.synchronize()
-    assert maxdiff(hv.t.permute(0, 3, 1, 2), ref) < tol
-
-
 def test_gru_hoisted_input_term(KP):
     """The GRU's constant `inp` columns applied once and passed as the pre-activation addend (pre_add) give the
     same half-step as the reference's single convolution over cat[h, inp, mf] (raft/update.py:45-52)."""
