@@ -219,3 +219,30 @@ def test_no_cpu_fallback():
     m = build_flow_estimator("raft")
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 3, 128, 128), torch.zeros(1, 3, 128, 128))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (nn.DataParallel replication)")
+def test_dataparallel_two_gpus_reuses_engines():
+    """test_cvo.py:18,26 wraps the model in nn.DataParallel: on a multi-GPU box every forward re-creates the replicas.
+    The engines (packed weights, workspaces, captured graph) must be cached per device on the SOURCE module and reused
+    by the replicas of later forwards, and the result must equal the single-GPU one."""
+    from accflow_b200 import _lib as L
+    from accflow_b200.networks import build_flow_estimator
+    from accflow_b200.networks.AccFlow_ import AccFlow
+    sd = cases.weights("acc+raft")
+    single = AccFlow(build_flow_estimator("acc|raft"))
+    single.load_state_dict(sd)
+    single = single.cuda().eval()
+    imgs = [torch.cat([t, t.flip(-1)]).cuda() for t in cases.clip_case(frames=3)]      # batch 2 -> one clip per GPU
+    want = single(images=imgs, test_mode=False)[-1]
+    model = torch.nn.DataParallel(AccFlow(build_flow_estimator("acc|raft")).cuda().eval(), device_ids=[0, 1])
+    model.load_state_dict({"module." + k: v for k, v in sd.items()})
+    outs = [model(images=imgs, test_mode=False)[-1] for _ in range(4)]
+    engines = model.module._engines
+    assert len(engines) == 2 and {k[0].index for k in engines} == {0, 1}
+    ids = {k: id(v[1]) for k, v in engines.items()}
+    model(images=imgs, test_mode=False)
+    assert {k: id(v[1]) for k, v in model.module._engines.items()} == ids          # no rebuild on later forwards
+    for o in outs:
+        assert o.shape == (2, 2, 128, 128)
+        assert maxdiff(o, want.cpu()) < 1e-4
