@@ -711,9 +711,15 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         continue;
       }
       if constexpr (GRU) {
+      // GRU gate epilogues (raft/update.py:47-58).  This path is instruction-bound (ncu: the epilogue warps of the hoisted
+      // z|r conv wait for the MMA only 13 % of the time), so it is written for instruction count: 32-bit pixel indices
+      // (one IMAD.WIDE per pointer), rows outside a ragged tile are clamped to the tile's first pixel so that every
+      // load and all the math run unpredicated and only the stores are guarded, and a 16-column step is uniformly in the
+      // z half or the r half.
+      const int hd = p.cout >> 1;
+      const int pix_first = (sample * p.out_h + oy0) * p.out_w + ox0;        // always inside the map
       for (int sub = 0; sub < p.msub; ++sub) {
-        // the four output rows this thread finishes per 16-column step (phase 2): fixed over the steps of a sub-tile
-        long long pix4[4];
+        int pix4[4];
         bool rok[4];
 #pragma unroll
         for (int itr = 0; itr < 4; ++itr) {
@@ -721,29 +727,32 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           const int r_slow = (row >> p.tw_shift) + 16 * sub, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
           const int oy = oy0 + (p.mode == 2 ? r_fast : r_slow), ox = ox0 + (p.mode == 2 ? r_slow : r_fast);
           rok[itr] = oy < p.out_h && ox < p.out_w;
-          pix4[itr] = ((long long)sample * p.out_h + oy) * p.out_w + ox;
+          pix4[itr] = rok[itr] ? (sample * p.out_h + oy) * p.out_w + ox : pix_first;
         }
         for (int c = cbeg; c < cend; c += 16) {
           const int nb = n0 + c + pc4 * 4;
           const bool active = nb < p.cout && !(p.debug & 4);
-          // Global reads of this step (hoisted GRU term, h, z, residual) are issued BEFORE the TMEM load / staging /
-          // warp sync below, all four rows at once: their latency overlaps phase 1 instead of being paid once per row
-          // inside the math (the GRU epilogues were bound by exactly that: 2 exposed L2/DRAM round trips per step).
+          const bool is_q = p.epilogue == ACCFLOW_EPI_GRU_Q;
+          const bool zr_r = !is_q && n0 + c >= hd;              // uniform over the warp: hd % 16 == 0 (host check)
+          // global reads of this step, all four rows, issued before the TMEM load / staging / warp sync below
           float4 ga[4], gb[4], gc[4];
-          const int hd = p.cout >> 1;
-          const bool want_pre = active && p.pre_add != nullptr;
-          const bool zr_r = p.epilogue == ACCFLOW_EPI_GRU_ZR && nb >= hd;
-          const bool want_b = active && (zr_r || p.epilogue == ACCFLOW_EPI_GRU_Q);
-          const bool want_c = active && p.epilogue == ACCFLOW_EPI_GRU_Q;
+          if (active) {
+            if (p.pre_add) {
 #pragma unroll
-          for (int itr = 0; itr < 4; ++itr) {
-            ga[itr] = gb[itr] = gc[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!rok[itr]) continue;
-            if (want_pre) ga[itr] = __ldg(reinterpret_cast<const float4*>(p.pre_add + pix4[itr] * p.pre_ld + nb));
-            if (want_b) {
-              gb[itr] = *reinterpret_cast<const float4*>(p.h + pix4[itr] * p.h_ld + (zr_r ? nb - hd : nb));
+              for (int itr = 0; itr < 4; ++itr)
+                ga[itr] = __ldg(reinterpret_cast<const float4*>(p.pre_add + (size_t)pix4[itr] * p.pre_ld + nb));
             }
-            if (want_c) gc[itr] = __ldg(reinterpret_cast<const float4*>(p.z + pix4[itr] * p.z_ld + nb));
+            if (is_q || zr_r) {
+              const int nh = zr_r ? nb - hd : nb;
+#pragma unroll
+              for (int itr = 0; itr < 4; ++itr)
+                gb[itr] = *reinterpret_cast<const float4*>(p.h + (size_t)pix4[itr] * p.h_ld + nh);
+            }
+            if (is_q) {
+#pragma unroll
+              for (int itr = 0; itr < 4; ++itr)
+                gc[itr] = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)pix4[itr] * p.z_ld + nb));
+            }
           }
           {
             float acc[16];
@@ -771,34 +780,52 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           if (active) {
             const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
             const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[lt & 1][c + pc4 * 4]);
-            const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+            const float* srow = stg + (32 * (warp & 3) + (lane >> 2)) * PITCH + pc4 * 4;
+            float y[4][4];
 #pragma unroll
             for (int itr = 0; itr < 4; ++itr) {
-              if (!rok[itr]) continue;
-              const int row = 32 * (warp & 3) + itr * 8 + (lane >> 2);
-              const long long pix = pix4[itr];
-              const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
-              float y[4] = {fmaf(a4.x, sc[0], sh[0]) + ga[itr].x, fmaf(a4.y, sc[1], sh[1]) + ga[itr].y,
-                            fmaf(a4.z, sc[2], sh[2]) + ga[itr].z, fmaf(a4.w, sc[3], sh[3]) + ga[itr].w};
-              if (p.epilogue == ACCFLOW_EPI_GRU_ZR) {
-                // hd is a multiple of 4 (checked on the host): a group never straddles z | r
-                float g4[4];
+              const float4 a4 = *reinterpret_cast<const float4*>(srow + itr * 8 * PITCH);
+              y[itr][0] = fmaf(a4.x, sc4.x, sh4.x); y[itr][1] = fmaf(a4.y, sc4.y, sh4.y);
+              y[itr][2] = fmaf(a4.z, sc4.z, sh4.z); y[itr][3] = fmaf(a4.w, sc4.w, sh4.w);
+            }
+            if (p.pre_add) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) g4[j] = sigmoid_fast(y[j]);
-                if (nb < hd) {
-                  *reinterpret_cast<float4*>(p.z + pix * p.z_ld + nb) = make_float4(g4[0], g4[1], g4[2], g4[3]);
-                } else {
-                  const int n = nb - hd;
-                  float o[4] = {g4[0] * gb[itr].x, g4[1] * gb[itr].y, g4[2] * gb[itr].z, g4[3] * gb[itr].w};
-                  if (p.out2) *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
-                  if (p.out2_pl.ptr) store_planes4(p.out2_pl, p.plane_fmt, pix, n, o);
-                }
+              for (int itr = 0; itr < 4; ++itr) {
+                y[itr][0] += ga[itr].x; y[itr][1] += ga[itr].y; y[itr][2] += ga[itr].z; y[itr][3] += ga[itr].w;
+              }
+            }
+            if (!is_q) {
+#pragma unroll
+              for (int itr = 0; itr < 4; ++itr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) y[itr][j] = sigmoid_fast(y[itr][j]);
+              }
+              if (!zr_r) {
+#pragma unroll
+                for (int itr = 0; itr < 4; ++itr)
+                  if (rok[itr])
+                    *reinterpret_cast<float4*>(p.z + (size_t)pix4[itr] * p.z_ld + nb) = make_float4(y[itr][0], y[itr][1], y[itr][2], y[itr][3]);
               } else {
+                const int n = nb - hd;
+#pragma unroll
+                for (int itr = 0; itr < 4; ++itr) {
+                  float o[4] = {y[itr][0] * gb[itr].x, y[itr][1] * gb[itr].y, y[itr][2] * gb[itr].z, y[itr][3] * gb[itr].w};
+                  if (rok[itr]) {
+                    if (p.out2) *reinterpret_cast<float4*>(p.out2 + (size_t)pix4[itr] * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (p.out2_pl.ptr) store_planes4(p.out2_pl, p.plane_fmt, pix4[itr], n, o);
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int itr = 0; itr < 4; ++itr) {
                 const float4 zz = gc[itr], hh = gb[itr];
-                float o[4] = {fmaf(zz.x, tanh_fast(y[0]) - hh.x, hh.x), fmaf(zz.y, tanh_fast(y[1]) - hh.y, hh.y),
-                              fmaf(zz.z, tanh_fast(y[2]) - hh.z, hh.z), fmaf(zz.w, tanh_fast(y[3]) - hh.w, hh.w)};
-                *reinterpret_cast<float4*>(p.h + pix * p.h_ld + nb) = make_float4(o[0], o[1], o[2], o[3]);
-                if (p.h_pl.ptr) store_planes4(p.h_pl, p.plane_fmt, pix, nb, o);
+                float o[4] = {fmaf(zz.x, tanh_fast(y[itr][0]) - hh.x, hh.x), fmaf(zz.y, tanh_fast(y[itr][1]) - hh.y, hh.y),
+                              fmaf(zz.z, tanh_fast(y[itr][2]) - hh.z, hh.z), fmaf(zz.w, tanh_fast(y[itr][3]) - hh.w, hh.w)};
+                if (rok[itr]) {
+                  *reinterpret_cast<float4*>(p.h + (size_t)pix4[itr] * p.h_ld + nb) = make_float4(o[0], o[1], o[2], o[3]);
+                  if (p.h_pl.ptr) store_planes4(p.h_pl, p.plane_fmt, pix4[itr], nb, o);
+                }
               }
             }
           }
@@ -806,7 +833,20 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         }
       }
       } else {
-      for (int sub = 0; sub < p.msub; ++sub)
+      const int pix_first = (sample * p.out_h + oy0) * p.out_w + ox0;        // always inside the map
+      for (int sub = 0; sub < p.msub; ++sub) {
+        // the four output rows this thread finishes per 16-column step: 32-bit pixel indices, rows outside a ragged tile
+        // clamped to the tile's first pixel (loads and math run unpredicated, only the stores are guarded)
+        int pix4[4];
+        bool rok[4];
+#pragma unroll
+        for (int itr = 0; itr < 4; ++itr) {
+          const int row = 32 * (warp & 3) + itr * 8 + (lane >> 2);
+          const int r_slow = (row >> p.tw_shift) + 16 * sub, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
+          const int oy = oy0 + (p.mode == 2 ? r_fast : r_slow), ox = ox0 + (p.mode == 2 ? r_slow : r_fast);
+          rok[itr] = oy < p.out_h && ox < p.out_w;
+          pix4[itr] = rok[itr] ? (sample * p.out_h + oy) * p.out_w + ox : pix_first;
+        }
       for (int c = cbeg; c < cend; c += 16) {
         {
           float acc[16];
@@ -839,79 +879,69 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         if (nb < p.cout && !(p.debug & 4)) {
           const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
           const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[lt & 1][c + pc4 * 4]);
-          const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
-          const bool vec4 = nb + 3 < p.cout;
-#pragma unroll 2
-          for (int itr = 0; itr < 4; ++itr) {
-            const int row = 32 * (warp & 3) + itr * 8 + (lane >> 2);
-            const int r_slow = (row >> p.tw_shift) + 16 * sub, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
-            const int oy = oy0 + (p.mode == 2 ? r_fast : r_slow), ox = ox0 + (p.mode == 2 ? r_slow : r_fast);
-            if (oy >= p.out_h || ox >= p.out_w) continue;
-            const long long pix = ((long long)sample * p.out_h + oy) * p.out_w + ox;
-            const float4 a4 = *reinterpret_cast<const float4*>(stg + row * PITCH + pc4 * 4);
-            float y[4] = {fmaf(a4.x, sc[0], sh[0]), fmaf(a4.y, sc[1], sh[1]), fmaf(a4.z, sc[2], sh[2]), fmaf(a4.w, sc[3], sh[3])};
-            if (p.pre_add) {
-              const float4 pa = __ldg(reinterpret_cast<const float4*>(p.pre_add + pix * p.pre_ld + nb));
-              y[0] += pa.x; y[1] += pa.y; y[2] += pa.z; y[3] += pa.w;
-            }
-            if (p.epilogue == ACCFLOW_EPI_STORE) {
-              if (p.out_vec && vec4) {
+          const float* srow = stg + (32 * (warp & 3) + (lane >> 2)) * PITCH + pc4 * 4;
+          if (p.out_vec && nb + 3 < p.cout) {
+            // fast path: four whole channels per thread and row, one destination
+#pragma unroll
+            for (int itr = 0; itr < 4; ++itr) {
+              const size_t pix = (size_t)pix4[itr];
+              const float4 a4 = *reinterpret_cast<const float4*>(srow + itr * 8 * PITCH);
+              float y[4] = {fmaf(a4.x, sc4.x, sh4.x), fmaf(a4.y, sc4.y, sh4.y), fmaf(a4.z, sc4.z, sh4.z), fmaf(a4.w, sc4.w, sh4.w)};
+              if (p.pre_add) {
+                const float4 pa = __ldg(reinterpret_cast<const float4*>(p.pre_add + pix * p.pre_ld + nb));
+                y[0] += pa.x; y[1] += pa.y; y[2] += pa.z; y[3] += pa.w;
+              }
+              if (p.act == ACCFLOW_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
+              } else if (p.act != ACCFLOW_ACT_NONE) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) y[j] = act_apply(y[j], p.act);
-                if (p.residual) {
-                  const float4 r = *reinterpret_cast<const float4*>(p.residual + pix * p.res_ld + nb);
-                  y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
-                }
-                if (p.post_relu) {
+              }
+              if (p.residual) {
+                const float4 r = *reinterpret_cast<const float4*>(p.residual + pix * p.res_ld + nb);
+                y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
+              }
+              if (p.post_relu) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
-                }
+                for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
+              }
+              if (rok[itr]) {
                 if (p.out) *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
                 if (p.out_pl.ptr) store_planes4(p.out_pl, p.plane_fmt, pix, nb, y);
-              } else {
+              }
+            }
+          } else {
+            // general path: ragged channel tail, tanh | relu split into two destinations (cnet head), unaligned slices
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int n = nb + j;
-                  if (n < p.cout) {
-                    const bool second = p.act_split > 0 && n >= p.act_split;
-                    float o = act_apply(y[j], second ? p.act2 : p.act);
-                    if (p.residual) o += p.residual[pix * p.res_ld + n];
-                    if (p.post_relu) o = fmaxf(o, 0.f);
-                    if (second && p.out2) {
-                      p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
-                      if (p.out2_pl.ptr) store_planes1(p.out2_pl, p.plane_fmt, pix, n - p.act_split, o);
-                    } else {
-                      if (p.out) p.out[pix * p.out_ld + n] = o;
-                      if (p.out_pl.ptr) store_planes1(p.out_pl, p.plane_fmt, pix, n, o);
-                    }
+            for (int itr = 0; itr < 4; ++itr) {
+              if (!rok[itr]) continue;
+              const size_t pix = (size_t)pix4[itr];
+              const float4 a4 = *reinterpret_cast<const float4*>(srow + itr * 8 * PITCH);
+              float y[4] = {fmaf(a4.x, sc4.x, sh4.x), fmaf(a4.y, sc4.y, sh4.y), fmaf(a4.z, sc4.z, sh4.z), fmaf(a4.w, sc4.w, sh4.w)};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int n = nb + j;
+                if (n < p.cout) {
+                  const bool second = p.act_split > 0 && n >= p.act_split;
+                  float o = y[j] + (p.pre_add ? __ldg(p.pre_add + pix * p.pre_ld + n) : 0.f);
+                  o = act_apply(o, second ? p.act2 : p.act);
+                  if (p.residual) o += p.residual[pix * p.res_ld + n];
+                  if (p.post_relu) o = fmaxf(o, 0.f);
+                  if (second && p.out2) {
+                    p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
+                    if (p.out2_pl.ptr) store_planes1(p.out2_pl, p.plane_fmt, pix, n - p.act_split, o);
+                  } else {
+                    if (p.out) p.out[pix * p.out_ld + n] = o;
+                    if (p.out_pl.ptr) store_planes1(p.out_pl, p.plane_fmt, pix, n, o);
                   }
                 }
               }
-            } else if (p.epilogue == ACCFLOW_EPI_GRU_ZR) {
-              const int hd = p.cout >> 1;   // multiple of 4 (checked on the host): a group never straddles z | r
-              float g4[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) g4[j] = 1.f / (1.f + expf(-y[j]));
-              if (nb < hd) {
-                *reinterpret_cast<float4*>(p.z + pix * p.z_ld + nb) = make_float4(g4[0], g4[1], g4[2], g4[3]);
-              } else {
-                const int n = nb - hd;
-                const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + n);
-                float o[4] = {g4[0] * hh.x, g4[1] * hh.y, g4[2] * hh.z, g4[3] * hh.w};
-                if (p.out2) *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
-                if (p.out2_pl.ptr) store_planes4(p.out2_pl, p.plane_fmt, pix, n, o);
-              }
-            } else {
-              const float4 zz = *reinterpret_cast<const float4*>(p.z + pix * p.z_ld + nb);
-              const float4 hh = *reinterpret_cast<const float4*>(p.h + pix * p.h_ld + nb);
-              float o[4] = {(1.f - zz.x) * hh.x + zz.x * tanhf(y[0]), (1.f - zz.y) * hh.y + zz.y * tanhf(y[1]),
-                            (1.f - zz.z) * hh.z + zz.z * tanhf(y[2]), (1.f - zz.w) * hh.w + zz.w * tanhf(y[3])};
-              *reinterpret_cast<float4*>(p.h + pix * p.h_ld + nb) = make_float4(o[0], o[1], o[2], o[3]);
-              if (p.h_pl.ptr) store_planes4(p.h_pl, p.plane_fmt, pix, nb, o);
             }
           }
         }
         __syncwarp();
+      }
       }
       }
     }
@@ -1105,6 +1135,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   p.out_h = (d.in_h + 2 * d.pad_h - d.kh) / d.stride + 1;
   p.out_w = (d.in_w + 2 * d.pad_w - d.kw) / d.stride + 1;
   ACCFLOW_REQUIRE(p.out_h > 0 && p.out_w > 0, "conv2d_tc: empty output");
+  ACCFLOW_REQUIRE((long long)d.batch * p.out_h * p.out_w < (1ll << 31), "conv2d_tc: more than 2^31 output pixels");
   ACCFLOW_REQUIRE(d.out_h >= 0 && d.out_h <= p.out_h && d.out_w >= 0 && d.out_w <= p.out_w, "conv2d_tc: out_h / out_w exceed the output map");
   if (d.out_h) p.out_h = d.out_h;
   if (d.out_w) p.out_w = d.out_w;
@@ -1187,8 +1218,8 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   if (d.epilogue == ACCFLOW_EPI_STORE) {
     ACCFLOW_REQUIRE(d.out != nullptr || io.out_planes != nullptr, "conv2d_tc: null output (fp32 and planes)");
   } else if (d.epilogue == ACCFLOW_EPI_GRU_ZR) {
-    ACCFLOW_REQUIRE(d.z && d.h && (d.out2 || io.out2_planes) && d.cout % 8 == 0,
-                    "conv2d_tc: GRU_ZR needs z, h, out2 (fp32 and/or planes) and cout % 8 == 0");
+    ACCFLOW_REQUIRE(d.z && d.h && (d.out2 || io.out2_planes) && d.cout % 32 == 0,
+                    "conv2d_tc: GRU_ZR needs z, h, out2 (fp32 and/or planes) and cout % 32 == 0");
     ACCFLOW_REQUIRE(aligned16(d.z) && aligned16(d.h) && aligned16(d.out2) && d.z_ld % 4 == 0 && d.h_ld % 4 == 0 &&
                         (!d.out2 || d.out2_ld % 4 == 0), "conv2d_tc: GRU buffers must be 16B aligned");
   } else if (d.epilogue == ACCFLOW_EPI_GRU_Q) {
