@@ -376,111 +376,6 @@ __global__ void __launch_bounds__(256) corr_lookup_fast_kernel(const LookupP p) 
   }
 }
 
-// 16-byte-gather variant of corr_lookup_fast_kernel for maps whose level widths are all multiples of 4 (w % 32 == 0:
-// the 512x512 and 1024x1024 configurations).  The previous version requested every texel of the (2R+4)^2 patches with a
-// 4-byte cp.async (576 per source pixel): ncu showed 2.0x the algorithmic DRAM bytes (48-byte patch rows straddle
-// 32-byte sectors at arbitrary offsets and every partial sector was requested texel by texel) and an LSU-bound issue
-// stream.  Here a patch row is the 16-float run that starts at the 16-byte-aligned column at or below the window's
-// first texel: four 16-byte cp.async.cg per row (L2 only - no reuse, nothing for L1 to keep), 192 requests per pixel
-// instead of 576, all four levels in flight together; a chunk is entirely inside or entirely outside the map
-// (zero-filled), so the zero padding of grid_sample costs nothing.  Arithmetic per tap is unchanged.
-template <int R>
-__global__ void __launch_bounds__(256) corr_lookup_vec_kernel(const LookupP p) {
-  constexpr int K1 = 2 * R + 1, K2 = K1 * K1, PD = K1 + 3, PW = 16, NIT = (K2 + 31) / 32;
-  constexpr int SLOTS = PD * 4, NLOAD = (4 * SLOTS + 31) / 32;       // (row, 16-byte chunk) slots per level
-  static_assert(PD + 3 <= PW, "a patch row must fit 16 floats after aligning its start down to a multiple of 4");
-  __shared__ __align__(16) float patch[8][4][PD * PW];
-  __shared__ float4 axis[8][2][16];             // (patch index, w0, w1, valid) per window column / row
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long pix = (long long)blockIdx.x * 8 + wib;
-  if (pix >= (long long)p.batch * p.h * p.w) return;
-  const float cx = __ldg(p.coords + pix * 2), cy = __ldg(p.coords + pix * 2 + 1);
-  float* orow = p.out ? p.out + pix * p.out_ld : nullptr;        // NULL: planes only (the tensor-core convc1 reads nothing else)
-  __nv_bfloat16* prow = p.out_pl ? p.out_pl + pix * p.pl_pitch : nullptr;
-  int tap_q[NIT];                               // (a, b) of every tap this lane owns: channel t = a*K1 + b
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int t = lane + 32 * it;
-    tap_q[it] = ((t / K1) << 8) | (t % K1);
-  }
-  int xs[4], y0[4];                             // patch origin per level: aligned first column, first row
-#pragma unroll
-  for (int lvl = 0; lvl < 4; ++lvl) {
-    const float inv = 1.f / (float)(1 << lvl);
-    const float fxo = floorf(fminf(fmaxf(cx * inv, -1.0e6f), 1.0e6f)), fyo = floorf(fminf(fmaxf(cy * inv, -1.0e6f), 1.0e6f));
-    xs[lvl] = ((int)fxo - R - 1) & ~3;          // one texel of slack on each side of the nominal window, then aligned down
-    y0[lvl] = (int)fyo - R - 1;
-  }
-#pragma unroll
-  for (int k = 0; k < NLOAD; ++k) {
-    const int s = lane + 32 * k;
-    if (s < 4 * SLOTS) {
-      const int lvl = s / SLOTS, wi = s - lvl * SLOTS, yy = wi >> 2, ch = wi & 3;
-      const int H = p.lh[lvl], W = p.lw[lvl];
-      const int gx = xs[lvl] + 4 * ch, gy = y0[lvl] + yy;
-      const bool ok = gx >= 0 && gx + 4 <= W && gy >= 0 && gy < H;
-      const float* img = p.lvl[lvl] + pix * (long long)(H * W);
-      const float* src = ok ? img + gy * W + gx : img;
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&patch[wib][lvl][yy * PW + 4 * ch]);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
-    }
-  }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncwarp();
-  const int xx = lane & 15, yh = lane >> 4;
-#pragma unroll 1
-  for (int lvl = 0; lvl < 4; ++lvl) {
-    const int H = p.lh[lvl], W = p.lw[lvl];
-    const float inv = 1.f / (float)(1 << lvl);
-    const float bx = cx * inv, by = cy * inv;
-    const float* pt = patch[wib][lvl];
-    if (xx < K1) {                              // lanes 0..K1-1: window columns (x); lanes 16..16+K1-1: rows (y)
-      const int size = yh ? H : W, org = yh ? y0[lvl] : xs[lvl], lim = yh ? PD : PW;
-      const float c = grid_roundtrip(__fadd_rn(yh ? by : bx, (float)(xx - R)), size);
-      const float cf = floorf(c);
-      const bool in_range = c > -2.f && c < (float)size + 1.f;
-      const int idx = in_range ? (int)cf - org : -1;
-      // idx must address a 2-texel run inside the patch; otherwise the tap is outside the map for every finite
-      // coordinate (the patch has a texel of slack), so it contributes zero
-      const bool ok = in_range && idx >= 0 && idx + 1 < lim;
-      axis[wib][yh][xx] = make_float4(__int_as_float(ok ? idx : 0), (cf + 1.f) - c, c - cf, ok ? 1.f : 0.f);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int t = lane + 32 * it;
-      if (t < K2) {
-        const float4 ex = axis[wib][0][tap_q[it] >> 8], ey = axis[wib][1][tap_q[it] & 255];
-        float v = 0.f;
-        if (ex.w != 0.f && ey.w != 0.f) {
-          const float* q = pt + __float_as_int(ey.x) * PW + __float_as_int(ex.x);
-          v = q[0] * (ex.y * ey.y);
-          v += q[1] * (ex.z * ey.y);
-          v += q[PW] * (ex.y * ey.z);
-          v += q[PW + 1] * (ex.z * ey.z);
-        }
-        if (orow) orow[t] = v;
-        if (prow) store_planes(prow + t, p.pl_stride, p.nplanes, v);
-      }
-    }
-    __syncwarp();                               // axis[] is rewritten by the next level
-    if (orow) orow += K2;
-    if (prow) prow += K2;
-  }
-  if (lane == 0) {
-    const int pl = (int)(pix % ((long long)p.h * p.w));
-    const float fx = cx - (float)(pl % p.w), fy = cy - (float)(pl / p.w);
-    if (p.flow_out) { p.flow_out[pix * 2] = fx; p.flow_out[pix * 2 + 1] = fy; }
-    if (p.mf_tail) {
-      p.mf_tail[pix * p.mf_ld] = fx; p.mf_tail[pix * p.mf_ld + 1] = fy;
-      if (p.tail_pl) {
-        store_planes(p.tail_pl + pix * p.tail_pitch, p.tail_stride, p.nplanes, fx);
-        store_planes(p.tail_pl + pix * p.tail_pitch + 1, p.tail_stride, p.nplanes, fy);
-      }
-    }
-  }
-}
-
 __global__ void coords_init_kernel(const float* __restrict__ finit, int batch, int h, int w, float* __restrict__ coords) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   const int hw = h * w;
@@ -863,11 +758,7 @@ extern "C" int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, con
   ACCFLOW_REQUIRE((!out_planes && !tail_planes) || valid_plane_fmt(nplanes), "corr_lookup: bad plane format");
   p.out_pl = reinterpret_cast<__nv_bfloat16*>(out_planes); p.pl_pitch = pl_pitch; p.pl_stride = pl_stride; p.nplanes = nplanes;
   p.tail_pl = reinterpret_cast<__nv_bfloat16*>(tail_planes); p.tail_pitch = tail_pitch; p.tail_stride = tail_stride;
-  const char* vec_env = getenv("ACCFLOW_LOOKUP_VEC");      // read per call: A/B experiments toggle it in-process
-  const bool vec_off = vec_env && atoi(vec_env) == 0;
-  const bool vec_ok = !vec_off && w % 32 == 0 && aligned16(lvl0) && aligned16(lvl1) && aligned16(lvl2) && aligned16(lvl3);
-  if (radius == 4 && vec_ok) corr_lookup_vec_kernel<4><<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(p);   // 16-byte gathers
-  else if (radius == 4) corr_lookup_fast_kernel<4><<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(p);     // RAFT / GMA
+  if (radius == 4) corr_lookup_fast_kernel<4><<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(p);     // RAFT / GMA
   else corr_lookup_kernel<0><<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(p);
   return launched("corr_lookup");
 }

@@ -1,6 +1,6 @@
 """One launch of each kernel of interest at bench shape between cudaProfilerStart/Stop, for
   ncu --set full --import-source on --clock-control none --profile-from-start off -o gpurun_out/X python scripts/ncu_targets.py <targets>
-Targets: gru_zr gru_q convc2 enc1 stem convc1 lookup_vec lookup_fast corr_gemm attn agg"""
+Targets: gru_zr gru_q convc2 enc1 stem convc1 lookup corr_gemm attn agg"""
 import math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,7 +8,7 @@ from accflow_b200 import _lib as L
 from accflow_b200.engine import FlowEstimatorEngine, Kernels, PackedConv, PlanesOnly, View
 
 torch.set_grad_enabled(False)
-targets = sys.argv[1:] or ["gru_zr", "convc2", "lookup_vec", "lookup_fast", "corr_gemm"]
+targets = sys.argv[1:] or ["gru_zr", "convc2", "lookup", "corr_gemm"]
 K = Kernels(torch.device("cuda:0"), os.environ.get("NCU_PREC", "fp16x2"))
 B, h, w = int(os.environ.get("NCU_PAIRS", "18")), 64, 64
 g = torch.Generator().manual_seed(0)
@@ -53,8 +53,7 @@ for t in targets:
         K.ensure_planes(x)
         pc = wz(64, 64, 3, 3)
         profiled(lambda: K.conv(pc, [x], out, emit_planes=False))
-    elif t in ("lookup_vec", "lookup_fast"):
-        os.environ["ACCFLOW_LOOKUP_VEC"] = "1" if t == "lookup_vec" else "0"
+    elif t == "lookup":
         P = h * w
         lv = [torch.randn(B * P, (h >> l) * (w >> l), device="cuda") for l in range(4)]
         coords = (torch.rand(B, P, 2, device="cuda") * 8 - 4) + torch.stack(torch.meshgrid(torch.arange(w), torch.arange(h), indexing="xy"), -1).reshape(1, P, 2).float().cuda()

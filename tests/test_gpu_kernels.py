@@ -276,9 +276,9 @@ def test_corr_pyramid_and_lookup(KP, golden):
 
 
 @pytest.mark.parametrize("hw", [(16, 32), (64, 64), (24, 96)])
-def test_corr_lookup_16byte_gather_path(hw):
-    """CorrBlock.__call__ (raft/corr.py:24-45) on maps whose widths are multiples of 32 (512x512 / 1024x1024
-    configurations): the 16-byte-gather kernel vs the oracle, coordinates far outside the map included."""
+def test_corr_lookup_bench_shaped_maps(hw):
+    """CorrBlock.__call__ (raft/corr.py:24-45) on maps whose widths are multiples of 32 (the 512x512 / 1024x1024
+    configurations) vs the oracle, coordinates far outside the map and exactly integer coordinates included."""
     from accflow_b200 import _lib as L
     from oracle import ops
     h, w = hw
