@@ -407,8 +407,8 @@ def run_b200(args):
         if os.path.exists(tfile):
             t = json.loads(open(tfile).readline())
             traffic = (t["dram_read_MB"] + t["dram_write_MB"]) * 1e6
-            traffic_note = (f"STATIC, not measured in this run: dram__bytes_read+write of one GRU z|r conv launch (1x5, 8 pairs x "
-                            f"64x64; `ncu --set full`) from profiles/{name}")
+            traffic_note = (f"STATIC, not measured in this run: dram__bytes_read+write of one GRU z|r conv launch (1x5, "
+                            f"{'18' if name.startswith('r2_') else '8'} pairs x 64x64; `ncu --set full`) from profiles/{name}")
             break
     roofline = {"bound": "tensor", "kernel": kname, "issued_mma_tflops": issued, "issued_frac": issued / pk["bf16_tflops_sustained"],
                 "traffic_note": traffic_note,
