@@ -355,8 +355,12 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
 // GRU = true: the instantiation for the GRU gate epilogues (its phase 2 issues all global reads of a 16-column step - the
 // hoisted input term, h, z - before the TMEM load; 48 more live registers, which the plain-store instantiation must
 // not pay: at 10 warps the allocator's ceiling is 168 registers per thread).
-template <bool GRU>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// TEAMS = 2 (GRU epilogues): two teams of eight epilogue warps, team k draining the tiles that accumulate in TMEM slot k,
+// so that TWO epilogues are in flight (the gate epilogues are issue/latency-bound with two warps per scheduler and take
+// longer than the main loop of these K = 256 layers).  18 warps cap the allocator at 96 registers per thread: this
+// variant loads its global operands where they are used instead of ahead of the TMEM stage.
+template <bool GRU, int TEAMS>
+__global__ void __launch_bounds__(64 + 256 * TEAMS, 1)
 conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPack maps) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t bar_afull[MAX_STAGES], bar_afree[MAX_STAGES], bar_bfull[MAX_B_STAGES],
@@ -560,14 +564,15 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
     // ================================ epilogue ================================================
     // Phase 1: TMEM -> registers (MAIN + CORR) -> padded smem panel (16 columns).  Phase 2: coalesced
     // global traffic with the affine / activation / GRU math, fp32 stores + bf16 planes.
-    const int half = (warp - 2) >> 2;
-    float* stg = stg_base + half * (BM * PITCH);
+    const int team = TEAMS == 2 ? (warp - 2) >> 3 : 0;
+    const int half = ((warp - 2) >> 2) & 1;
+    float* stg = stg_base + (team * 2 + half) * (BM * PITCH);
     const int trow = 32 * (warp & 3) + lane;                    // TMEM lane owned by this thread
-    const int st = tid - 64 - 128 * half;                       // 0..127 inside this warp set
-    const int pc4 = st & 3;                                     // float4 group inside the 16-column panel
+    const int pc4 = lane & 3;                                   // float4 group inside the 16-column panel
     const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      if (TEAMS == 2 && (lt & 1) != team) continue;             // team k owns the tiles of TMEM slot k
       const int n_tile = tile / m_tiles;
       int t = tile - n_tile * m_tiles;
       const int tile_x = t % p.tiles_x; t /= p.tiles_x;
@@ -576,7 +581,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       const int ox0 = tile_x * p.tile_w, oy0 = tile_y * p.tile_h, n0 = n_tile * BN;
       const int slot = lt & 1, use = lt >> 1;
       {  // stage this tile's scale / shift (global-load latency off the per-panel critical path)
-        const int et = tid - 64;                                  // 0..255
+        const int et = (tid - 64) & 255;                          // 0..255 inside this team
         if (et < BN) {
           const int n = n0 + et;
           const bool ok = n < p.cout;
@@ -586,7 +591,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       }
       mbar_wait(&bar_acc_full[slot], use & 1);
       tc_fence_after();
-      asm volatile("bar.sync 3, 256;" ::: "memory");             // staged affine visible to both warp sets
+      asm volatile("bar.sync %0, 256;" ::"r"(3 + team) : "memory");   // staged affine visible to both warp sets of the team
       const uint32_t lane_addr = tmem_base + slot * acc_cols + ((uint32_t)(32 * (warp & 3)) << 16);
       // this thread's own output row (TMEM lane), mode 0 tiles: used by the row-wise epilogues below
       const int own_oy = oy0 + (trow >> p.tw_shift), own_ox = ox0 + (trow & (p.tw - 1));
@@ -736,7 +741,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           const bool zr_r = !is_q && n0 + c >= hd;              // uniform over the warp: hd % 16 == 0 (host check)
           // global reads of this step, all four rows, issued before the TMEM load / staging / warp sync below
           float4 ga[4], gb[4], gc[4];
-          if (active) {
+          auto load_operands = [&]() {
             if (p.pre_add) {
 #pragma unroll
               for (int itr = 0; itr < 4; ++itr)
@@ -753,7 +758,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
               for (int itr = 0; itr < 4; ++itr)
                 gc[itr] = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)pix4[itr] * p.z_ld + nb));
             }
-          }
+          };
+          if (TEAMS == 1 && active) load_operands();          // one team: ahead of the TMEM stage (latency hiding)
           {
             float acc[16];
             if (p.debug & 8) {
@@ -778,6 +784,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           }
           __syncwarp();                         // the panel rows this warp reads back are the ones it staged
           if (active) {
+            if (TEAMS == 2) load_operands();                    // two teams: 16 warps hide the latency, 96 registers
             const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
             const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[lt & 1][c + pc4 * 4]);
             const float* srow = stg + (32 * (warp & 3) + (lane >> 2)) * PITCH + pc4 * 4;
@@ -1189,7 +1196,11 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   p.a_plane_bytes = (tc::BM * p.msub + 8 * (p.n_inner - 1)) * tc::KC * 2;
   const int a_stage = nplanes * p.a_plane_bytes, b_stage = nplanes * bn * tc::KC * 2;
   const int stage_bytes = a_stage + b_stage;
-  const int epi_bytes = 2 * tc::BM * 20 * 4;                 // two 128 x (16+4)-float epilogue panels
+  const bool gru_epi = d.epilogue == ACCFLOW_EPI_GRU_ZR || d.epilogue == ACCFLOW_EPI_GRU_Q;
+  int gru_teams = 2;                                         // ACCFLOW_TC_GRU_TEAMS=1: one team of 8 epilogue warps (A/B runs)
+  if (const char* e = getenv("ACCFLOW_TC_GRU_TEAMS")) gru_teams = atoi(e) == 1 ? 1 : 2;
+  const int teams = gru_epi ? gru_teams : 1;
+  const int epi_bytes = teams * 2 * tc::BM * 20 * 4;         // two 128 x (16+4)-float epilogue panels per team
   const int ring_bytes = 222 * 1024 - 1024 - epi_bytes;
   int stages = ring_bytes / stage_bytes, stages_b;
   if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
@@ -1307,8 +1318,9 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   int dev = 0;
   cudaGetDevice(&dev);
   if (cfg_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
     if (e != cudaSuccess) return fail((int)e, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
     cfg_dev = dev;
   }
@@ -1316,9 +1328,11 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
   const int total_tiles = p.tiles_x * p.tiles_y * d.batch * p.n_tiles;
   dim3 grid(total_tiles < sm_count ? total_tiles : sm_count, 1, 1);
-  if (d.epilogue == ACCFLOW_EPI_GRU_ZR || d.epilogue == ACCFLOW_EPI_GRU_Q)
-    tc::conv_tc_kernel<true><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
+  if (gru_epi && teams == 2)
+    tc::conv_tc_kernel<true, 2><<<grid, 64 + 256 * 2, smem, (cudaStream_t)stream>>>(p, maps);
+  else if (gru_epi)
+    tc::conv_tc_kernel<true, 1><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
   else
-    tc::conv_tc_kernel<false><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
+    tc::conv_tc_kernel<false, 1><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
   return launched("conv2d_tc");
 }
