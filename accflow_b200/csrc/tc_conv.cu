@@ -60,6 +60,7 @@ struct Params {
   int msub;    // shift modes, narrow N tiles: 128-pixel sub-tiles per CTA tile (stacked along the slow axis, one
                // activation box); every weight tile is used msub times, i.e. 1/msub of the weight bytes per pixel
   int pool_w;  // ACCFLOW_EPI_STORE_POOL: width of the map the N axis is a row-major view of
+  int tma_store;  // ACCFLOW_EPI_STORE_POOL: level 0 leaves through 32 x 32 fp32 TMA store boxes (maps.out)
   int debug;   // perf experiments only (ACCFLOW_TC_DEBUG): bit 0 = no TMA loads, bit 1 = no MMAs (results are garbage)
   float alpha;
   const float* scale;
@@ -79,6 +80,7 @@ struct Params {
 struct alignas(64) TmapPack {
   CUtensorMap w;
   CUtensorMap a[ACCFLOW_MAX_SRC];
+  CUtensorMap out;   // STORE_POOL with tma_store: the level-0 volume [B*P rows][P cols] fp32, box 32 x 32, SWIZZLE_128B
 };
 
 // ---------------------------------------------------------------------------------- PTX helpers
@@ -146,6 +148,14 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+
+// TMA store of one 2-D box from shared memory (bulk async group), and the group bookkeeping around it
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
@@ -355,12 +365,8 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
 // GRU = true: the instantiation for the GRU gate epilogues (its phase 2 issues all global reads of a 16-column step - the
 // hoisted input term, h, z - before the TMEM load; 48 more live registers, which the plain-store instantiation must
 // not pay: at 10 warps the allocator's ceiling is 168 registers per thread).
-// TEAMS = 2 (GRU epilogues): two teams of eight epilogue warps, team k draining the tiles that accumulate in TMEM slot k,
-// so that TWO epilogues are in flight (the gate epilogues are issue/latency-bound with two warps per scheduler and take
-// longer than the main loop of these K = 256 layers).  18 warps cap the allocator at 96 registers per thread: this
-// variant loads its global operands where they are used instead of ahead of the TMEM stage.
-template <bool GRU, int TEAMS>
-__global__ void __launch_bounds__(64 + 256 * TEAMS, 1)
+template <bool GRU>
+__global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPack maps) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t bar_afull[MAX_STAGES], bar_afree[MAX_STAGES], bar_bfull[MAX_B_STAGES],
@@ -564,15 +570,14 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
     // ================================ epilogue ================================================
     // Phase 1: TMEM -> registers (MAIN + CORR) -> padded smem panel (16 columns).  Phase 2: coalesced
     // global traffic with the affine / activation / GRU math, fp32 stores + bf16 planes.
-    const int team = TEAMS == 2 ? (warp - 2) >> 3 : 0;
-    const int half = ((warp - 2) >> 2) & 1;
-    float* stg = stg_base + (team * 2 + half) * (BM * PITCH);
+    const int half = (warp - 2) >> 2;
+    float* stg = stg_base + half * (BM * PITCH);
     const int trow = 32 * (warp & 3) + lane;                    // TMEM lane owned by this thread
-    const int pc4 = lane & 3;                                   // float4 group inside the 16-column panel
+    const int st = tid - 64 - 128 * half;                       // 0..127 inside this warp set
+    const int pc4 = st & 3;                                     // float4 group inside the 16-column panel
     const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      if (TEAMS == 2 && (lt & 1) != team) continue;             // team k owns the tiles of TMEM slot k
       const int n_tile = tile / m_tiles;
       int t = tile - n_tile * m_tiles;
       const int tile_x = t % p.tiles_x; t /= p.tiles_x;
@@ -581,7 +586,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       const int ox0 = tile_x * p.tile_w, oy0 = tile_y * p.tile_h, n0 = n_tile * BN;
       const int slot = lt & 1, use = lt >> 1;
       {  // stage this tile's scale / shift (global-load latency off the per-panel critical path)
-        const int et = (tid - 64) & 255;                          // 0..255 inside this team
+        const int et = tid - 64;                                  // 0..255
         if (et < BN) {
           const int n = n0 + et;
           const bool ok = n < p.cout;
@@ -591,7 +596,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       }
       mbar_wait(&bar_acc_full[slot], use & 1);
       tc_fence_after();
-      asm volatile("bar.sync %0, 256;" ::"r"(3 + team) : "memory");   // staged affine visible to both warp sets of the team
+      asm volatile("bar.sync 3, 256;" ::: "memory");             // staged affine visible to both warp sets
       const uint32_t lane_addr = tmem_base + slot * acc_cols + ((uint32_t)(32 * (warp & 3)) << 16);
       // this thread's own output row (TMEM lane), mode 0 tiles: used by the row-wise epilogues below
       const int own_oy = oy0 + (trow >> p.tw_shift), own_ox = ox0 + (trow & (p.tw - 1));
@@ -662,6 +667,14 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         const long long my_pix = ((long long)sample * p.out_h + my_oy) * p.out_w + my_ox;
         const int npairs = BN / (2 * w), nsteps = hw2 >> 4;
         float* stg_w = stg + 0;                                   // this warp reads back only the rows it staged
+        // tma_store (w = 64, BN = 128): this warp's 32 rows x its half's 32 columns of target rows 0 and 1 are two
+        // 4 KB boxes in the 128-byte-swizzled layout (16-byte chunk j of row r at chunk j ^ (r & 7): a quarter-warp's
+        // float4 stores hit 32 distinct banks); one elected lane stores each box with a single cp.async.bulk.tensor.
+        uint8_t* box0 = reinterpret_cast<uint8_t*>(stg_base) + (size_t)(warp - 2) * 8192;
+        if (p.tma_store) {
+          if (lane == 0) tma_store_wait_read();                   // the previous tile's boxes have left shared memory
+          __syncwarp();
+        }
         for (int pr = 0; pr < npairs; ++pr) {
           for (int xs = 0; xs < nsteps; ++xs) {
             const int cc[2] = {2 * pr * w + half * hw2 + xs * 16, 2 * pr * w + half * hw2 + xs * 16 + w};
@@ -692,6 +705,27 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
               float* d1 = p.out2 + my_pix * p.out2_ld + (((n0 / w) >> 1) + pr) * hw2 + ((half * hw2 + xs * 16) >> 1);
               *reinterpret_cast<float4*>(d1) = make_float4(pl[0], pl[1], pl[2], pl[3]);
               *reinterpret_cast<float4*>(d1 + 4) = make_float4(pl[4], pl[5], pl[6], pl[7]);
+            }
+            if (p.tma_store) {
+#pragma unroll
+              for (int rr = 0; rr < 2; ++rr) {
+                uint8_t* rowp = box0 + rr * 4096 + lane * 128;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<float4*>(rowp + (((xs * 4 + j) ^ (lane & 7)) << 4)) =
+                      make_float4(y[rr][4 * j], y[rr][4 * j + 1], y[rr][4 * j + 2], y[rr][4 * j + 3]);
+              }
+              if (xs == nsteps - 1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+                __syncwarp();
+                if (lane == 0) {
+                  const int r0 = (int)my_pix;                                   // first of this warp's 32 consecutive rows
+                  tma_store_2d(&maps.out, box0, n0 + half * 32, r0);
+                  tma_store_2d(&maps.out, box0 + 4096, n0 + 64 + half * 32, r0);
+                  tma_store_commit();
+                }
+              }
+              continue;
             }
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
@@ -741,7 +775,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           const bool zr_r = !is_q && n0 + c >= hd;              // uniform over the warp: hd % 16 == 0 (host check)
           // global reads of this step, all four rows, issued before the TMEM load / staging / warp sync below
           float4 ga[4], gb[4], gc[4];
-          auto load_operands = [&]() {
+          if (active) {
             if (p.pre_add) {
 #pragma unroll
               for (int itr = 0; itr < 4; ++itr)
@@ -758,8 +792,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
               for (int itr = 0; itr < 4; ++itr)
                 gc[itr] = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)pix4[itr] * p.z_ld + nb));
             }
-          };
-          if (TEAMS == 1 && active) load_operands();          // one team: ahead of the TMEM stage (latency hiding)
+          }
           {
             float acc[16];
             if (p.debug & 8) {
@@ -784,7 +817,6 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           }
           __syncwarp();                         // the panel rows this warp reads back are the ones it staged
           if (active) {
-            if (TEAMS == 2) load_operands();                    // two teams: 16 warps hide the latency, 96 registers
             const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
             const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[lt & 1][c + pc4 * 4]);
             const float* srow = stg + (32 * (warp & 3) + (lane >> 2)) * PITCH + pc4 * 4;
@@ -953,6 +985,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       }
     }
   }
+  if (p.tma_store && warp >= 2 && lane == 0) tma_store_wait_read();     // shared memory must outlive the bulk stores
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
@@ -1196,11 +1229,12 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   p.a_plane_bytes = (tc::BM * p.msub + 8 * (p.n_inner - 1)) * tc::KC * 2;
   const int a_stage = nplanes * p.a_plane_bytes, b_stage = nplanes * bn * tc::KC * 2;
   const int stage_bytes = a_stage + b_stage;
-  const bool gru_epi = d.epilogue == ACCFLOW_EPI_GRU_ZR || d.epilogue == ACCFLOW_EPI_GRU_Q;
-  int gru_teams = 2;                                         // ACCFLOW_TC_GRU_TEAMS=1: one team of 8 epilogue warps (A/B runs)
-  if (const char* e = getenv("ACCFLOW_TC_GRU_TEAMS")) gru_teams = atoi(e) == 1 ? 1 : 2;
-  const int teams = gru_epi ? gru_teams : 1;
-  const int epi_bytes = teams * 2 * tc::BM * 20 * 4;         // two 128 x (16+4)-float epilogue panels per team
+  // correlation volume through TMA stores: 512x512 shape class (64-wide target map, N tile = two map rows, exact tiles)
+  bool tma_store = d.epilogue == ACCFLOW_EPI_STORE_POOL && d.pool_w == 64 && bn == 128 && p.out_w == 64 && p.tw == 64 &&
+                   p.out_h % 2 == 0 && d.out_ld == d.cout && d.cout % 128 == 0;
+  if (const char* e = getenv("ACCFLOW_TC_TMA_STORE")) tma_store = tma_store && atoi(e) != 0;
+  p.tma_store = tma_store;
+  const int epi_bytes = tma_store ? 8 * 8192 : 2 * tc::BM * 20 * 4;   // 8 warps x two 4 KB boxes | two 128 x (16+4)-float panels
   const int ring_bytes = 222 * 1024 - 1024 - epi_bytes;
   int stages = ring_bytes / stage_bytes, stages_b;
   if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
@@ -1313,14 +1347,22 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     ACCFLOW_REQUIRE(cr == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(source %d) failed (%d)", s, (int)cr);
   }
 
+  if (tma_store) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)d.cout, (cuuint64_t)d.batch * p.out_h * p.out_w};
+    const cuuint64_t gstr[1] = {(cuuint64_t)d.out_ld * 4};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = enc(&maps.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d.out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACCFLOW_REQUIRE(cr == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(output) failed (%d)", (int)cr);
+  }
   const size_t smem = (size_t)stages * a_stage + (size_t)stages_b * b_stage + epi_bytes + 1024;
   static thread_local int cfg_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (cfg_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
     if (e != cudaSuccess) return fail((int)e, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
     cfg_dev = dev;
   }
@@ -1328,11 +1370,9 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
   const int total_tiles = p.tiles_x * p.tiles_y * d.batch * p.n_tiles;
   dim3 grid(total_tiles < sm_count ? total_tiles : sm_count, 1, 1);
-  if (gru_epi && teams == 2)
-    tc::conv_tc_kernel<true, 2><<<grid, 64 + 256 * 2, smem, (cudaStream_t)stream>>>(p, maps);
-  else if (gru_epi)
-    tc::conv_tc_kernel<true, 1><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
+  if (d.epilogue == ACCFLOW_EPI_GRU_ZR || d.epilogue == ACCFLOW_EPI_GRU_Q)
+    tc::conv_tc_kernel<true><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
   else
-    tc::conv_tc_kernel<false, 1><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
+    tc::conv_tc_kernel<false><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
   return launched("conv2d_tc");
 }
