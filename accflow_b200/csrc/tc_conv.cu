@@ -60,6 +60,8 @@ struct Params {
   int msub;    // shift modes, narrow N tiles: 128-pixel sub-tiles per CTA tile (stacked along the slow axis, one
                // activation box); every weight tile is used msub times, i.e. 1/msub of the weight bytes per pixel
   int pool_w;  // ACCFLOW_EPI_STORE_POOL: width of the map the N axis is a row-major view of
+  int m_major;    // tile walk: 0 = N-major (CTAs that run together share a weight tile), 1 = M-major (per-sample GEMMs with a
+                  // P x P output: the CTAs that run together write adjacent column ranges of the same rows)
   int tma_store;  // ACCFLOW_EPI_STORE_POOL: level 0 leaves through 32 x 32 fp32 TMA store boxes (maps.out)
   int debug;   // perf experiments only (ACCFLOW_TC_DEBUG): bit 0 = no TMA loads, bit 1 = no MMAs (results are garbage)
   float alpha;
@@ -427,8 +429,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       int sa = 0, sb = 0;                                    // ring positions (A boxes, weight tiles)
       uint32_t pa = 1, pb = 1;                               // parity of the "free" phase to wait for (first lap passes)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile / m_tiles;
-        int t = tile - n_tile * m_tiles;
+        const int n_tile = p.m_major ? tile % p.n_tiles : tile / m_tiles;
+        int t = p.m_major ? tile / p.n_tiles : tile - n_tile * m_tiles;
         const int tile_x = t % p.tiles_x; t /= p.tiles_x;
         const int tile_y = t % p.tiles_y;
         const int sample = t / p.tiles_y;
@@ -486,8 +488,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         Chunk ck;
       };
       auto decode = [&](Cur& c) {
-        const int n_tile = c.tile / m_tiles;
-        int t = c.tile - n_tile * m_tiles;
+        const int n_tile = p.m_major ? c.tile % p.n_tiles : c.tile / m_tiles;
+        int t = p.m_major ? c.tile / p.n_tiles : c.tile - n_tile * m_tiles;
         const int tile_x = t % p.tiles_x; t /= p.tiles_x;
         const int tile_y = t % p.tiles_y;
         c.sample = t / p.tiles_y;
@@ -578,8 +580,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
     const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      const int n_tile = tile / m_tiles;
-      int t = tile - n_tile * m_tiles;
+      const int n_tile = p.m_major ? tile % p.n_tiles : tile / m_tiles;
+      int t = p.m_major ? tile / p.n_tiles : tile - n_tile * m_tiles;
       const int tile_x = t % p.tiles_x; t /= p.tiles_x;
       const int tile_y = t % p.tiles_y;
       const int sample = t / p.tiles_y;
@@ -1234,6 +1236,8 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
                    p.out_h % 2 == 0 && d.out_ld == d.cout && d.cout % 128 == 0;
   if (const char* e = getenv("ACCFLOW_TC_TMA_STORE")) tma_store = tma_store && atoi(e) != 0;
   p.tma_store = tma_store;
+  p.m_major = per_sample && p.n_tiles >= 8;                  // wide per-sample outputs (correlation volume, attention passes)
+  if (const char* e = getenv("ACCFLOW_TC_M_MAJOR")) p.m_major = p.m_major && atoi(e) != 0;
   const int epi_bytes = tma_store ? 8 * 8192 : 2 * tc::BM * 20 * 4;   // 8 warps x two 4 KB boxes | two 128 x (16+4)-float panels
   const int ring_bytes = 222 * 1024 - 1024 - epi_bytes;
   int stages = ring_bytes / stage_bytes, stages_b;

@@ -15,8 +15,9 @@ for B in (8, 27):
     g = torch.Generator().manual_seed(0)
     f1 = View(torch.randn(B, 64, 64, 256, generator=g).cuda()); f2 = View(torch.randn(B, 64, 64, 256, generator=g).cuda())
     ref = None
-    for mode in ("1", "0"):
+    for mode, mm in (("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")):
         os.environ["ACCFLOW_TC_TMA_STORE"] = mode
+        os.environ["ACCFLOW_TC_M_MAJOR"] = mm
         for _ in range(3):
             lv = eng.corr_pyramid(f1, f2, f"cb{B}")
         torch.cuda.synchronize()
@@ -31,4 +32,4 @@ for B in (8, 27):
             ref = out
         diff = max(float((a - b).abs().max()) for a, b in zip(out, ref))
         mb = B * 4096 * 4096 * 4 * 1.3125 / 1e6
-        print(json.dumps({"pairs": B, "tma_store": mode, "us_pyramid": round(us, 1), "GBps_written": round(mb / us * 1e3 / 1e3, 1), "max_diff_vs_tma": diff}), flush=True)
+        print(json.dumps({"pairs": B, "tma_store": mode, "m_major": mm, "us_pyramid": round(us, 1), "GBps_written": round(mb / us * 1e3 / 1e3, 1), "max_diff_vs_tma": diff}), flush=True)

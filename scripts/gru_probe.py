@@ -49,10 +49,22 @@ for B in (int(x) for x in os.environ.get("PROBE_PAIRS", "18,27").split(",")):
         "q 5x1 256->128 + pre_add": lambda: K.conv(q256, [rh, mf], epilogue=L.EPI_GRU_Q, h=hid, z=z, pre_add=pre_q),
         "convc2 3x3 256->192 relu planes-only": lambda: K.conv(c2, [x256], out192, act=L.ACT_RELU, planes_only=True),
         "plain 1x5 256->256 relu planes-only": lambda: K.conv(zr256, [hid, mf], pre_zr_out, act=L.ACT_RELU, planes_only=True),
+        "convf1 1x1 98->128 relu planes-only": lambda: K.conv(f1, [x98], out128, act=L.ACT_RELU, planes_only=True),
+        "convc1 1x1 324->256 relu planes-only": lambda: K.conv(c1, [x324], pre_zr_out, act=L.ACT_RELU, planes_only=True),
+        "enc1 3x3 64->64 @256x256 x9 fp32 out": lambda: K.conv(e1, [x64], out64, emit_planes=False),
     }
+    if os.environ.get("PROBE_ONLY"):
+        variants = {k: v for k, v in variants.items() if os.environ["PROBE_ONLY"] in k}
     zr384, zr256 = wz(384, 256, 1, 5), wz(256, 256, 1, 5)
     q384, q256 = wz(384, 128, 5, 1), wz(256, 128, 5, 1)
     c2 = wz(256, 192, 3, 3)
+    f1, c1, e1 = wz(98, 128, 1, 1), wz(324, 256, 1, 1), wz(64, 64, 3, 3)
+    x98, x324 = View(torch.randn(B, h, w, 104, generator=g).cuda()).ch(0, 98), mk(324)
+    x64, out64 = View(torch.randn(9, 256, 256, 64, generator=g).cuda()), View(torch.empty(9, 256, 256, 64, device="cuda"))
+    out128 = mk(128)
+    for v in (x98, x324, x64):
+        K.ensure_planes(v)
+    K.planes_ptr(out128, create=True)
     pre_zr_out = mk(256)
     K.planes_ptr(pre_zr_out, create=True)
     for name, fn in variants.items():
