@@ -15,8 +15,9 @@
 // Epilogue: tcgen05.ld -> padded smem panel -> coalesced affine / activation / residual / GRU
 // math -> fp32 stores (+ bf16 planes of the result for the next convolution).
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..9 = epilogue (two sets of four warps, one per half of the N tile).
+// Warp roles (352 threads): warp 0 = TMA producer of the weight ring, warp 1 = TMEM owner + MMA issuer,
+// warps 2..9 = epilogue (two sets of four warps, one per half of the N tile), warp 10 = TMA producer of the
+// activation ring (shift modes).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -32,7 +33,7 @@ constexpr int KC = 64;        // K elements per pipeline stage (one 128-byte swi
 constexpr int A_PLANE_BYTES = BM * KC * 2;  // 16 KB
 constexpr int MAX_STAGES = 6;
 constexpr int MAX_B_STAGES = 8;
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 352;   // warp 0: weight producer, 1: TMEM + MMA issue, 2-9: epilogue, 10: activation producer
 
 struct PlaneOut {  // optional bf16 planes written next to an fp32 output
   __nv_bfloat16* ptr;
@@ -422,12 +423,24 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp == 0) {
-    // ================================ TMA producer ============================================
-    if (lane == 0 && !(n_inner > 1 && p.stages_b - 1 < n_inner - 1)) {
-      const bool comb = n_inner == 1;
+  if (warp == 0 || warp == 10) {
+    // ================================ TMA producers ===========================================
+    // Two single-thread producers on two warps: warp 0 feeds the weight ring (and, when one weight tile is used per
+    // activation box - n_inner == 1 - the activation box too: both operands then share the weight ring's barriers and
+    // slot index, one handshake per K step), warp 10 feeds the activation ring of the shift modes.  The rings are
+    // independent, so each thread simply runs as far ahead as its ring allows.  The loops are written for
+    // instruction count - one thread's serial latency per step is on the critical path (round-2 finding: the former
+    // single producer spent ~200 instructions per weight tile, i.e. about the 768 clk of tensor work it has to
+    // hide behind; with TMA and MMA disabled the kernel still took 650 clk per step): ring pointers and tap offsets
+    // are carried and updated only when they change, nothing is divided or re-derived per step.
+    const bool comb = n_inner == 1;
+    const bool w_thread = warp == 0, a_thread = comb ? warp == 0 : warp == 10;
+    if (lane == 0 && (w_thread || a_thread)) {
+      const bool no_tma = (p.debug & 1) != 0;
+      const uint32_t a_bytes = no_tma ? 0u : (uint32_t)a_stage, b_bytes = no_tma ? 0u : (uint32_t)b_stage;
       int sa = 0, sb = 0;                                    // ring positions (A boxes, weight tiles)
       uint32_t pa = 1, pb = 1;                               // parity of the "free" phase to wait for (first lap passes)
+      const int tstep = p.mode == 1 ? p.kw : 1;              // weight tap index = tbase + j * tstep
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = p.m_major ? tile % p.n_tiles : tile / m_tiles;
         int t = p.m_major ? tile / p.n_tiles : tile - n_tile * m_tiles;
@@ -435,121 +448,57 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         const int tile_y = t % p.tiles_y;
         const int sample = t / p.tiles_y;
         const int ox0 = tile_x * p.tile_w, oy0 = tile_y * p.tile_h, n0 = n_tile * BN;
-        Chunk ck{0, 0, 0};                                   // ck.tap = outer tap index
+        // box origin along tensor-map dims 1, 2 = (b1 + d1, b2 + d2); d1 / d2 follow the outer tap
+        //   mode 0: dims (C, W, H), one box per tap (kx, ky);  mode 1: dims (C, W, H), outer tap = kx, halo along y;
+        //   mode 2: dims (C, H, W), outer tap = ky, halo along x
+        const int b1 = p.mode == 2 ? oy0 : ox0 * p.stride, b2 = p.mode == 2 ? ox0 : oy0 * p.stride;
+        int d1 = p.mode == 2 ? -p.pad_h : -p.pad_w, d2 = p.mode == 2 ? -p.pad_w : -p.pad_h;
+        int kx = 0, tbase = 0;                               // mode 0: column of the outer tap; first weight tap of the chunk
+        int s = 0, c0 = 0;                                   // source / channel block of the chunk
         for (int i = 0; i < nchunks; ++i) {
-          // n_inner == 1 (one weight tile per activation box): both operands share the weight ring's
-          // barriers and slot index, i.e. one handshake per K step instead of two.
-          uint64_t* abar = comb ? &bar_bfull[sb] : &bar_afull[sa];
-          uint8_t* adst = smem + (size_t)(comb ? sb : sa) * a_stage;
-          if (comb) {
-            mbar_wait(&bar_bfree[sb], pb);
-            mbar_expect_tx(abar, (p.debug & 1) ? 0u : (uint32_t)(a_stage + b_stage));
-          } else {
-            mbar_wait(&bar_afree[sa], pa);
-            mbar_expect_tx(abar, (p.debug & 1) ? 0u : (uint32_t)a_stage);
-          }
-          int c1, c2;                                        // box origin along tensor-map dims 1, 2
-          if (p.mode == 0) {
-            const int ky = ck.tap / p.kw, kx = ck.tap - ky * p.kw;
-            c1 = ox0 * p.stride + kx - p.pad_w; c2 = oy0 * p.stride + ky - p.pad_h;
-          } else if (p.mode == 1) {                          // dims (C, W, H): outer tap = kx, halo along y
-            c1 = ox0 + ck.tap - p.pad_w; c2 = oy0 - p.pad_h;
-          } else {                                           // dims (C, H, W): outer tap = ky, halo along x
-            c1 = oy0 + ck.tap - p.pad_h; c2 = ox0 - p.pad_w;
-          }
-          // one TMA op brings all operand planes (the plane index is the box's outermost dimension)
-          if (!(p.debug & 1)) tma_load_5d(adst, &maps.a[ck.s], abar, ck.c0, c1, c2, sample, 0);
-          const int kcoord = p.src_off[ck.s] + ck.c0;
-          for (int j = 0; j < n_inner; ++j) {
-            uint8_t* wdst = smem_b + (size_t)sb * b_stage;
-            if (!comb) {
+          if (a_thread) {
+            uint64_t* abar = comb ? &bar_bfull[sb] : &bar_afull[sa];
+            uint8_t* adst = smem + (size_t)(comb ? sb : sa) * a_stage;
+            if (comb) {
               mbar_wait(&bar_bfree[sb], pb);
-              mbar_expect_tx(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)b_stage);
+              mbar_expect_tx(abar, a_bytes + b_bytes);
+            } else {
+              mbar_wait(&bar_afree[sa], pa);
+              mbar_expect_tx(abar, a_bytes);
+              if (++sa == SA) { sa = 0; pa ^= 1; }
             }
-            const int tap = p.per_sample ? sample : p.mode == 0 ? ck.tap : p.mode == 1 ? j * p.kw + ck.tap : ck.tap * p.kw + j;
-            if (!(p.debug & 1)) tma_load_4d(wdst, &maps.w, &bar_bfull[sb], kcoord, n0, tap, 0);
-            if (++sb == SB) { sb = 0; pb ^= 1; }
+            // one TMA op brings all operand planes (the plane index is the box's outermost dimension)
+            if (!no_tma) tma_load_5d(adst, &maps.a[s], abar, c0, b1 + d1, b2 + d2, sample, 0);
           }
-          if (++sa == SA) { sa = 0; pa ^= 1; }
-          ck.next(p, n_outer);
-        }
-      }
-    }
-    if (lane == 0 && n_inner > 1 && p.stages_b - 1 < n_inner - 1) {   // activation boxes requested one chunk ahead
-      const bool comb = n_inner == 1;
-      int sa = 0, sb = 0;                                    // ring positions (A boxes, weight tiles)
-      uint32_t pa = 1, pb = 1;                               // parity of the "free" phase to wait for (first lap passes)
-      // Cursor over (tile, chunk): tile decode + the chunk iterator.  The activation boxes have their own cursor that
-      // runs one chunk ahead of the weight tiles (shift modes): the box of chunk c+1 is requested after the first
-      // SB-1 weight tiles of chunk c - the moment its ring slot is released anyway - instead of after the last one,
-      // which left it ~2 weight tiles of lead and stalled the MMA thread at every chunk boundary.
-      struct Cur {
-        int tile, i, sample, ox0, oy0, n0;
-        Chunk ck;
-      };
-      auto decode = [&](Cur& c) {
-        const int n_tile = p.m_major ? c.tile % p.n_tiles : c.tile / m_tiles;
-        int t = p.m_major ? c.tile / p.n_tiles : c.tile - n_tile * m_tiles;
-        const int tile_x = t % p.tiles_x; t /= p.tiles_x;
-        const int tile_y = t % p.tiles_y;
-        c.sample = t / p.tiles_y;
-        c.ox0 = tile_x * p.tile_w; c.oy0 = tile_y * p.tile_h; c.n0 = n_tile * BN;
-        c.i = 0; c.ck = Chunk{0, 0, 0};                      // ck.tap = outer tap index
-      };
-      auto advance = [&](Cur& c) {
-        c.ck.next(p, n_outer);
-        if (++c.i == nchunks) {
-          c.tile += gridDim.x;
-          if (c.tile < total_tiles) decode(c);
-        }
-      };
-      auto issue_a = [&](const Cur& c, uint64_t* abar, uint8_t* adst) {
-        int c1, c2;                                          // box origin along tensor-map dims 1, 2
-        if (p.mode == 0) {
-          const int ky = c.ck.tap / p.kw, kx = c.ck.tap - ky * p.kw;
-          c1 = c.ox0 * p.stride + kx - p.pad_w; c2 = c.oy0 * p.stride + ky - p.pad_h;
-        } else if (p.mode == 1) {                            // dims (C, W, H): outer tap = kx, halo along y
-          c1 = c.ox0 + c.ck.tap - p.pad_w; c2 = c.oy0 - p.pad_h;
-        } else {                                             // dims (C, H, W): outer tap = ky, halo along x
-          c1 = c.oy0 + c.ck.tap - p.pad_h; c2 = c.ox0 - p.pad_w;
-        }
-        if (!(p.debug & 1)) tma_load_5d(adst, &maps.a[c.ck.s], abar, c.ck.c0, c1, c2, c.sample, 0);
-      };
-      auto issue_a_ring = [&](const Cur& c) {               // shift modes: the box goes to the activation ring
-        mbar_wait(&bar_afree[sa], pa);
-        mbar_expect_tx(&bar_afull[sa], (p.debug & 1) ? 0u : (uint32_t)a_stage);
-        issue_a(c, &bar_afull[sa], smem + (size_t)sa * a_stage);
-        if (++sa == SA) { sa = 0; pa ^= 1; }
-      };
-      Cur cb;
-      cb.tile = blockIdx.x;
-      if (cb.tile < total_tiles) decode(cb);
-      Cur ca = cb;
-      const int ja = SB - 1;                                 // weight tile after which the next box is requested
-      const bool ahead = !comb && ja < n_inner - 1;          // else: the box of a chunk is requested at the chunk's start
-      if (ahead && ca.tile < total_tiles) { issue_a_ring(ca); advance(ca); }
-      while (cb.tile < total_tiles) {
-        const int kcoord = p.src_off[cb.ck.s] + cb.ck.c0;
-        if (!comb && !ahead) issue_a_ring(cb);
-        if (comb) {
-          // n_inner == 1 (one weight tile per activation box): both operands share the weight ring's
-          // barriers and slot index, i.e. one handshake per K step instead of two.
-          mbar_wait(&bar_bfree[sb], pb);
-          mbar_expect_tx(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)(a_stage + b_stage));
-          issue_a(cb, &bar_bfull[sb], smem + (size_t)sb * a_stage);
-        }
-        for (int j = 0; j < n_inner; ++j) {
-          uint8_t* wdst = smem_b + (size_t)sb * b_stage;
-          if (!comb) {
-            mbar_wait(&bar_bfree[sb], pb);
-            mbar_expect_tx(&bar_bfull[sb], (p.debug & 1) ? 0u : (uint32_t)b_stage);
+          if (w_thread) {
+            const int kcoord = p.src_off[s] + c0;
+            int tap = p.per_sample ? sample : tbase;
+            for (int j = 0; j < n_inner; ++j, tap += tstep) {
+              if (!comb) {
+                mbar_wait(&bar_bfree[sb], pb);
+                mbar_expect_tx(&bar_bfull[sb], b_bytes);
+              }
+              if (!no_tma) tma_load_4d(smem_b + (size_t)sb * b_stage, &maps.w, &bar_bfull[sb], kcoord, n0, tap, 0);
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+            }
           }
-          const int tap = p.per_sample ? cb.sample : p.mode == 0 ? cb.ck.tap : p.mode == 1 ? j * p.kw + cb.ck.tap : cb.ck.tap * p.kw + j;
-          if (!(p.debug & 1)) tma_load_4d(wdst, &maps.w, &bar_bfull[sb], kcoord, cb.n0, tap, 0);
-          if (++sb == SB) { sb = 0; pb ^= 1; }
-          if (ahead && j == ja && ca.tile < total_tiles) { issue_a_ring(ca); advance(ca); }
+          // next chunk: next 64-channel block, next source, next outer tap
+          c0 += KC;
+          if (c0 >= p.src_c[s]) {
+            c0 = 0;
+            if (++s >= p.nsrc) {
+              s = 0;
+              if (p.mode == 0) {                             // tap = ky * kw + kx
+                ++tbase; ++d1;
+                if (++kx == p.kw) { kx = 0; d1 -= p.kw; ++d2; }
+              } else if (p.mode == 1) {                      // outer tap = kx: taps kx, kx + kw, ...
+                ++tbase; ++d1;
+              } else {                                       // outer tap = ky: taps ky * kw ...
+                tbase += p.kw; ++d1;
+              }
+            }
+          }
         }
-        advance(cb);
       }
     }
   } else if (warp == 1) {
