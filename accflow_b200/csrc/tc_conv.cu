@@ -1056,8 +1056,7 @@ extern "C" int accflow_tc_debug_trace(long long* host, int n) {
 }
 
 static int tc_bn_for(int cout, int nprod) {
-  int bn_cap = nprod <= 2 ? 256 : 128;                // single-product modes (1 = bf16, 2 = fp16): one accumulator
-  if (const char* e = getenv("ACCFLOW_TC_BN_CAP")) { const int v = atoi(e); if (v >= 32 && v <= bn_cap && v % 32 == 0) bn_cap = v; }
+  const int bn_cap = nprod <= 2 ? 256 : 128;          // single-product modes (1 = bf16, 2 = fp16): one accumulator
   const int ntiles = cdiv(cout, bn_cap);
   return cdiv(cdiv(cout, ntiles), 32) * 32;
 }
@@ -1173,9 +1172,9 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     if (!msub_env_read) { if (const char* e = getenv("ACCFLOW_TC_MSUB")) msub_enabled = atoi(e) != 0; msub_env_read = true; }
     const int sub_cols = (nprod > 1 ? 2 : 1) * bn;
     const int slow_extent = p.mode == 1 ? p.out_h : p.out_w;
-    int msub_min_tiles = 4 * 148;
-    if (const char* e = getenv("ACCFLOW_TC_MSUB_MIN")) msub_min_tiles = atoi(e);
-    if (msub_enabled && p.mode != 0 && 2 * 2 * sub_cols <= 512 && slow_extent > 16 && m_tiles_all >= msub_min_tiles) {
+    // (narrower N tiles with two sub-tiles for the 256-channel layers were measured and are slower: the N = 64 MMA costs
+    //  48 clk for 32 clk of math - GRU z|r 136 -> 158 us, profiles/r2o_narrow_tile_experiment.txt)
+    if (msub_enabled && p.mode != 0 && 2 * 2 * sub_cols <= 512 && slow_extent > 16 && m_tiles_all >= 4 * 148) {
       p.msub = 2;
       if (p.mode == 1) { p.tile_h = 32; p.tiles_y = cdiv(p.out_h, 32); } else { p.tile_w = 32; p.tiles_x = cdiv(p.out_w, 32); }
     }
