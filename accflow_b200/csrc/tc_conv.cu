@@ -290,13 +290,6 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
   bool next_ready = false, a_ready = false;
   uint32_t pa = 0, pb = 0;                                           // ring parities
   uint32_t a_slot = c.smem_a, w_slot = c.smem_b;
-  // Deferred commits: the tcgen05.commit that releases a weight tile (and, at a chunk's end, the activation box) is issued
-  // after the FIRST K16 group of the next weight tile instead of right after its own last MMA.  The tensor pipe queues
-  // only ~180 clk of work, while commit + ring bookkeeping + barrier checks take ~285 clk of this thread (mma_trace): issued
-  // back to back they left the pipe idle ~100 clk per weight tile (more in the single-product modes, where a weight tile
-  // is 256 clk of work).  The released slot additionally waits for that first K16 group - negligible against the ring depth.
-  uint64_t* pend_b = nullptr;
-  uint64_t* pend_a = nullptr;
   int lt = 0;
   for (int tile = c.first_tile; tile < c.total_tiles; tile += c.stride_tiles, ++lt) {
     const int slot = lt & 1, use = lt >> 1;
@@ -350,31 +343,21 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
                   umma_bf16(sm_corr, a2, w0, idesc1, 1);
                 }
               }
-              if (sub == 0 && k4 == 0) {                             // the previous weight tile's (and box's) release
-                if (pend_b) { umma_commit(pend_b); pend_b = nullptr; }
-                if (pend_a) { umma_commit(pend_a); pend_a = nullptr; }
-              }
             }
           }
-        } else {
-          if (pend_b) { umma_commit(pend_b); pend_b = nullptr; }
-          if (pend_a) { umma_commit(pend_a); pend_a = nullptr; }
         }
         first = 1;
         if (tr) g_tc_trace[3 * ntr + 1] = clock64();
-        pend_b = &c.bfree[sb];                                       // weight tile reusable once these MMAs retire
+        umma_commit(&c.bfree[sb]);                                   // weight tile reusable once these MMAs retire
         if (tr) { g_tc_trace[3 * ntr + 2] = clock64(); ++ntr; }
         a_lo += 1024 >> 4;                                           // shift modes: next tap = 8 pixel rows further
         w_slot += c.b_stage;
         if (++sb == c.SB) { sb = 0; pb ^= 1; w_slot = c.smem_b; }
       }
-      if (!comb) pend_a = &c.afree[sa];                              // ... and so is the activation box
+      if (!comb) umma_commit(&c.afree[sa]);                          // ... and so is the activation box
       a_slot += c.a_stage;
       if (++sa == c.SA) { sa = 0; pa ^= 1; a_slot = c.smem_a; }
     }
-    // tile end: nothing is deferred across the accumulator hand-over
-    if (pend_b) { umma_commit(pend_b); pend_b = nullptr; }
-    if (pend_a) { umma_commit(pend_a); pend_a = nullptr; }
     umma_commit(&c.acc_full[slot]);
   }
 }
