@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_f32_kernel(const ConvK p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = fmaf(acc[i][j], sc[j], sh[j]);
     if (d.pre_add) {   // cout % 4 == 0 (host check): the group is whole
-      const float4 a = *reinterpret_cast<const float4*>(d.pre_add + pix * d.pre_ld + nb);
+      const long long ppix = d.pre_mod > 0 ? (long long)(b % d.pre_mod) * npix + pm : pix;
+      const float4 a = *reinterpret_cast<const float4*>(d.pre_add + ppix * d.pre_ld + nb);
       v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
     }
     if (d.epilogue == ACCFLOW_EPI_STORE) {

@@ -72,6 +72,7 @@ struct Params {
   const float* residual;
   int res_ld, post_relu, epilogue, out_vec;
   const float* pre_add; int pre_ld;         // added before the activation / gate math (hoisted GRU `inp` term)
+  int pre_mod;                              // > 0: sample s reads pre_add sample s % pre_mod
   const float* row_stats; float sm_alpha;   // softmax emit pass: value = exp(acc*sm_alpha - max) * inv_sum per row
   float* out; int out_ld;
   float* out2; int out2_ld;
@@ -708,6 +709,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       // z half or the r half.
       const int hd = p.cout >> 1;
       const int pix_first = (sample * p.out_h + oy0) * p.out_w + ox0;        // always inside the map
+      const int pre_off = p.pre_mod ? (sample % p.pre_mod - sample) * p.out_h * p.out_w : 0;   // shared-frame term
       for (int sub = 0; sub < p.msub; ++sub) {
         int pix4[4];
         bool rok[4];
@@ -730,7 +732,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             if (p.pre_add) {
 #pragma unroll
               for (int itr = 0; itr < 4; ++itr)
-                ga[itr] = __ldg(reinterpret_cast<const float4*>(p.pre_add + (size_t)pix4[itr] * p.pre_ld + nb));
+                ga[itr] = __ldg(reinterpret_cast<const float4*>(p.pre_add + (size_t)(pix4[itr] + pre_off) * p.pre_ld + nb));
             }
             if (is_q || zr_r) {
               const int nh = zr_r ? nb - hd : nb;
@@ -824,6 +826,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       }
       } else {
       const int pix_first = (sample * p.out_h + oy0) * p.out_w + ox0;        // always inside the map
+      const int pre_off = p.pre_mod ? (sample % p.pre_mod - sample) * p.out_h * p.out_w : 0;
       for (int sub = 0; sub < p.msub; ++sub) {
         // the four output rows this thread finishes per 16-column step: 32-bit pixel indices, rows outside a ragged tile
         // clamped to the tile's first pixel (loads and math run unpredicated, only the stores are guarded)
@@ -878,7 +881,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
               const float4 a4 = *reinterpret_cast<const float4*>(srow + itr * 8 * PITCH);
               float y[4] = {fmaf(a4.x, sc4.x, sh4.x), fmaf(a4.y, sc4.y, sh4.y), fmaf(a4.z, sc4.z, sh4.z), fmaf(a4.w, sc4.w, sh4.w)};
               if (p.pre_add) {
-                const float4 pa = __ldg(reinterpret_cast<const float4*>(p.pre_add + pix * p.pre_ld + nb));
+                const float4 pa = __ldg(reinterpret_cast<const float4*>(p.pre_add + (pix + pre_off) * p.pre_ld + nb));
                 y[0] += pa.x; y[1] += pa.y; y[2] += pa.z; y[3] += pa.w;
               }
               if (p.act == ACCFLOW_ACT_RELU) {
@@ -914,7 +917,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
                 const int n = nb + j;
                 if (n < p.cout) {
                   const bool second = p.act_split > 0 && n >= p.act_split;
-                  float o = y[j] + (p.pre_add ? __ldg(p.pre_add + pix * p.pre_ld + n) : 0.f);
+                  float o = y[j] + (p.pre_add ? __ldg(p.pre_add + (pix + pre_off) * p.pre_ld + n) : 0.f);
                   o = act_apply(o, second ? p.act2 : p.act);
                   if (p.residual) o += p.residual[pix * p.res_ld + n];
                   if (p.post_relu) o = fmaxf(o, 0.f);
@@ -1256,7 +1259,7 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   ACCFLOW_REQUIRE(!d.pre_add || (aligned16(d.pre_add) && d.pre_ld % 4 == 0 && d.cout % 4 == 0 &&
                                  d.epilogue != ACCFLOW_EPI_STORE_POOL),
                   "conv2d_tc: pre_add must be 16B aligned with pre_ld %% 4 == 0 and cout %% 4 == 0");
-  p.pre_add = d.pre_add; p.pre_ld = d.pre_ld;
+  p.pre_add = d.pre_add; p.pre_ld = d.pre_ld; p.pre_mod = d.pre_mod > 0 ? d.pre_mod : 0;
 
   tc::EncodeTiledFn enc = tc::encode_fn();
   ACCFLOW_REQUIRE(enc != nullptr, "conv2d_tc: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");

@@ -268,11 +268,13 @@ class Kernels:
              weight_ptr: Optional[int] = None, weight_batch_stride=0, cout=None, cout_pad=None,
              use_affine=True, tc_b: Optional["L.TcWeights"] = None, tc_src_planes=None, planes_only=False,
              emit_planes=True, pool_w=0, pre_add: Optional[View] = None, row_stats: Optional[torch.Tensor] = None,
-             tc_out_planes=None, out_h: int = 0):
+             tc_out_planes=None, out_h: int = 0, pre_mod: int = 0):
         """``planes_only``: the output (``out``; ``out2`` for the GRU z|r epilogue) is read by tensor-core
         convolutions only, so in the tensor-core modes its fp32 copy is not written (half the store bytes).
         ``emit_planes=False``: the next reader is not a tensor-core conv (InstanceNorm), so no planes are written.
-        ``pre_add``: fp32 slice added before the activation / gate math (the hoisted GRU ``inp`` term)."""
+        ``pre_add``: fp32 slice added before the activation / gate math (the hoisted GRU ``inp`` term); with
+        ``pre_mod`` > 0 it holds ``pre_mod`` samples and sample s reads sample s % pre_mod (pairs that share their
+        first frame share the term)."""
         d = L.ConvDesc()
         cin = 0
         for k, s in enumerate(srcs):
@@ -305,8 +307,8 @@ class Kernels:
         if z is not None:
             d.z, d.z_ld = z.ptr, z.ld
         if pre_add is not None:
-            assert pre_add.c == d.cout and pre_add.b == s0.b
-            d.pre_add, d.pre_ld = pre_add.ptr, pre_add.ld
+            assert pre_add.c == d.cout and pre_add.b == (pre_mod or s0.b) and s0.b % (pre_mod or s0.b) == 0
+            d.pre_add, d.pre_ld, d.pre_mod = pre_add.ptr, pre_add.ld, pre_mod
         if row_stats is not None:
             d.row_stats = row_stats.data_ptr()
         d.out_h = out_h
@@ -762,6 +764,7 @@ class FlowEstimatorEngine:
         B, h, w = f1.b, f1.h, f1.w
         st = dict(B=B, h=h, w=w, P=h * w, H=H, W=W, hid=hid, inp=inp)
         st["gru_pre"] = gru_pre if gru_pre is not None else self.gru_inp_terms(inp, tag)
+        st["pre_mod"] = 0 if st["gru_pre"][0][0].b == B else st["gru_pre"][0][0].b     # terms shared by pairs of one frame
         st["pyr"] = self.corr_pyramid(f1, f2, tag)
         if self.gma:
             st["attn"] = self.attention(inp, tag)
@@ -896,8 +899,9 @@ class FlowEstimatorEngine:
             if self.gma:
                 self.aggregate(st["attn"], mf, mfg, tag)
             for (zr, q), (pre_zr, pre_q) in zip(self.gru, st["gru_pre"]):
-                k.conv(zr, [hid] + x_srcs, epilogue=L.EPI_GRU_ZR, h=hid, z=z, out2=rh, planes_only=True, pre_add=pre_zr)
-                k.conv(q, [rh] + x_srcs, epilogue=L.EPI_GRU_Q, h=hid, z=z, pre_add=pre_q)
+                k.conv(zr, [hid] + x_srcs, epilogue=L.EPI_GRU_ZR, h=hid, z=z, out2=rh, planes_only=True, pre_add=pre_zr,
+                       pre_mod=st["pre_mod"])
+                k.conv(q, [rh] + x_srcs, epilogue=L.EPI_GRU_Q, h=hid, z=z, pre_add=pre_q, pre_mod=st["pre_mod"])
             k.conv(self.fh1, [hid], fh, act=L.ACT_RELU, planes_only=True)
             k.conv_smallcout(self.fh2, fh, delta, accum=coords, accum_ld=2)     # coords1 += delta_flow
         # mask head + convex upsample: only the last iteration's is observable (raft.py:139-146)
@@ -1107,8 +1111,11 @@ class AccFlowEngine:
                 f2 = gather(fm, [p[1] for p in pairs], tag + ".f2")
                 hid = gather(hid_all, [p[0] - 1 for p in pairs], tag + ".hid")
                 inp = gather(inp_all, [p[0] - 1 for p in pairs], tag + ".inpg") if ofe.gma else None   # attention only
-                pre = [tuple(gather(t, [p[0] - 1 for p in pairs], f"{tag}.gi{hf}{j}") for j, t in enumerate(pr))
-                       for hf, pr in enumerate(gi_all)]
+                if len({p[0] for p in pairs}) == 1:       # (i, i-1), (i, 0): one term per clip, read by both pairs (pre_mod)
+                    pre = [tuple(t.rows((i - 1) * b, i * b) for t in pr) for pr in gi_all]
+                else:
+                    pre = [tuple(gather(t, [p[0] - 1 for p in pairs], f"{tag}.gi{hf}{j}") for j, t in enumerate(pr))
+                           for hf, pr in enumerate(gi_all)]
                 st = ofe.prepare(f1, f2, hid, inp, H, W, tag, gru_pre=pre)
                 if warm_start and flow is not None:
                     flows = ofe.iterate(st, warm_iters or iters, torch.cat([self.last_dflow, flow]), tag)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ACCFLOW_ABI_VERSION 3
+#define ACCFLOW_ABI_VERSION 4
 #if defined(__GNUC__)
 #define ACCFLOW_API __attribute__((visibility("default")))
 #else
@@ -97,6 +97,8 @@ typedef struct accflow_conv_desc {
    * iterations of raft/raft.py:127: its contribution conv(inp) is evaluated once and passed here, the
    * per-iteration convolution then contracts over [h, mf] only.  Needs cout % 4 == 0, 16B alignment. */
   const float* pre_add; int pre_ld;
+  int pre_mod;              /* > 0: pre_add holds pre_mod samples and sample s of the launch reads sample s % pre_mod (pairs that
+                             * share their first frame share the term: AccFlow's (i, i-1) and (i, 0), AccFlow_.py:188) */
   /* EPI_STORE on the tensor-core kernel: per-row (max, 1/sum) pairs [batch*out_h*out_w][2]; when set the stored value
    * is exp(acc*alpha - max) * (1/sum) (softmax emit pass, see ACCFLOW_EPI_ROWSTATS); scale/shift/act must be unset. */
   const float* row_stats;

@@ -145,16 +145,20 @@ def test_gru_epilogues(KP):
     assert maxdiff(hv.t.permute(0, 3, 1, 2), ref) < tol
 
 
-def test_gru_hoisted_input_term(KP):
+@pytest.mark.parametrize("shared", [False, True])
+def test_gru_hoisted_input_term(KP, shared):
     """The GRU's constant `inp` columns applied once and passed as the pre-activation addend (pre_add) give the
-    same half-step as the reference's single convolution over cat[h, inp, mf] (raft/update.py:45-52)."""
+    same half-step as the reference's single convolution over cat[h, inp, mf] (raft/update.py:45-52).
+    ``shared``: samples s and s + B/2 are pairs with the same first frame and read one term (pre_mod)."""
     K, tol = KP
     from accflow_b200 import _lib as L
     from accflow_b200.engine import PackedConv, View
     g = torch.Generator().manual_seed(41)
-    B, H, W = 2, 20, 12
+    B, H, W = (4, 20, 12) if shared else (2, 20, 12)
     h = torch.tanh(torch.randn(B, 128, H, W, generator=g))
     inp = torch.relu(torch.randn(B, 128, H, W, generator=g))
+    if shared:
+        inp[B // 2:] = inp[:B // 2]
     mf = torch.randn(B, 128, H, W, generator=g)
     ws = [torch.randn(128, 384, 5, 1, generator=g) * 0.03 for _ in range(3)]
     bs = [torch.randn(128, generator=g) * 0.1 for _ in range(3)]
@@ -169,13 +173,14 @@ def test_gru_hoisted_input_term(KP):
     qc = PackedConv([rest(ws[2])], [dev(bs[2])], 1, (2, 0))
     zr_i = PackedConv([only(ws[0]), only(ws[1])], [None, None], 1, (2, 0))
     q_i = PackedConv([only(ws[2])], [None], 1, (2, 0))
-    hv, iv, mv = View(dev(nhwc(h))), View(dev(nhwc(inp))), View(dev(nhwc(mf)))
-    pre_zr, pre_q = View(torch.empty(B, H, W, 256, device="cuda")), View(torch.empty(B, H, W, 128, device="cuda"))
+    nb, mod = (B // 2, B // 2) if shared else (B, 0)
+    hv, iv, mv = View(dev(nhwc(h))), View(dev(nhwc(inp[:nb]))), View(dev(nhwc(mf)))
+    pre_zr, pre_q = View(torch.empty(nb, H, W, 256, device="cuda")), View(torch.empty(nb, H, W, 128, device="cuda"))
     K.conv(zr_i, [iv], pre_zr, emit_planes=False)
     K.conv(q_i, [iv], pre_q, emit_planes=False)
     zb, rh = View(torch.empty(B, H, W, 128, device="cuda")), View(torch.empty(B, H, W, 128, device="cuda"))
-    K.conv(zr, [hv, mv], epilogue=L.EPI_GRU_ZR, h=hv, z=zb, out2=rh, pre_add=pre_zr)
-    K.conv(qc, [rh, mv], epilogue=L.EPI_GRU_Q, h=hv, z=zb, pre_add=pre_q)
+    K.conv(zr, [hv, mv], epilogue=L.EPI_GRU_ZR, h=hv, z=zb, out2=rh, pre_add=pre_zr, pre_mod=mod)
+    K.conv(qc, [rh, mv], epilogue=L.EPI_GRU_Q, h=hv, z=zb, pre_add=pre_q, pre_mod=mod)
     torch.cuda.synchronize()
     assert maxdiff(hv.t.permute(0, 3, 1, 2), ref) < tol
 
@@ -199,19 +204,22 @@ def test_fp16x2_operands_saturate_instead_of_nan():
     assert maxdiff(out.t.permute(0, 3, 1, 2), ref) < 2e-5 * float(ref.abs().max())
 
 
-def test_pre_add_store_epilogue(KP):
-    """pre_add on the plain store epilogue: out = relu(conv(x) + b + pre)."""
+@pytest.mark.parametrize("mod", [0, 2])
+def test_pre_add_store_epilogue(KP, mod):
+    """pre_add on the plain store epilogue: out = relu(conv(x) + b + pre); ``mod``: sample s reads pre[s % mod]."""
     K, tol = KP
     from accflow_b200 import _lib as L
     from accflow_b200.engine import PackedConv, View
     g = torch.Generator().manual_seed(42)
-    x = torch.randn(2, 96, 11, 13, generator=g)
-    pre = torch.randn(2, 64, 11, 13, generator=g)
+    nb = 4 if mod else 2
+    x = torch.randn(nb, 96, 11, 13, generator=g)
+    pre = torch.randn(mod or nb, 64, 11, 13, generator=g)
     w = torch.randn(64, 96, 3, 3, generator=g) * 0.05
     b = torch.randn(64, generator=g)
-    ref = torch.relu(F.conv2d(x, w, b, padding=1) + pre)
-    out = View(torch.empty(2, 11, 13, 64, device="cuda"))
-    K.conv(PackedConv([dev(w)], [dev(b)], 1, (1, 1)), [View(dev(nhwc(x)))], out, act=L.ACT_RELU, pre_add=View(dev(nhwc(pre))))
+    ref = torch.relu(F.conv2d(x, w, b, padding=1) + (pre.repeat(nb // mod, 1, 1, 1) if mod else pre))
+    out = View(torch.empty(nb, 11, 13, 64, device="cuda"))
+    K.conv(PackedConv([dev(w)], [dev(b)], 1, (1, 1)), [View(dev(nhwc(x)))], out, act=L.ACT_RELU,
+           pre_add=View(dev(nhwc(pre))), pre_mod=mod)
     torch.cuda.synchronize()
     assert maxdiff(out.t.permute(0, 3, 1, 2), ref) < tol
 
