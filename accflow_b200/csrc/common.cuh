@@ -141,4 +141,47 @@ __device__ __forceinline__ void store_planes4_at(__nv_bfloat16* base, long long 
   }
 }
 
+// Compile-time-format version of store_planes4_at for the tensor-core epilogues (the format is a template parameter of
+// the kernel there): no format branches in the instruction stream.  SAT = false skips the fp16 range clamp for values
+// that are bounded by construction (the GRU state and r*h lie in [-1, 1]).
+template <int FMT, bool SAT>
+__device__ __forceinline__ void store_planes4_t(__nv_bfloat16* base, long long plane_stride, const float* yin) {
+  if constexpr (FMT == ACCFLOW_PLANES_FP16 || FMT == 2) {
+    float y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = SAT ? sat_fp16(yin[j]) : yin[j];
+    const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
+    *reinterpret_cast<uint2*>(base) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    if constexpr (FMT == 2) {
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn((y[0] - f01.x) * ACCFLOW_FP16X2_SCALE, (y[1] - f01.y) * ACCFLOW_FP16X2_SCALE);
+      const __half2 l23 = __floats2half2_rn((y[2] - f23.x) * ACCFLOW_FP16X2_SCALE, (y[3] - f23.y) * ACCFLOW_FP16X2_SCALE);
+      *reinterpret_cast<uint2*>(base + plane_stride) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
+  } else {
+    store_planes4_at(base, plane_stride, FMT, yin);
+  }
+}
+template <int FMT>
+__device__ __forceinline__ void store_planes_t(__nv_bfloat16* dst, long long plane_stride, float v) {
+  store_planes(dst, plane_stride, FMT, v);       // FMT is a constant here: the format branches fold
+}
+
+// Gate math of the tensor-core epilogues: sigmoid / tanh through ex2.approx + rcp.approx (4 / 5 instructions, no
+// slow-path branches; __frcp_rn and __expf expand to ~20 instructions with a reconvergence region each).  Absolute
+// error <= ~4e-7 (ex2.approx: 2 ulp, rcp.approx: 1 ulp; d(sigmoid)/dx <= 1/4), saturating correctly at +-inf.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(-2.f, rcp_approx(1.f + ex2_approx(2.8853900817779268f * x)), 1.f); }
+
 }  // namespace accflow

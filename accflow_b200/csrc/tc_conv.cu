@@ -255,11 +255,52 @@ __device__ __forceinline__ void store_planes1(const PlaneOut& po, int nplanes, l
   store_planes(po.ptr + pix * po.pitch + n, po.plane_stride, nplanes, y);
 }
 
-// Gate math of the GRU epilogues (raft/update.py:47-58): sigmoid / tanh through ex2.approx + rcp (about 8 instructions
-// instead of ~40 for expf + IEEE division / tanhf).  Absolute error <= ~3e-7 for |x| <= 20 (the multiply by log2(e)
-// rounds the exponent argument to ~1e-6 relative; d(sigmoid)/dx <= 1/4), saturating correctly at +-inf.
-__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return 1.f - 2.f * __frcp_rn(1.f + __expf(2.f * x)); }
+// Arithmetic format of a launch = the plane-format code of its operands (common.cuh); a template parameter of the
+// kernel, so none of the format branches reach the instruction stream of the epilogues.
+template <int FMT> struct Fmt {
+  static constexpr int NPROD = FMT == 2 ? 3 : FMT == 3 ? 6 : 1;      // tensor-core products per MAC
+  static constexpr int NPL = FMT == 2 ? 2 : FMT == 3 ? 3 : 1;        // 16-bit planes per operand
+  static constexpr bool FP16 = FMT == 2 || FMT == ACCFLOW_PLANES_FP16;
+};
+
+// 16 accumulator columns of this thread's TMEM lane; split formats: MAIN + scale * CORR (CORR sits bn columns further).
+template <int FMT>
+__device__ __forceinline__ void load_acc16(uint32_t taddr, int bn, float* acc) {
+  if constexpr (Fmt<FMT>::NPROD == 1) {
+    tmem_ld16(taddr, acc);
+  } else {
+    float corr[16];
+    tmem_ld16x2(taddr, taddr + bn, acc, corr);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = FMT == 2 ? fmaf(corr[j], 1.0f / ACCFLOW_FP16X2_SCALE, acc[j]) : acc[j] + corr[j];
+  }
+}
+
+// Address of a 16-byte group: column base pointer (bytes) + pixel * row pitch (bytes) - one IMAD.WIDE.U32.
+__device__ __forceinline__ const float4* row_f4(const char* colbase, uint32_t pix, uint32_t ld_bytes) {
+  return reinterpret_cast<const float4*>(colbase + (size_t)pix * ld_bytes);
+}
+__device__ __forceinline__ float4* row_f4(char* colbase, uint32_t pix, uint32_t ld_bytes) {
+  return reinterpret_cast<float4*>(colbase + (size_t)pix * ld_bytes);
+}
+
+// One output value of the plain-store epilogue's general path (ragged channel tails, the tanh | relu split into two
+// destinations of the cnet head, sigmoid / tanh activations, unaligned slices).  Out of line on purpose.
+template <int FMT>
+__device__ __noinline__ void store_general(const Params& p, const float* pre, size_t pix, int n, float y) {
+  const bool second = p.act_split > 0 && n >= p.act_split;
+  float o = y + (p.pre_add ? __ldg(pre + pix * p.pre_ld + n) : 0.f);
+  o = act_apply(o, second ? p.act2 : p.act);
+  if (p.residual) o += p.residual[pix * p.res_ld + n];
+  if (p.post_relu) o = fmaxf(o, 0.f);
+  if (second && p.out2) {
+    p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
+    if (p.out2_pl.ptr) store_planes_t<FMT>(p.out2_pl.ptr + pix * p.out2_pl.pitch + (n - p.act_split), p.out2_pl.plane_stride, o);
+  } else {
+    if (p.out) p.out[pix * p.out_ld + n] = o;
+    if (p.out_pl.ptr) store_planes_t<FMT>(p.out_pl.ptr + pix * p.out_pl.pitch + n, p.out_pl.plane_stride, o);
+  }
+}
 
 // ---------------------------------------------------------------------------------- MMA issue loop
 // One thread issues every tcgen05.mma of the CTA, so its instruction count per weight tile is on the
@@ -366,12 +407,14 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
 // Persistent: grid = min(#tiles, #SMs); CTA c walks tiles c, c+grid, ... (tiles are N-major so that
 // neighbouring CTAs share one weight tile in L2).  Two TMEM accumulator slots let the epilogue of
 // tile i overlap the TMA/MMA main loop of tile i+1; the smem operand ring runs across tiles.
-// GRU = true: the instantiation for the GRU gate epilogues (its phase 2 issues all global reads of a 16-column step - the
-// hoisted input term, h, z - before the TMEM load; 48 more live registers, which the plain-store instantiation must
-// not pay: at 10 warps the allocator's ceiling is 168 registers per thread).
-template <bool GRU>
+// Template parameters: GRU = 0 (store / row-wise / pooled epilogues), 1 (GRU z|r gates), 2 (GRU q + blend): the gate
+// instantiations issue all global reads of a 16-column step - the hoisted input term, h, z - before the TMEM load, 48
+// more live registers which the plain-store instantiation must not pay (at 11 warps the allocator's ceiling is 168
+// registers per thread).  FMT = arithmetic format (Fmt<>): operand type, products per MAC, emitted planes.
+template <int GRU, int FMT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPack maps) {
+  constexpr int NPROD = Fmt<FMT>::NPROD;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t bar_afull[MAX_STAGES], bar_afree[MAX_STAGES], bar_bfull[MAX_B_STAGES],
       bar_bfree[MAX_B_STAGES], bar_acc_full[2], bar_acc_empty[2];
@@ -380,13 +423,16 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   __shared__ __align__(16) float s_scale[2][256], s_shift[2][256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int BN = p.bn, SA = p.stages, SB = p.stages_b, NPL = p.nplanes;
+  constexpr int NPL = Fmt<FMT>::NPL;
+  const int BN = p.bn, SA = p.stages, SB = p.stages_b;
   const int n_outer = p.n_outer, n_inner = p.n_inner;          // A boxes per K block / taps served by one box
   const int w_plane_bytes = BN * KC * 2;
   const int a_plane_bytes = p.a_plane_bytes;                    // (128 + 8 * halo rows) pixels x 128 B
   const int a_stage = NPL * a_plane_bytes, b_stage = NPL * w_plane_bytes;
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms): [A ring][W ring] then the epilogue panels
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the shared array, not an integer round trip: the compiler keeps the shared address space and
+  //  emits LDS / STS for the epilogue panels instead of generic LD / ST)
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   uint8_t* smem_b = smem + (size_t)SA * a_stage;
   constexpr int PITCH = 20;                                     // floats per staged row: 16 columns + 4 pad
   float* stg_base = reinterpret_cast<float*>(smem_b + (size_t)SB * b_stage);
@@ -394,7 +440,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   int nchunks = 0;
   for (int s = 0; s < p.nsrc; ++s) nchunks += (p.src_c[s] + KC - 1) / KC;
   nchunks *= n_outer;
-  const int sub_cols = (p.nprod > 1 ? 2 : 1) * BN;              // TMEM columns of one 128-pixel sub-tile (MAIN | CORR)
+  const int sub_cols = (NPROD > 1 ? 2 : 1) * BN;                // TMEM columns of one 128-pixel sub-tile (MAIN | CORR)
   const int acc_cols = p.msub * sub_cols;                       // TMEM columns of one accumulator slot
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
@@ -511,23 +557,29 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       c.a_stage = a_stage; c.b_stage = b_stage; c.a_plane16 = a_plane_bytes >> 4; c.w_plane16 = w_plane_bytes >> 4;
       c.smem_a = smem_u32(smem); c.smem_b = smem_u32(smem_b);
       c.tmem_base = tmem_base; c.acc_cols = acc_cols; c.debug = p.debug; c.msub = p.msub; c.sub_cols = sub_cols;
-      c.fp16 = p.fp16;
+      c.fp16 = Fmt<FMT>::FP16;
       c.afull = bar_afull; c.afree = bar_afree; c.bfull = bar_bfull; c.bfree = bar_bfree;
       c.acc_full = bar_acc_full; c.acc_empty = bar_acc_empty;
-      if (p.nprod == 3) { if (p.msub == 2) mma_issue_loop<3, 2>(c); else mma_issue_loop<3, 1>(c); }
-      else if (p.nprod == 1) { if (p.msub == 2) mma_issue_loop<1, 2>(c); else mma_issue_loop<1, 1>(c); }
-      else mma_issue_loop<6, 1>(c);
+      if (NPROD == 6 || p.msub == 1) mma_issue_loop<NPROD, 1>(c); else mma_issue_loop<NPROD, 2>(c);
     }
   } else {
     // ================================ epilogue ================================================
     // Phase 1: TMEM -> registers (MAIN + CORR) -> padded smem panel (16 columns).  Phase 2: coalesced
-    // global traffic with the affine / activation / GRU math, fp32 stores + bf16 planes.
+    // global traffic with the affine / activation / GRU math, fp32 stores + 16-bit planes.
+    // ncu's instruction sampling (profiles/r2_conv_targets_hot_sass.txt) showed this code, not the tensor pipe, setting
+    // the tile rate of every layer with little K per output (two epilogue warps per scheduler, latency/issue-bound), so
+    // it is written for instruction count: the arithmetic format is a template parameter, addresses are a 64-bit
+    // column base + 32-bit pixel index * byte pitch (one IMAD.WIDE each), rows outside a ragged tile are clamped to the
+    // tile's first pixel so loads and math run unpredicated and only the stores are guarded.
     const int half = (warp - 2) >> 2;
     float* stg = stg_base + half * (BM * PITCH);
     const int trow = 32 * (warp & 3) + lane;                    // TMEM lane owned by this thread
     const int st = tid - 64 - 128 * half;                       // 0..127 inside this warp set
     const int pc4 = st & 3;                                     // float4 group inside the 16-column panel
     const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
+    float4* const stg_own = reinterpret_cast<float4*>(stg + trow * PITCH);                          // row this thread stages
+    const float* const srow = stg + (32 * (warp & 3) + (lane >> 2)) * PITCH + pc4 * 4;              // rows it reads back
+    const long long map_px = (long long)p.out_h * p.out_w;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int n_tile = p.m_major ? tile % p.n_tiles : tile / m_tiles;
@@ -550,24 +602,19 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       tc_fence_after();
       asm volatile("bar.sync 3, 256;" ::: "memory");             // staged affine visible to both warp sets
       const uint32_t lane_addr = tmem_base + slot * acc_cols + ((uint32_t)(32 * (warp & 3)) << 16);
+      const float* const sc_t = s_scale[lt & 1];
+      const float* const sh_t = s_shift[lt & 1];
       // this thread's own output row (TMEM lane), mode 0 tiles: used by the row-wise epilogues below
       const int own_oy = oy0 + (trow >> p.tw_shift), own_ox = ox0 + (trow & (p.tw - 1));
       const bool own_in = own_oy < p.out_h && own_ox < p.out_w;
       const long long own_pix = ((long long)sample * p.out_h + own_oy) * p.out_w + own_ox;
-      if (!GRU && (p.epilogue == ACCFLOW_EPI_ROWSTATS || p.epilogue == ACCFLOW_EPI_STORE_T)) {
+      if (GRU == 0 && (p.epilogue == ACCFLOW_EPI_ROWSTATS || p.epilogue == ACCFLOW_EPI_STORE_T)) {
         // Row-wise epilogues straight from registers (no staging panel): softmax partial statistics of
         // s = acc*alpha over this half tile (gma/modules.py:66-74), or the transposed operand-plane store.
         float m_run = -INFINITY, l_run = 0.f;
         for (int c = cbeg; c < cend; c += 16) {
           float acc[16];
-          if (p.nprod == 1) tmem_ld16(lane_addr + c, acc);
-          if (p.nprod > 1) {
-            float corr[16];
-            tmem_ld16x2(lane_addr + c, lane_addr + BN + c, acc, corr);
-            const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
-          }
+          load_acc16<FMT>(lane_addr + c, BN, acc);
           if (c + 16 >= cend) {                                  // last TMEM read of this tile
             tc_fence_before();
             __syncwarp();
@@ -595,8 +642,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             for (int j = 0; j < 16; ++j) {
               const int n = n0 + c + j;
               if (n < p.cout)
-                store_planes(p.out_pl.ptr + (col0 + n) * p.out_pl.pitch + pin, p.out_pl.plane_stride, p.plane_fmt,
-                             fmaf(acc[j], s_scale[lt & 1][c + j], s_shift[lt & 1][c + j]));
+                store_planes_t<FMT>(p.out_pl.ptr + (col0 + n) * p.out_pl.pitch + pin, p.out_pl.plane_stride,
+                                    fmaf(acc[j], sc_t[c + j], sh_t[c + j]));
             }
           }
         }
@@ -604,9 +651,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           *reinterpret_cast<float2*>(p.out + own_pix * p.out_ld + 2 * (2 * n_tile + half)) = make_float2(m_run, l_run);
         continue;
       }
-      float2 sm_stats = make_float2(0.f, 0.f);                    // softmax emit pass: (max, 1/sum) of this thread's row
-      if (p.row_stats && own_in) sm_stats = __ldg(reinterpret_cast<const float2*>(p.row_stats) + own_pix);
-      if (!GRU && p.epilogue == ACCFLOW_EPI_STORE_POOL) {
+      if (GRU == 0 && p.epilogue == ACCFLOW_EPI_STORE_POOL) {
         // Correlation volume + first pyramid level (raft/corr.py:47-55 and :20-22).  The N axis of the tile is a
         // (BN / w) x w piece of the target map; this warp set owns the x range [half*w/2, (half+1)*w/2) of every
         // row, so a thread holds the two vertically adjacent 16-column runs of a row pair in registers: the 2x2
@@ -634,16 +679,9 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
               float acc[16];
-              if (p.nprod == 1) tmem_ld16(lane_addr + cc[rr], acc);
-              if (p.nprod > 1) {
-                float corr[16];
-                tmem_ld16x2(lane_addr + cc[rr], lane_addr + BN + cc[rr], acc, corr);
-                const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;
+              load_acc16<FMT>(lane_addr + cc[rr], BN, acc);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
-              }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) y[rr][j] = fmaf(acc[j], s_scale[lt & 1][cc[rr] + j], s_shift[lt & 1][cc[rr] + j]);
+              for (int j = 0; j < 16; ++j) y[rr][j] = fmaf(acc[j], sc_t[cc[rr] + j], sh_t[cc[rr] + j]);
             }
             if (pr == npairs - 1 && xs == nsteps - 1) {            // last TMEM read of this tile
               tc_fence_before();
@@ -701,17 +739,17 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
         }
         continue;
       }
-      if constexpr (GRU) {
-      // GRU gate epilogues (raft/update.py:47-58).  This path is instruction-bound (ncu: the epilogue warps of the hoisted
-      // z|r conv wait for the MMA only 13 % of the time), so it is written for instruction count: 32-bit pixel indices
-      // (one IMAD.WIDE per pointer), rows outside a ragged tile are clamped to the tile's first pixel so that every
-      // load and all the math run unpredicated and only the stores are guarded, and a 16-column step is uniformly in the
-      // z half or the r half.
-      const int hd = p.cout >> 1;
-      const int pix_first = (sample * p.out_h + oy0) * p.out_w + ox0;        // always inside the map
-      const int pre_off = p.pre_mod ? (sample % p.pre_mod - sample) * p.out_h * p.out_w : 0;   // shared-frame term
+      // ---- panel epilogues: GRU gates / plain store ----
+      const uint32_t pix_first = (uint32_t)((sample * p.out_h + oy0) * p.out_w + ox0);     // always inside the map
+      // pre-activation addend: samples that share their first frame read one term (pre_mod): shift the base, not the pixels
+      const char* const pre_b = reinterpret_cast<const char*>(
+          p.pre_add + (p.pre_mod ? (long long)(sample % p.pre_mod - sample) * map_px * p.pre_ld : 0ll));
+      const uint32_t pre_ldb = (uint32_t)p.pre_ld * 4u;
+      float2 sm_stats = make_float2(0.f, 0.f);                    // softmax emit pass: (max, 1/sum) of this thread's row
+      if (GRU == 0 && p.row_stats && own_in) sm_stats = __ldg(reinterpret_cast<const float2*>(p.row_stats) + own_pix);
       for (int sub = 0; sub < p.msub; ++sub) {
-        int pix4[4];
+        // the four output rows this thread finishes per 16-column step
+        uint32_t pix4[4];
         bool rok[4];
 #pragma unroll
         for (int itr = 0; itr < 4; ++itr) {
@@ -719,223 +757,203 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           const int r_slow = (row >> p.tw_shift) + 16 * sub, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
           const int oy = oy0 + (p.mode == 2 ? r_fast : r_slow), ox = ox0 + (p.mode == 2 ? r_slow : r_fast);
           rok[itr] = oy < p.out_h && ox < p.out_w;
-          pix4[itr] = rok[itr] ? (sample * p.out_h + oy) * p.out_w + ox : pix_first;
+          pix4[itr] = rok[itr] ? (uint32_t)((sample * p.out_h + oy) * p.out_w + ox) : pix_first;
         }
-        for (int c = cbeg; c < cend; c += 16) {
-          const int nb = n0 + c + pc4 * 4;
-          const bool active = nb < p.cout && !(p.debug & 4);
-          const bool is_q = p.epilogue == ACCFLOW_EPI_GRU_Q;
-          const bool zr_r = !is_q && n0 + c >= hd;              // uniform over the warp: hd % 16 == 0 (host check)
-          // global reads of this step, all four rows, issued before the TMEM load / staging / warp sync below
-          float4 ga[4], gb[4], gc[4];
-          if (active) {
-            if (p.pre_add) {
+        const uint32_t sub_addr = lane_addr + sub * sub_cols;
+        if constexpr (GRU != 0) {
+          // GRU gate epilogues (raft/update.py:47-58); a 16-column step is uniformly in the z half or the r half.
+          constexpr bool IS_Q = GRU == 2;
+          const int hd = p.cout >> 1;
+          const uint32_t h_ldb = (uint32_t)p.h_ld * 4u, z_ldb = (uint32_t)p.z_ld * 4u, o2_ldb = (uint32_t)p.out2_ld * 4u;
+          const PlaneOut& po = IS_Q ? p.h_pl : p.out2_pl;           // planes of the new state / of r*h
+          const uint32_t pl_pb = (uint32_t)po.pitch * 2u;
+          for (int c = cbeg; c < cend; c += 16) {
+            const int nb = n0 + c + pc4 * 4;
+            const bool active = nb < p.cout;
+            const bool zr_r = !IS_Q && n0 + c >= hd;                // uniform over the warp: hd % 16 == 0 (host check)
+            const int nh = zr_r ? nb - hd : nb;                     // column in the hd-wide maps (h, r*h)
+            // global reads of this step, all four rows, issued before the TMEM load / staging / warp sync below
+            float4 ga[4], gb[4], gc[4];
+            if (active) {
+              if (p.pre_add) {
+                const char* cb = pre_b + (size_t)nb * 4;
 #pragma unroll
-              for (int itr = 0; itr < 4; ++itr)
-                ga[itr] = __ldg(reinterpret_cast<const float4*>(p.pre_add + (size_t)(pix4[itr] + pre_off) * p.pre_ld + nb));
-            }
-            if (is_q || zr_r) {
-              const int nh = zr_r ? nb - hd : nb;
+                for (int itr = 0; itr < 4; ++itr) ga[itr] = __ldg(row_f4(cb, pix4[itr], pre_ldb));
+              }
+              if (IS_Q || zr_r) {
+                const char* cb = reinterpret_cast<const char*>(p.h + nh);
 #pragma unroll
-              for (int itr = 0; itr < 4; ++itr)
-                gb[itr] = *reinterpret_cast<const float4*>(p.h + (size_t)pix4[itr] * p.h_ld + nh);
-            }
-            if (is_q) {
+                for (int itr = 0; itr < 4; ++itr) gb[itr] = *row_f4(cb, pix4[itr], h_ldb);
+              }
+              if (IS_Q) {
+                const char* cb = reinterpret_cast<const char*>(p.z + nb);
 #pragma unroll
-              for (int itr = 0; itr < 4; ++itr)
-                gc[itr] = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)pix4[itr] * p.z_ld + nb));
-            }
-          }
-          {
-            float acc[16];
-            if (p.debug & 8) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-            } else if (p.nprod == 1) tmem_ld16(lane_addr + sub * sub_cols + c, acc);
-            if (p.nprod > 1 && !(p.debug & 8)) {
-              float corr[16];
-              tmem_ld16x2(lane_addr + sub * sub_cols + c, lane_addr + sub * sub_cols + BN + c, acc, corr);
-              const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;   // fp16x2: lo planes carry 2^11
-#pragma unroll
-              for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
-            }
-            float4* d4 = reinterpret_cast<float4*>(stg + trow * PITCH);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) d4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-          }
-          if (c + 16 >= cend && sub == p.msub - 1) {   // last TMEM read of this tile: hand the slot back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
-          }
-          __syncwarp();                         // the panel rows this warp reads back are the ones it staged
-          if (active) {
-            const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
-            const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[lt & 1][c + pc4 * 4]);
-            const float* srow = stg + (32 * (warp & 3) + (lane >> 2)) * PITCH + pc4 * 4;
-            float y[4][4];
-#pragma unroll
-            for (int itr = 0; itr < 4; ++itr) {
-              const float4 a4 = *reinterpret_cast<const float4*>(srow + itr * 8 * PITCH);
-              y[itr][0] = fmaf(a4.x, sc4.x, sh4.x); y[itr][1] = fmaf(a4.y, sc4.y, sh4.y);
-              y[itr][2] = fmaf(a4.z, sc4.z, sh4.z); y[itr][3] = fmaf(a4.w, sc4.w, sh4.w);
-            }
-            if (p.pre_add) {
-#pragma unroll
-              for (int itr = 0; itr < 4; ++itr) {
-                y[itr][0] += ga[itr].x; y[itr][1] += ga[itr].y; y[itr][2] += ga[itr].z; y[itr][3] += ga[itr].w;
+                for (int itr = 0; itr < 4; ++itr) gc[itr] = __ldg(row_f4(cb, pix4[itr], z_ldb));
               }
             }
-            if (!is_q) {
+            {
+              float acc[16];
+              load_acc16<FMT>(sub_addr + c, BN, acc);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) stg_own[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            }
+            if (c + 16 >= cend && sub == p.msub - 1) {   // last TMEM read of this tile: hand the slot back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
+            }
+            __syncwarp();                         // the panel rows this warp reads back are the ones it staged
+            if (active) {
+              const float4 sc4 = *reinterpret_cast<const float4*>(sc_t + c + pc4 * 4);
+              const float4 sh4 = *reinterpret_cast<const float4*>(sh_t + c + pc4 * 4);
+              float y[4][4];
 #pragma unroll
               for (int itr = 0; itr < 4; ++itr) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) y[itr][j] = sigmoid_fast(y[itr][j]);
+                const float4 a4 = *reinterpret_cast<const float4*>(srow + itr * 8 * PITCH);
+                y[itr][0] = fmaf(a4.x, sc4.x, sh4.x); y[itr][1] = fmaf(a4.y, sc4.y, sh4.y);
+                y[itr][2] = fmaf(a4.z, sc4.z, sh4.z); y[itr][3] = fmaf(a4.w, sc4.w, sh4.w);
               }
-              if (!zr_r) {
-#pragma unroll
-                for (int itr = 0; itr < 4; ++itr)
-                  if (rok[itr])
-                    *reinterpret_cast<float4*>(p.z + (size_t)pix4[itr] * p.z_ld + nb) = make_float4(y[itr][0], y[itr][1], y[itr][2], y[itr][3]);
-              } else {
-                const int n = nb - hd;
+              if (p.pre_add) {
 #pragma unroll
                 for (int itr = 0; itr < 4; ++itr) {
-                  float o[4] = {y[itr][0] * gb[itr].x, y[itr][1] * gb[itr].y, y[itr][2] * gb[itr].z, y[itr][3] * gb[itr].w};
+                  y[itr][0] += ga[itr].x; y[itr][1] += ga[itr].y; y[itr][2] += ga[itr].z; y[itr][3] += ga[itr].w;
+                }
+              }
+              if constexpr (!IS_Q) {
+#pragma unroll
+                for (int itr = 0; itr < 4; ++itr) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) y[itr][j] = sigmoid_fast(y[itr][j]);
+                }
+                if (!zr_r) {
+                  char* cb = reinterpret_cast<char*>(p.z + nb);
+#pragma unroll
+                  for (int itr = 0; itr < 4; ++itr)
+                    if (rok[itr]) *row_f4(cb, pix4[itr], z_ldb) = make_float4(y[itr][0], y[itr][1], y[itr][2], y[itr][3]);
+                } else {
+                  char* ob = reinterpret_cast<char*>(p.out2 + nh);
+                  char* pb = reinterpret_cast<char*>(po.ptr + nh);
+#pragma unroll
+                  for (int itr = 0; itr < 4; ++itr) {
+                    const float o[4] = {y[itr][0] * gb[itr].x, y[itr][1] * gb[itr].y, y[itr][2] * gb[itr].z, y[itr][3] * gb[itr].w};
+                    if (rok[itr]) {
+                      if (p.out2) *row_f4(ob, pix4[itr], o2_ldb) = make_float4(o[0], o[1], o[2], o[3]);
+                      if (po.ptr)       // |r*h| <= 1: no fp16 range clamp
+                        store_planes4_t<FMT, false>(reinterpret_cast<__nv_bfloat16*>(pb + (size_t)pix4[itr] * pl_pb), po.plane_stride, o);
+                    }
+                  }
+                }
+              } else {
+                char* hb = reinterpret_cast<char*>(p.h + nb);
+                char* pb = reinterpret_cast<char*>(po.ptr + nb);
+#pragma unroll
+                for (int itr = 0; itr < 4; ++itr) {
+                  const float4 zz = gc[itr], hh = gb[itr];
+                  const float o[4] = {fmaf(zz.x, tanh_fast(y[itr][0]) - hh.x, hh.x), fmaf(zz.y, tanh_fast(y[itr][1]) - hh.y, hh.y),
+                                      fmaf(zz.z, tanh_fast(y[itr][2]) - hh.z, hh.z), fmaf(zz.w, tanh_fast(y[itr][3]) - hh.w, hh.w)};
                   if (rok[itr]) {
-                    if (p.out2) *reinterpret_cast<float4*>(p.out2 + (size_t)pix4[itr] * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
-                    if (p.out2_pl.ptr) store_planes4(p.out2_pl, p.plane_fmt, pix4[itr], n, o);
-                  }
-                }
-              }
-            } else {
-#pragma unroll
-              for (int itr = 0; itr < 4; ++itr) {
-                const float4 zz = gc[itr], hh = gb[itr];
-                float o[4] = {fmaf(zz.x, tanh_fast(y[itr][0]) - hh.x, hh.x), fmaf(zz.y, tanh_fast(y[itr][1]) - hh.y, hh.y),
-                              fmaf(zz.z, tanh_fast(y[itr][2]) - hh.z, hh.z), fmaf(zz.w, tanh_fast(y[itr][3]) - hh.w, hh.w)};
-                if (rok[itr]) {
-                  *reinterpret_cast<float4*>(p.h + (size_t)pix4[itr] * p.h_ld + nb) = make_float4(o[0], o[1], o[2], o[3]);
-                  if (p.h_pl.ptr) store_planes4(p.h_pl, p.plane_fmt, pix4[itr], nb, o);
-                }
-              }
-            }
-          }
-          __syncwarp();
-        }
-      }
-      } else {
-      const int pix_first = (sample * p.out_h + oy0) * p.out_w + ox0;        // always inside the map
-      const int pre_off = p.pre_mod ? (sample % p.pre_mod - sample) * p.out_h * p.out_w : 0;
-      for (int sub = 0; sub < p.msub; ++sub) {
-        // the four output rows this thread finishes per 16-column step: 32-bit pixel indices, rows outside a ragged tile
-        // clamped to the tile's first pixel (loads and math run unpredicated, only the stores are guarded)
-        int pix4[4];
-        bool rok[4];
-#pragma unroll
-        for (int itr = 0; itr < 4; ++itr) {
-          const int row = 32 * (warp & 3) + itr * 8 + (lane >> 2);
-          const int r_slow = (row >> p.tw_shift) + 16 * sub, r_fast = row & (p.tw - 1);   // row = slow * tw + fast
-          const int oy = oy0 + (p.mode == 2 ? r_fast : r_slow), ox = ox0 + (p.mode == 2 ? r_slow : r_fast);
-          rok[itr] = oy < p.out_h && ox < p.out_w;
-          pix4[itr] = rok[itr] ? (sample * p.out_h + oy) * p.out_w + ox : pix_first;
-        }
-      for (int c = cbeg; c < cend; c += 16) {
-        {
-          float acc[16];
-          if (p.debug & 8) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-          } else if (p.nprod == 1) tmem_ld16(lane_addr + sub * sub_cols + c, acc);
-          if (p.nprod > 1 && !(p.debug & 8)) {
-            float corr[16];
-            tmem_ld16x2(lane_addr + sub * sub_cols + c, lane_addr + sub * sub_cols + BN + c, acc, corr);
-            const float cs = p.nprod == 3 ? (1.0f / ACCFLOW_FP16X2_SCALE) : 1.0f;   // fp16x2: lo planes carry 2^11
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = fmaf(corr[j], cs, acc[j]);
-          }
-          if (p.row_stats) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = expf(fmaf(acc[j], p.sm_alpha, -sm_stats.x)) * sm_stats.y;
-          }
-          float4* d4 = reinterpret_cast<float4*>(stg + trow * PITCH);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) d4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-        }
-        if (c + 16 >= cend && sub == p.msub - 1) {   // last TMEM read of this tile: hand the slot back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
-        }
-        __syncwarp();                         // the panel rows this warp reads back are the ones it staged
-        const int nb = n0 + c + pc4 * 4;
-        if (nb < p.cout && !(p.debug & 4)) {
-          const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[lt & 1][c + pc4 * 4]);
-          const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[lt & 1][c + pc4 * 4]);
-          const float* srow = stg + (32 * (warp & 3) + (lane >> 2)) * PITCH + pc4 * 4;
-          if (p.out_vec && nb + 3 < p.cout) {
-            // fast path: four whole channels per thread and row, one destination
-#pragma unroll
-            for (int itr = 0; itr < 4; ++itr) {
-              const size_t pix = (size_t)pix4[itr];
-              const float4 a4 = *reinterpret_cast<const float4*>(srow + itr * 8 * PITCH);
-              float y[4] = {fmaf(a4.x, sc4.x, sh4.x), fmaf(a4.y, sc4.y, sh4.y), fmaf(a4.z, sc4.z, sh4.z), fmaf(a4.w, sc4.w, sh4.w)};
-              if (p.pre_add) {
-                const float4 pa = __ldg(reinterpret_cast<const float4*>(p.pre_add + (pix + pre_off) * p.pre_ld + nb));
-                y[0] += pa.x; y[1] += pa.y; y[2] += pa.z; y[3] += pa.w;
-              }
-              if (p.act == ACCFLOW_ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
-              } else if (p.act != ACCFLOW_ACT_NONE) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) y[j] = act_apply(y[j], p.act);
-              }
-              if (p.residual) {
-                const float4 r = *reinterpret_cast<const float4*>(p.residual + pix * p.res_ld + nb);
-                y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
-              }
-              if (p.post_relu) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
-              }
-              if (rok[itr]) {
-                if (p.out) *reinterpret_cast<float4*>(p.out + pix * p.out_ld + nb) = make_float4(y[0], y[1], y[2], y[3]);
-                if (p.out_pl.ptr) store_planes4(p.out_pl, p.plane_fmt, pix, nb, y);
-              }
-            }
-          } else {
-            // general path: ragged channel tail, tanh | relu split into two destinations (cnet head), unaligned slices
-#pragma unroll
-            for (int itr = 0; itr < 4; ++itr) {
-              if (!rok[itr]) continue;
-              const size_t pix = (size_t)pix4[itr];
-              const float4 a4 = *reinterpret_cast<const float4*>(srow + itr * 8 * PITCH);
-              float y[4] = {fmaf(a4.x, sc4.x, sh4.x), fmaf(a4.y, sc4.y, sh4.y), fmaf(a4.z, sc4.z, sh4.z), fmaf(a4.w, sc4.w, sh4.w)};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int n = nb + j;
-                if (n < p.cout) {
-                  const bool second = p.act_split > 0 && n >= p.act_split;
-                  float o = y[j] + (p.pre_add ? __ldg(p.pre_add + (pix + pre_off) * p.pre_ld + n) : 0.f);
-                  o = act_apply(o, second ? p.act2 : p.act);
-                  if (p.residual) o += p.residual[pix * p.res_ld + n];
-                  if (p.post_relu) o = fmaxf(o, 0.f);
-                  if (second && p.out2) {
-                    p.out2[pix * p.out2_ld + (n - p.act_split)] = o;
-                    if (p.out2_pl.ptr) store_planes1(p.out2_pl, p.plane_fmt, pix, n - p.act_split, o);
-                  } else {
-                    if (p.out) p.out[pix * p.out_ld + n] = o;
-                    if (p.out_pl.ptr) store_planes1(p.out_pl, p.plane_fmt, pix, n, o);
+                    *row_f4(hb, pix4[itr], h_ldb) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (po.ptr)         // the state is a convex combination of tanh values: no clamp
+                      store_planes4_t<FMT, false>(reinterpret_cast<__nv_bfloat16*>(pb + (size_t)pix4[itr] * pl_pb), po.plane_stride, o);
                   }
                 }
               }
             }
+            __syncwarp();
+          }
+        } else {
+          const uint32_t out_ldb = (uint32_t)p.out_ld * 4u, res_ldb = (uint32_t)p.res_ld * 4u;
+          const uint32_t pl_pb = (uint32_t)p.out_pl.pitch * 2u;
+          for (int c = cbeg; c < cend; c += 16) {
+            {
+              float acc[16];
+              load_acc16<FMT>(sub_addr + c, BN, acc);
+              if (p.row_stats) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = expf(fmaf(acc[j], p.sm_alpha, -sm_stats.x)) * sm_stats.y;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) stg_own[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            }
+            if (c + 16 >= cend && sub == p.msub - 1) {   // last TMEM read of this tile: hand the slot back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bar_acc_empty[slot]);
+            }
+            __syncwarp();                         // the panel rows this warp reads back are the ones it staged
+            const int nb = n0 + c + pc4 * 4;
+            if (nb < p.cout) {
+              const float4 sc4 = *reinterpret_cast<const float4*>(sc_t + c + pc4 * 4);
+              const float4 sh4 = *reinterpret_cast<const float4*>(sh_t + c + pc4 * 4);
+              if (p.out_vec && nb + 3 < p.cout) {
+                // fast path: four whole channels per thread and row, one destination
+                float y[4][4];
+#pragma unroll
+                for (int itr = 0; itr < 4; ++itr) {
+                  const float4 a4 = *reinterpret_cast<const float4*>(srow + itr * 8 * PITCH);
+                  y[itr][0] = fmaf(a4.x, sc4.x, sh4.x); y[itr][1] = fmaf(a4.y, sc4.y, sh4.y);
+                  y[itr][2] = fmaf(a4.z, sc4.z, sh4.z); y[itr][3] = fmaf(a4.w, sc4.w, sh4.w);
+                }
+                if (p.pre_add) {
+                  const char* cb = pre_b + (size_t)nb * 4;
+#pragma unroll
+                  for (int itr = 0; itr < 4; ++itr) {
+                    const float4 pa = __ldg(row_f4(cb, pix4[itr], pre_ldb));
+                    y[itr][0] += pa.x; y[itr][1] += pa.y; y[itr][2] += pa.z; y[itr][3] += pa.w;
+                  }
+                }
+                if (p.act == ACCFLOW_ACT_RELU) {          // (out_vec: the activation is none or ReLU, host check)
+#pragma unroll
+                  for (int itr = 0; itr < 4; ++itr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) y[itr][j] = fmaxf(y[itr][j], 0.f);
+                  }
+                }
+                if (p.residual) {
+                  const char* cb = reinterpret_cast<const char*>(p.residual + nb);
+#pragma unroll
+                  for (int itr = 0; itr < 4; ++itr) {
+                    const float4 r = *row_f4(cb, pix4[itr], res_ldb);
+                    y[itr][0] += r.x; y[itr][1] += r.y; y[itr][2] += r.z; y[itr][3] += r.w;
+                  }
+                  if (p.post_relu) {
+#pragma unroll
+                    for (int itr = 0; itr < 4; ++itr) {
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) y[itr][j] = fmaxf(y[itr][j], 0.f);
+                    }
+                  }
+                }
+                if (p.out) {
+                  char* ob = reinterpret_cast<char*>(p.out + nb);
+#pragma unroll
+                  for (int itr = 0; itr < 4; ++itr)
+                    if (rok[itr]) *row_f4(ob, pix4[itr], out_ldb) = make_float4(y[itr][0], y[itr][1], y[itr][2], y[itr][3]);
+                }
+                if (p.out_pl.ptr) {
+                  char* pb = reinterpret_cast<char*>(p.out_pl.ptr + nb);
+#pragma unroll
+                  for (int itr = 0; itr < 4; ++itr)
+                    if (rok[itr])
+                      store_planes4_t<FMT, true>(reinterpret_cast<__nv_bfloat16*>(pb + (size_t)pix4[itr] * pl_pb), p.out_pl.plane_stride, y[itr]);
+                }
+              } else {
+                // general path: ragged channel tail, tanh | relu split into two destinations (cnet head), sigmoid / tanh
+                // activations, unaligned slices.  Rare: one out-of-line call per value keeps it out of the instruction cache.
+#pragma unroll
+                for (int itr = 0; itr < 4; ++itr) {
+                  if (!rok[itr]) continue;
+                  const float4 a4 = *reinterpret_cast<const float4*>(srow + itr * 8 * PITCH);
+                  const float y[4] = {fmaf(a4.x, sc4.x, sh4.x), fmaf(a4.y, sc4.y, sh4.y), fmaf(a4.z, sc4.z, sh4.z), fmaf(a4.w, sc4.w, sh4.w)};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (nb + j < p.cout) store_general<FMT>(p, reinterpret_cast<const float*>(pre_b), (size_t)pix4[itr], nb + j, y[j]);
+                }
+              }
+            }
+            __syncwarp();
           }
         }
-        __syncwarp();
-      }
-      }
       }
     }
   }
@@ -1255,7 +1273,8 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     p.row_stats = d.row_stats; p.sm_alpha = d.alpha; p.alpha = 1.0f;
   }
   p.out_vec = d.epilogue == ACCFLOW_EPI_STORE && d.act_split == 0 && aligned16(d.out) && (!d.out || d.out_ld % 4 == 0) &&
-              (!d.residual || (aligned16(d.residual) && d.res_ld % 4 == 0));
+              (!d.residual || (aligned16(d.residual) && d.res_ld % 4 == 0)) &&
+              (d.act == ACCFLOW_ACT_NONE || d.act == ACCFLOW_ACT_RELU);
   ACCFLOW_REQUIRE(!d.pre_add || (aligned16(d.pre_add) && d.pre_ld % 4 == 0 && d.cout % 4 == 0 &&
                                  d.epilogue != ACCFLOW_EPI_STORE_POOL),
                   "conv2d_tc: pre_add must be 16B aligned with pre_ld %% 4 == 0 and cout %% 4 == 0");
@@ -1315,22 +1334,28 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     ACCFLOW_REQUIRE(cr == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(output) failed (%d)", (int)cr);
   }
   const size_t smem = (size_t)stages * a_stage + (size_t)stages_b * b_stage + epi_bytes + 1024;
+  // kernel instantiation: [GRU epilogue class][arithmetic format]
+  typedef void (*KernelFn)(const tc::Params, const tc::TmapPack);
+  static const KernelFn kernels[3][4] = {
+      {tc::conv_tc_kernel<0, 1>, tc::conv_tc_kernel<0, 2>, tc::conv_tc_kernel<0, 3>, tc::conv_tc_kernel<0, 4>},
+      {tc::conv_tc_kernel<1, 1>, tc::conv_tc_kernel<1, 2>, tc::conv_tc_kernel<1, 3>, tc::conv_tc_kernel<1, 4>},
+      {tc::conv_tc_kernel<2, 1>, tc::conv_tc_kernel<2, 2>, tc::conv_tc_kernel<2, 3>, tc::conv_tc_kernel<2, 4>}};
   static thread_local int cfg_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (cfg_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
-    if (e != cudaSuccess) return fail((int)e, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
+    for (int g = 0; g < 3; ++g)
+      for (int f = 0; f < 4; ++f) {
+        cudaError_t e = cudaFuncSetAttribute(kernels[g][f], cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+        if (e != cudaSuccess) return fail((int)e, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
+      }
     cfg_dev = dev;
   }
   static thread_local int sm_count = 0;
   if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
   const int total_tiles = p.tiles_x * p.tiles_y * d.batch * p.n_tiles;
   dim3 grid(total_tiles < sm_count ? total_tiles : sm_count, 1, 1);
-  if (d.epilogue == ACCFLOW_EPI_GRU_ZR || d.epilogue == ACCFLOW_EPI_GRU_Q)
-    tc::conv_tc_kernel<true><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
-  else
-    tc::conv_tc_kernel<false><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
+  const int gru = d.epilogue == ACCFLOW_EPI_GRU_ZR ? 1 : d.epilogue == ACCFLOW_EPI_GRU_Q ? 2 : 0;
+  kernels[gru][p.plane_fmt - 1]<<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p, maps);
   return launched("conv2d_tc");
 }

@@ -1,0 +1,24 @@
+#!/bin/bash
+# usage (on the GPU box, through gpurun): TAG=r2x [STEPS=...] bash scripts/gpu_batch.sh [tests] [bench] [fp16] [breakdown] [gma]
+# Each stage writes gpurun_out/${TAG}_<stage>.{log,json}; stages are independent.
+TAG=${TAG:-run}
+mkdir -p gpurun_out
+for stage in "$@"; do
+  case $stage in
+    tests) timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log ;;
+    ktests) timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q > gpurun_out/${TAG}_pytest_kernels.log 2>&1; echo "ktests rc=$?"; tail -3 gpurun_out/${TAG}_pytest_kernels.log ;;
+    bench) timeout 900 python bench.py ${BENCH_ARGS:-} > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench_default.err; echo "bench rc=$?"; python -c "
+import json,sys
+d=json.loads(open('gpurun_out/${TAG}_bench_default.json').read().strip().splitlines()[-1])
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'parity',d.get('parity'),'issued_frac',d['roofline'].get('issued_frac'))" ;;
+    quick) timeout 600 python bench.py --no-cpu-baseline --no-ref-cuda ${BENCH_ARGS:-} > gpurun_out/${TAG}_bench_quick.json 2> gpurun_out/${TAG}_bench_quick.err; echo "quick rc=$?"; tail -c 600 gpurun_out/${TAG}_bench_quick.json ;;
+    fp16) timeout 600 python bench.py --precision fp16 --no-cpu-baseline --no-ref-cuda > gpurun_out/${TAG}_bench_fp16.json 2> gpurun_out/${TAG}_bench_fp16.err; echo "fp16 rc=$?"; python -c "
+import json
+d=json.loads(open('gpurun_out/${TAG}_bench_fp16.json').read().strip().splitlines()[-1]); print('fp16 value',d['value'],'parity',d.get('parity'))" ;;
+    gma) timeout 900 python bench.py --ofe gma --clips 4 --no-cpu-baseline --no-ref-cuda > gpurun_out/${TAG}_bench_gma.json 2> gpurun_out/${TAG}_bench_gma.err; echo "gma rc=$?"; python -c "
+import json
+d=json.loads(open('gpurun_out/${TAG}_bench_gma.json').read().strip().splitlines()[-1]); print('gma value',d['value'],'parity',d.get('parity'))" ;;
+    breakdown) timeout 600 python scripts/conv_breakdown.py > gpurun_out/${TAG}_conv_breakdown.txt 2>&1; echo "breakdown rc=$?"; head -40 gpurun_out/${TAG}_conv_breakdown.txt ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done
