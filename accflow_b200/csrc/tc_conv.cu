@@ -64,7 +64,7 @@ struct Params {
   int m_major;    // tile walk: 0 = N-major (CTAs that run together share a weight tile), 1 = M-major (per-sample GEMMs with a
                   // P x P output: the CTAs that run together write adjacent column ranges of the same rows)
   int tma_store;  // ACCFLOW_EPI_STORE_POOL: level 0 leaves through 32 x 32 fp32 TMA store boxes (maps.out)
-  int debug;   // perf experiments only (ACCFLOW_TC_DEBUG): bit 0 = no TMA loads, bit 1 = no MMAs (results are garbage)
+  int debug;   // perf experiments only (ACCFLOW_TC_DEBUG): bit 0 = no TMA loads, bit 1 = no MMAs, bit 5 = no main loop (results are garbage)
   float alpha;
   const float* scale;
   const float* shift;
@@ -440,6 +440,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   int nchunks = 0;
   for (int s = 0; s < p.nsrc; ++s) nchunks += (p.src_c[s] + KC - 1) / KC;
   nchunks *= n_outer;
+  if (p.debug & 32) nchunks = 0;       // perf experiments: no main loop at all (the epilogue's own throughput)
   const int sub_cols = (NPROD > 1 ? 2 : 1) * BN;                // TMEM columns of one 128-pixel sub-tile (MAIN | CORR)
   const int acc_cols = p.msub * sub_cols;                       // TMEM columns of one accumulator slot
   uint32_t tmem_cols = 32;

@@ -18,7 +18,12 @@ d=json.loads(open('gpurun_out/${TAG}_bench_fp16.json').read().strip().splitlines
     gma) timeout 900 python bench.py --ofe gma --clips 4 --no-cpu-baseline --no-ref-cuda > gpurun_out/${TAG}_bench_gma.json 2> gpurun_out/${TAG}_bench_gma.err; echo "gma rc=$?"; python -c "
 import json
 d=json.loads(open('gpurun_out/${TAG}_bench_gma.json').read().strip().splitlines()[-1]); print('gma value',d['value'],'parity',d.get('parity'))" ;;
-    breakdown) timeout 600 python scripts/conv_breakdown.py > gpurun_out/${TAG}_conv_breakdown.txt 2>&1; echo "breakdown rc=$?"; head -40 gpurun_out/${TAG}_conv_breakdown.txt ;;
+    breakdown) CLIPS=${CLIPS:-9} timeout 600 python scripts/conv_breakdown.py > gpurun_out/${TAG}_conv_breakdown.txt 2>&1; echo "breakdown rc=$?"; head -40 gpurun_out/${TAG}_conv_breakdown.txt ;;
+    ncu_conv) timeout 900 ncu --set full --import-source on --clock-control none --profile-from-start off -f -o gpurun_out/${TAG}_conv_targets python scripts/ncu_targets.py ${NCU_TARGETS:-gru_zr gru_q convc2 enc1 convc1} > gpurun_out/${TAG}_ncu_conv.log 2>&1; echo "ncu_conv rc=$?"; tail -3 gpurun_out/${TAG}_ncu_conv.log ;;
+    ncu_aux) timeout 900 ncu --set full --import-source on --clock-control none --profile-from-start off -f -o gpurun_out/${TAG}_aux_targets python scripts/ncu_targets.py ${NCU_AUX:-lookup corr_gemm} > gpurun_out/${TAG}_ncu_aux.log 2>&1; echo "ncu_aux rc=$?"; tail -3 gpurun_out/${TAG}_ncu_aux.log ;;
+    trace3) for x in 3 2 1; do TRACE_EXTRA=$x timeout 300 python scripts/mma_trace.py > gpurun_out/${TAG}_mma_trace_dbg$x.jsonl 2> gpurun_out/${TAG}_mma_trace_dbg$x.err; echo "== dbg $x rc=$?"; cat gpurun_out/${TAG}_mma_trace_dbg$x.jsonl; done ;;
+    trace) timeout 300 python scripts/mma_trace.py > gpurun_out/${TAG}_mma_trace.jsonl 2> gpurun_out/${TAG}_mma_trace.err; echo "trace rc=$?"; cat gpurun_out/${TAG}_mma_trace.jsonl ;;
+    probe) PROBE_PAIRS=${PROBE_PAIRS:-18} timeout 300 python scripts/gru_probe.py > gpurun_out/${TAG}_gru_probe.jsonl 2> gpurun_out/${TAG}_gru_probe.err; echo "probe rc=$?"; cat gpurun_out/${TAG}_gru_probe.jsonl ;;
     *) echo "unknown stage $stage" ;;
   esac
 done

@@ -1,6 +1,7 @@
 """GPU experiment: what bounds the GRU convolutions (and a plain 3x3) of conv_tc_kernel?
-Times each variant with parts of the kernel disabled (ACCFLOW_TC_DEBUG: 1 = no TMA loads, 2 = no MMAs, 4 = no
-phase-2 global traffic, 8 = no TMEM loads; results are garbage with any bit set)."""
+Times each variant with parts of the kernel disabled (ACCFLOW_TC_DEBUG: 1 = no TMA loads, 2 = no MMAs; results are
+garbage with any bit set): dbg32 = the epilogue alone (no main loop), dbg3 = epilogue + the main loop's barrier skeleton,
+dbg2 = + operand traffic, dbg0 = everything."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -69,7 +70,7 @@ for B in (int(x) for x in os.environ.get("PROBE_PAIRS", "18,27").split(",")):
     K.planes_ptr(pre_zr_out, create=True)
     for name, fn in variants.items():
         row = {"pairs": B, "conv": name}
-        for dbg in (0, 2, 4, 6, 8, 1, 3, 12, 15):
+        for dbg in (0, 2, 1, 3, 32):
             os.environ["ACCFLOW_TC_DEBUG"] = str(dbg)
             try:
                 row[f"us_dbg{dbg}"] = round(timeit(fn), 1)
