@@ -864,7 +864,6 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
           }
         } else {
           const uint32_t out_ldb = (uint32_t)p.out_ld * 4u, res_ldb = (uint32_t)p.res_ld * 4u;
-          const uint32_t pl_pb = (uint32_t)p.out_pl.pitch * 2u;
           for (int c = cbeg; c < cend; c += 16) {
             {
               float acc[16];
@@ -903,11 +902,26 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
                     y[itr][0] += pa.x; y[itr][1] += pa.y; y[itr][2] += pa.z; y[itr][3] += pa.w;
                   }
                 }
-                if (p.act == ACCFLOW_ACT_RELU) {          // (out_vec: the activation is none or ReLU, host check)
+                // tanh | relu split (cnet head): a 16-column step lies on one side (act_split % 16 == 0, host check)
+                const bool second = p.act_split > 0 && n0 + c >= p.act_split;
+                const int act = second ? p.act2 : p.act;
+                if (act == ACCFLOW_ACT_RELU) {
 #pragma unroll
                   for (int itr = 0; itr < 4; ++itr) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) y[itr][j] = fmaxf(y[itr][j], 0.f);
+                  }
+                } else if (act == ACCFLOW_ACT_TANH) {
+#pragma unroll
+                  for (int itr = 0; itr < 4; ++itr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) y[itr][j] = tanh_fast(y[itr][j]);
+                  }
+                } else if (act == ACCFLOW_ACT_SIGMOID) {
+#pragma unroll
+                  for (int itr = 0; itr < 4; ++itr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) y[itr][j] = sigmoid_fast(y[itr][j]);
                   }
                 }
                 if (p.residual) {
@@ -925,18 +939,23 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
                     }
                   }
                 }
-                if (p.out) {
-                  char* ob = reinterpret_cast<char*>(p.out + nb);
+                float* const o_f32 = second ? p.out2 : p.out;
+                const PlaneOut& o_pl = second ? p.out2_pl : p.out_pl;
+                const int ncol = second ? nb - p.act_split : nb;
+                if (o_f32) {
+                  char* ob = reinterpret_cast<char*>(o_f32 + ncol);
+                  const uint32_t ldb = second ? (uint32_t)p.out2_ld * 4u : out_ldb;
 #pragma unroll
                   for (int itr = 0; itr < 4; ++itr)
-                    if (rok[itr]) *row_f4(ob, pix4[itr], out_ldb) = make_float4(y[itr][0], y[itr][1], y[itr][2], y[itr][3]);
+                    if (rok[itr]) *row_f4(ob, pix4[itr], ldb) = make_float4(y[itr][0], y[itr][1], y[itr][2], y[itr][3]);
                 }
-                if (p.out_pl.ptr) {
-                  char* pb = reinterpret_cast<char*>(p.out_pl.ptr + nb);
+                if (o_pl.ptr) {
+                  char* pb = reinterpret_cast<char*>(o_pl.ptr + ncol);
+                  const uint32_t ppb = (uint32_t)o_pl.pitch * 2u;
 #pragma unroll
                   for (int itr = 0; itr < 4; ++itr)
                     if (rok[itr])
-                      store_planes4_t<FMT, true>(reinterpret_cast<__nv_bfloat16*>(pb + (size_t)pix4[itr] * pl_pb), p.out_pl.plane_stride, y[itr]);
+                      store_planes4_t<FMT, true>(reinterpret_cast<__nv_bfloat16*>(pb + (size_t)pix4[itr] * ppb), o_pl.plane_stride, y[itr]);
                 }
               } else {
                 // general path: ragged channel tail, tanh | relu split into two destinations (cnet head), sigmoid / tanh
@@ -1273,9 +1292,11 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
                     "conv2d_tc: row_stats (softmax emit) needs a plain 1x1 / per-sample GEMM store epilogue");
     p.row_stats = d.row_stats; p.sm_alpha = d.alpha; p.alpha = 1.0f;
   }
-  p.out_vec = d.epilogue == ACCFLOW_EPI_STORE && d.act_split == 0 && aligned16(d.out) && (!d.out || d.out_ld % 4 == 0) &&
+  // fast path of the store epilogue: four whole channels per thread and row; with the tanh | relu split a 16-column step
+  // must lie on one side.  (Its sigmoid / tanh are the ex2/rcp.approx versions: abs error <= 4e-7.)
+  p.out_vec = d.epilogue == ACCFLOW_EPI_STORE && aligned16(d.out) && (!d.out || d.out_ld % 4 == 0) &&
               (!d.residual || (aligned16(d.residual) && d.res_ld % 4 == 0)) &&
-              (d.act == ACCFLOW_ACT_NONE || d.act == ACCFLOW_ACT_RELU);
+              (d.act_split == 0 || (d.act_split % 16 == 0 && aligned16(d.out2) && (!d.out2 || d.out2_ld % 4 == 0)));
   ACCFLOW_REQUIRE(!d.pre_add || (aligned16(d.pre_add) && d.pre_ld % 4 == 0 && d.cout % 4 == 0 &&
                                  d.epilogue != ACCFLOW_EPI_STORE_POOL),
                   "conv2d_tc: pre_add must be 16B aligned with pre_ld %% 4 == 0 and cout %% 4 == 0");

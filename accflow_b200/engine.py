@@ -113,7 +113,10 @@ class PackedConv:
         """A 3x3 filter with few outputs as a 1x1 conv with 9*cout outputs (row = tap*cout + o); bias, scale and
         activation are applied after the nine taps are summed (accflow_tapsum3x3_f32)."""
         if getattr(self, "_astaps", None) is None:
-            w = self.w_oihw.permute(2, 3, 0, 1).reshape(self.kh * self.kw * self.cout, self.cin, 1, 1).contiguous()
+            w = self.w_oihw.permute(2, 3, 0, 1).reshape(self.kh * self.kw * self.cout, self.cin, 1, 1)
+            if w.shape[0] % 4:       # zero rows up to a multiple of 4: every output group takes the epilogue's vector path
+                w = torch.cat([w, w.new_zeros(4 - w.shape[0] % 4, self.cin, 1, 1)])
+            w = w.contiguous()
             pc = PackedConv.__new__(PackedConv)
             pc.w_oihw, pc._tc, pc._as1x1, pc._astaps = w, None, None, None
             pc.cout, pc.cin, pc.kh, pc.kw = w.shape
@@ -405,7 +408,7 @@ class Kernels:
         if self.tc:
             n9 = 9 * pc.cout
             t = self.view(f"tapsum{n9}", x.b, x.h, x.w, (n9 + 3) // 4 * 4)
-            self.conv(pc.as_taps1x1(), [x], t.ch(0, n9))
+            self.conv(pc.as_taps1x1(), [x], t)           # (rows 9*cout.. of the padded filter are zero)
             L.call("accflow_tapsum3x3_f32", t.ptr, t.ld, x.b, x.h, x.w, pc.cout, scale, pc.shift.data_ptr(), act,
                    out.ptr, out.ld, None if accum is None else accum.data_ptr(), accum_ld, _stream())
         else:

@@ -34,6 +34,6 @@ for tag, (a, b, fl) in zip(tags, eng.k.profile):
     agg[tag][0] += 1; agg[tag][1] += ms; agg[tag][2] += fl
 cm = sum(v[1] for v in agg.values())
 print(f"precision {prec}: step {tot:.1f} ms, conv launches {len(tags)}, conv time {cm:.1f} ms")
-for tag, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
+for tag, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get("TOP", "60"))]:
     kh, kw, st, cin, cout, pix = tag
     print(f"{v[1]:7.2f} ms {100*v[1]/cm:5.1f}%  n={v[0]:4d}  avg {1e3*v[1]/v[0]:7.1f} us  {v[2]/v[1]/1e9:7.1f} TFLOP/s   {kh}x{kw}/s{st} {cin}->{cout}  pix={pix}")

@@ -24,6 +24,7 @@ d=json.loads(open('gpurun_out/${TAG}_bench_gma.json').read().strip().splitlines(
     trace3) for x in 3 2 1; do TRACE_EXTRA=$x timeout 300 python scripts/mma_trace.py > gpurun_out/${TAG}_mma_trace_dbg$x.jsonl 2> gpurun_out/${TAG}_mma_trace_dbg$x.err; echo "== dbg $x rc=$?"; cat gpurun_out/${TAG}_mma_trace_dbg$x.jsonl; done ;;
     trace) timeout 300 python scripts/mma_trace.py > gpurun_out/${TAG}_mma_trace.jsonl 2> gpurun_out/${TAG}_mma_trace.err; echo "trace rc=$?"; cat gpurun_out/${TAG}_mma_trace.jsonl ;;
     probe) PROBE_PAIRS=${PROBE_PAIRS:-18} timeout 300 python scripts/gru_probe.py > gpurun_out/${TAG}_gru_probe.jsonl 2> gpurun_out/${TAG}_gru_probe.err; echo "probe rc=$?"; cat gpurun_out/${TAG}_gru_probe.jsonl ;;
+    launches) timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python scripts/one_step.py > gpurun_out/${TAG}_launches.log 2>&1; echo "launches rc=$?"; python scripts/agg_launches.py gpurun_out/${TAG}_launches.csv 24 | tee gpurun_out/${TAG}_launches_summary.txt ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
