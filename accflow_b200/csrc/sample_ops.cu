@@ -376,6 +376,148 @@ __global__ void __launch_bounds__(256) corr_lookup_fast_kernel(const LookupP p) 
   }
 }
 
+// Radius-4 lookup, flat channel pairs (round 2, second rewrite).  ncu on corr_lookup_fast_kernel: 83 % of the SM's
+// issue slots busy at ~1 700 instructions per pixel, 38 % of DRAM: issue-bound.  This version spends ~half of that:
+//  * the 324 output channels are one run of 162 channel PAIRS; lane l finishes pairs l, l+32, ... (6 rounds, 84 % of
+//    the lane slots used instead of 12 rounds of single channels) and writes a pair as one 4-byte store per plane
+//    (fp32: one float2) - half the store instructions and half the address arithmetic;
+//  * the axis tables of all four levels are built first (72 entries, 3 rounds) with the validity folded into the
+//    weights (outside the map: both weights 0, index 0), so a tap is branch-free: 2 table reads, 4 texels,
+//    a separable bilinear blend;
+//  * the y table holds row offsets (index * patch pitch).
+// The arithmetic per tap is the reference's (coordinate round trip of raft/utils/utils.py:70-74 evaluated per window
+// column / row); only the order of the four-term blend differs (<= 1 ulp).
+// Two adjacent channels -> fp32 (float2, may be NULL) and / or operand planes of format FMT (0: none): one store per plane.
+template <int FMT>
+__device__ __forceinline__ void lookup_store_pair(float* o32, __nv_bfloat16* d, long long pl_stride, float v0, float v1) {
+  if (o32) *reinterpret_cast<float2*>(o32) = make_float2(v0, v1);
+  if constexpr (FMT != 0) {
+    if constexpr (FMT == 2 || FMT == ACCFLOW_PLANES_FP16) {
+      v0 = sat_fp16(v0); v1 = sat_fp16(v1);
+      const __half2 hi = __floats2half2_rn(v0, v1);
+      *reinterpret_cast<__half2*>(d) = hi;
+      if constexpr (FMT == 2) {
+        const float2 hf = __half22float2(hi);
+        *reinterpret_cast<__half2*>(d + pl_stride) = __floats2half2_rn((v0 - hf.x) * ACCFLOW_FP16X2_SCALE, (v1 - hf.y) * ACCFLOW_FP16X2_SCALE);
+      }
+    } else {
+      const __nv_bfloat162 q0 = __floats2bfloat162_rn(v0, v1);
+      *reinterpret_cast<__nv_bfloat162*>(d) = q0;
+      if constexpr (FMT == 3) {
+        const float r0 = v0 - __bfloat162float(q0.x), r1 = v1 - __bfloat162float(q0.y);
+        const __nv_bfloat162 q1 = __floats2bfloat162_rn(r0, r1);
+        *reinterpret_cast<__nv_bfloat162*>(d + pl_stride) = q1;
+        *reinterpret_cast<__nv_bfloat162*>(d + 2 * pl_stride) =
+            __floats2bfloat162_rn(r0 - __bfloat162float(q1.x), r1 - __bfloat162float(q1.y));
+      }
+    }
+  }
+}
+
+// grid_roundtrip with the exact halving written as a multiplication (x / 2 == x * 0.5 in IEEE arithmetic).
+__device__ __forceinline__ float grid_roundtrip_h(float x, int size) {
+  const float s = (float)(size - 1);
+  const float xn = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, x), s), 1.f);
+  return __fmul_rn(__fmul_rn(__fadd_rn(xn, 1.f), 0.5f), s);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) corr_lookup_pairs_kernel(const LookupP p) {
+  constexpr int R = 4, K1 = 9, K2 = 81, PD = 12, NCH = 4 * K2, NPAIR = NCH / 2, NIT = (NPAIR + 31) / 32;
+  __shared__ float patch[8][4][PD * PD];
+  __shared__ float4 axis[8][4][2][12];          // per level: 9 window columns (x), 9 window rows (y): (byte offset, w0, w1, -)
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned upix = blockIdx.x * 8u + (unsigned)wib;          // < 2^31 (host check)
+  if (upix >= (unsigned)(p.batch * p.h * p.w)) return;
+  const long long pix = upix;
+  const float cx = __ldg(p.coords + pix * 2), cy = __ldg(p.coords + pix * 2 + 1);
+  const int xx = lane & 15, yh = lane >> 4;     // patch loader: column, row parity
+  // All four patches are requested up front with 4-byte cp.async (zero fill outside the map): rows outside the map are
+  // clamped to a valid row and requested with source size 0.
+#pragma unroll
+  for (int lvl = 0; lvl < 4; ++lvl) {
+    const int H = p.lh[lvl], W = p.lw[lvl];
+    const float inv = 1.f / (float)(1 << lvl);
+    const float bx = cx * inv, by = cy * inv;
+    const float fxo = floorf(fminf(fmaxf(bx, -1.0e6f), 1.0e6f)), fyo = floorf(fminf(fmaxf(by, -1.0e6f), 1.0e6f));
+    const int x0 = (int)fxo - R - 1, y0 = (int)fyo - R - 1;      // patch origin: one texel of slack on each side
+    const int gx = x0 + xx;
+    const bool xok = gx >= 0 && gx < W;
+    const float* col = p.lvl[lvl] + (size_t)upix * (unsigned)(H * W) + (xok ? gx : 0);
+    const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(&patch[wib][lvl][xx]);
+    if (xx < PD) {
+#pragma unroll
+      for (int it = 0; it < PD / 2; ++it) {
+        const int yy = 2 * it + yh, gy = y0 + yy;
+        const int gyc = min(max(gy, 0), H - 1);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + (uint32_t)(yy * PD * 4)),
+                     "l"(col + gyc * W), "r"((xok && gy == gyc) ? 4 : 0) : "memory");
+      }
+    }
+  }
+  // axis tables while the gathers are in flight: entry e = (level, axis, k), 72 entries
+#pragma unroll
+  for (int rnd = 0; rnd < 3; ++rnd) {
+    const int e = lane + 32 * rnd;
+    if (e < 72) {
+      const int lvl = e / 18, rem = e - lvl * 18, ax = rem >= 9 ? 1 : 0, k = rem - 9 * ax;
+      const float inv = 1.f / (float)(1 << lvl);
+      const float b = (ax ? cy : cx) * inv;
+      const float bo = floorf(fminf(fmaxf(b, -1.0e6f), 1.0e6f));
+      const int size = (ax ? p.h : p.w) >> lvl, org = (int)bo - R - 1;
+      const float c = grid_roundtrip_h(__fadd_rn(b, (float)(k - R)), size);
+      const float cf = floorf(c);
+      const bool in_range = c > -2.f && c < (float)size + 1.f;
+      const int idx = in_range ? (int)cf - org : -1;
+      // idx must address a 2-texel run inside the patch; otherwise the tap is outside the map for every finite
+      // coordinate (the patch has a texel of slack), so it contributes zero: weights 0, offset 0
+      const bool ok = in_range && idx >= 0 && idx + 1 < PD;
+      const int off = ok ? (ax ? idx * PD * 4 : idx * 4) : 0;
+      axis[wib][lvl][ax][k] = make_float4(__int_as_float(off), ok ? (cf + 1.f) - c : 0.f, ok ? c - cf : 0.f, 0.f);
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
+  // channel ch = 81 * level + 9 * a + b (a: window column, b: window row).  Lane l starts at ch = 2l (level 0) and moves
+  // 64 channels = (a + 7, b + 1) per round; the indices are carried, not divided out.
+  int a = (2 * lane) / K1, bb = 2 * lane - K1 * a;
+  const float4* ax = &axis[wib][0][0][0];       // level base: [0..11] columns, [12..23] rows
+  const char* pt = reinterpret_cast<const char*>(&patch[wib][0][0]);
+  float* o32 = p.out ? p.out + pix * p.out_ld + 2 * lane : nullptr;
+  __nv_bfloat16* opl = FMT ? p.out_pl + pix * p.pl_pitch + 2 * lane : nullptr;
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    if (it < NIT - 1 || lane < NPAIR - 32 * (NIT - 1)) {
+      float v[2];
+      int a1 = a, b1 = bb;
+      const float4* ax1 = ax;
+      const char* pt1 = pt;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const float4 ex = ax1[a1], ey = ax1[12 + b1];
+        const float* q = reinterpret_cast<const float*>(pt1 + __float_as_int(ey.x) + __float_as_int(ex.x));
+        const float top = fmaf(q[1], ex.z, q[0] * ex.y), bot = fmaf(q[PD + 1], ex.z, q[PD] * ex.y);
+        v[hh] = fmaf(bot, ey.z, top * ey.y);
+        if (hh == 0 && ++b1 == K1) {            // second channel of the pair: next row, carrying into column / level
+          b1 = 0;
+          if (++a1 == K1) { a1 = 0; ax1 += 24; pt1 += PD * PD * 4; }
+        }
+      }
+      lookup_store_pair<FMT>(o32 ? o32 + 64 * it : nullptr, opl + 64 * it, p.pl_stride, v[0], v[1]);
+    }
+    a += 7; ++bb;
+    if (bb >= K1) { bb -= K1; ++a; }
+    if (a >= K1) { a -= K1; ax += 24; pt += PD * PD * 4; }
+  }
+  if (lane == 0) {
+    const unsigned hw = (unsigned)(p.h * p.w), pl = upix % hw, py = pl / (unsigned)p.w;
+    const float fx = cx - (float)(pl - py * (unsigned)p.w), fy = cy - (float)py;
+    if (p.flow_out) *reinterpret_cast<float2*>(p.flow_out + pix * 2) = make_float2(fx, fy);
+    if (p.mf_tail)
+      lookup_store_pair<FMT>(p.mf_tail + pix * p.mf_ld, FMT && p.tail_pl ? p.tail_pl + pix * p.tail_pitch : nullptr, p.tail_stride, fx, fy);
+  }
+}
+
 __global__ void coords_init_kernel(const float* __restrict__ finit, int batch, int h, int w, float* __restrict__ coords) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   const int hw = h * w;
@@ -758,8 +900,25 @@ extern "C" int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, con
   ACCFLOW_REQUIRE((!out_planes && !tail_planes) || valid_plane_fmt(nplanes), "corr_lookup: bad plane format");
   p.out_pl = reinterpret_cast<__nv_bfloat16*>(out_planes); p.pl_pitch = pl_pitch; p.pl_stride = pl_stride; p.nplanes = nplanes;
   p.tail_pl = reinterpret_cast<__nv_bfloat16*>(tail_planes); p.tail_pitch = tail_pitch; p.tail_stride = tail_stride;
-  if (radius == 4) corr_lookup_fast_kernel<4><<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(p);     // RAFT / GMA
-  else corr_lookup_kernel<0><<<cdiv((long long)batch * h * w, 8), 256, 0, ST>>>(p);
+  const int nblk = cdiv((long long)batch * h * w, 8);
+  auto al = [](const void* q, unsigned m) { return (reinterpret_cast<uintptr_t>(q) & m) == 0; };
+  const bool pairs_ok = radius == 4 && (long long)batch * h * w < (1ll << 31) && al(coords, 7) &&
+                        (!out || (out_ld % 2 == 0 && al(out, 7))) && (!flow_out || al(flow_out, 7)) &&
+                        (!out_planes || (pl_pitch % 2 == 0 && pl_stride % 2 == 0 && al(out_planes, 3))) &&
+                        (!mf_tail || (mf_ld % 2 == 0 && al(mf_tail, 7))) &&
+                        (!tail_planes || (out_planes && tail_pitch % 2 == 0 && tail_stride % 2 == 0 && al(tail_planes, 3)));
+  static int variant = -1;            // ACCFLOW_LOOKUP=fast: the single-channel kernel (kept for A/B measurements)
+  if (variant < 0) { const char* e = getenv("ACCFLOW_LOOKUP"); variant = (e && !strcmp(e, "fast")) ? 1 : 0; }
+  if (pairs_ok && variant == 0) {     // RAFT / GMA
+    switch (out_planes ? nplanes : 0) {
+      case 0: corr_lookup_pairs_kernel<0><<<nblk, 256, 0, ST>>>(p); break;
+      case 1: corr_lookup_pairs_kernel<1><<<nblk, 256, 0, ST>>>(p); break;
+      case 2: corr_lookup_pairs_kernel<2><<<nblk, 256, 0, ST>>>(p); break;
+      case 3: corr_lookup_pairs_kernel<3><<<nblk, 256, 0, ST>>>(p); break;
+      default: corr_lookup_pairs_kernel<4><<<nblk, 256, 0, ST>>>(p); break;
+    }
+  } else if (radius == 4) corr_lookup_fast_kernel<4><<<nblk, 256, 0, ST>>>(p);
+  else corr_lookup_kernel<0><<<nblk, 256, 0, ST>>>(p);
   return launched("corr_lookup");
 }
 

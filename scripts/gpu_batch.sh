@@ -25,6 +25,7 @@ d=json.loads(open('gpurun_out/${TAG}_bench_gma.json').read().strip().splitlines(
     trace) timeout 300 python scripts/mma_trace.py > gpurun_out/${TAG}_mma_trace.jsonl 2> gpurun_out/${TAG}_mma_trace.err; echo "trace rc=$?"; cat gpurun_out/${TAG}_mma_trace.jsonl ;;
     probe) PROBE_PAIRS=${PROBE_PAIRS:-18} timeout 300 python scripts/gru_probe.py > gpurun_out/${TAG}_gru_probe.jsonl 2> gpurun_out/${TAG}_gru_probe.err; echo "probe rc=$?"; cat gpurun_out/${TAG}_gru_probe.jsonl ;;
     launches) timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python scripts/one_step.py > gpurun_out/${TAG}_launches.log 2>&1; echo "launches rc=$?"; python scripts/agg_launches.py gpurun_out/${TAG}_launches.csv 24 | tee gpurun_out/${TAG}_launches_summary.txt ;;
+    lookup_ab) (python scripts/lookup_ab.py; ACCFLOW_LOOKUP=fast python scripts/lookup_ab.py) > gpurun_out/${TAG}_lookup_ab.jsonl 2> gpurun_out/${TAG}_lookup_ab.err; echo "lookup_ab rc=$?"; cat gpurun_out/${TAG}_lookup_ab.jsonl ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
