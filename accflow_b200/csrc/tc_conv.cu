@@ -96,8 +96,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes, uint32_t on = 1) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}"
+               ::"r"(smem_u32(bar)), "r"(bytes), "r"(on) : "memory");
 }
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -138,18 +139,20 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                            int c2, int c3) {
+                                            int c2, int c3, uint32_t on = 1) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %7, 0;\n"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n}"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(on)
       : "memory");
 }
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                            int c2, int c3, int c4) {
+                                            int c2, int c3, int c4, uint32_t on = 1) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %8, 0;\n"
+      "@q cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n}"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(on)
       : "memory");
 }
 
@@ -168,17 +171,31 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+// The MMA-issuing warp runs its loop warp-uniformly (all 32 lanes execute the same scalar stream, so ring positions,
+// parities and descriptors live on the uniform datapath and reach UTCHMMA without R2UR moves); the instructions with side
+// effects carry the elected lane's predicate `on`.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred;
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint32_t on = 1) {
   asm volatile(
       "{\n"
-      ".reg .pred p;\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %1, 0;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}" ::"r"(smem_u32(bar)), "r"(on) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate, uint32_t on = 1) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(on)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
@@ -328,6 +345,7 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
   const uint32_t idesc1 = make_idesc(BM, c.BN, c.fp16 != 0);
   const uint32_t idesc2 = make_idesc(BM, 2 * c.BN, c.fp16 != 0);      // a0 x [w0; w1] -> MAIN | CORR
   const bool comb = c.n_inner == 1;        // operands share the weight ring's barriers (SA == SB, slots advance together)
+  const uint32_t on = elect_one();         // the lane that issues (the whole warp runs this loop, see umma_bf16)
   int sa = 0, sb = 0, ntr = 0;
   bool next_ready = false, a_ready = false;
   uint32_t pa = 0, pb = 0;                                           // ring parities
@@ -351,7 +369,7 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
         // probe target: the next weight tile's barrier (ring successor), tested while this tile's MMAs drain
         const int sbn = sb + 1 == c.SB ? 0 : sb + 1;
         const uint32_t pbn = sb + 1 == c.SB ? pb ^ 1u : pb;
-        const bool tr = (c.debug & 16) && blockIdx.x == 0 && ntr < 1024;
+        const bool tr = (c.debug & 16) && blockIdx.x == 0 && ntr < 1024 && on;
         if (tr) g_tc_trace[3 * ntr] = clock64();
         const uint32_t w_lo = desc_lo(w_slot);
         if (!(c.debug & 2)) {
@@ -371,18 +389,18 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
               const uint64_t a0 = desc_from_lo(as_lo + 2 * k4), w0 = desc_from_lo(w_lo + 2 * k4);
               const uint32_t acc = first | (uint32_t)k4;
               if (NPROD == 1) {
-                umma_bf16(sm_main, a0, w0, idesc1, acc);
+                umma_bf16(sm_main, a0, w0, idesc1, acc, on);
               } else {
                 const uint64_t a1 = desc_from_lo(as_lo + c.a_plane16 + 2 * k4);
-                umma_bf16(sm_main, a0, w0, idesc2, acc);             // MAIN += a0 w0 ; CORR += a0 w1
-                umma_bf16(sm_corr, a1, w0, idesc1, 1);               // CORR += a1 w0
+                umma_bf16(sm_main, a0, w0, idesc2, acc, on);         // MAIN += a0 w0 ; CORR += a0 w1
+                umma_bf16(sm_corr, a1, w0, idesc1, 1, on);           // CORR += a1 w0
                 if (NPROD == 6) {
                   const uint64_t w1 = desc_from_lo(w_lo + c.w_plane16 + 2 * k4);
                   const uint64_t a2 = desc_from_lo(as_lo + 2 * c.a_plane16 + 2 * k4);
                   const uint64_t w2 = desc_from_lo(w_lo + 2 * c.w_plane16 + 2 * k4);
-                  umma_bf16(sm_corr, a1, w1, idesc1, 1);
-                  umma_bf16(sm_corr, a0, w2, idesc1, 1);
-                  umma_bf16(sm_corr, a2, w0, idesc1, 1);
+                  umma_bf16(sm_corr, a1, w1, idesc1, 1, on);
+                  umma_bf16(sm_corr, a0, w2, idesc1, 1, on);
+                  umma_bf16(sm_corr, a2, w0, idesc1, 1, on);
                 }
               }
             }
@@ -390,17 +408,17 @@ __device__ __forceinline__ void mma_issue_loop(const MmaCtx& c) {
         }
         first = 1;
         if (tr) g_tc_trace[3 * ntr + 1] = clock64();
-        umma_commit(&c.bfree[sb]);                                   // weight tile reusable once these MMAs retire
+        umma_commit(&c.bfree[sb], on);                               // weight tile reusable once these MMAs retire
         if (tr) { g_tc_trace[3 * ntr + 2] = clock64(); ++ntr; }
         a_lo += 1024 >> 4;                                           // shift modes: next tap = 8 pixel rows further
         w_slot += c.b_stage;
         if (++sb == c.SB) { sb = 0; pb ^= 1; w_slot = c.smem_b; }
       }
-      if (!comb) umma_commit(&c.afree[sa]);                          // ... and so is the activation box
+      if (!comb) umma_commit(&c.afree[sa], on);                      // ... and so is the activation box
       a_slot += c.a_stage;
       if (++sa == c.SA) { sa = 0; pa ^= 1; a_slot = c.smem_a; }
     }
-    umma_commit(&c.acc_full[slot]);
+    umma_commit(&c.acc_full[slot], on);
   }
 }
 
@@ -422,7 +440,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
   // per-tile epilogue affine (alpha folded in), staged once per tile; two copies: a warp set may run one tile ahead
   __shared__ __align__(16) float s_scale[2][256], s_shift[2][256];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // provably warp-uniform: role branches do not diverge
   constexpr int NPL = Fmt<FMT>::NPL;
   const int BN = p.bn, SA = p.stages, SB = p.stages_b;
   const int n_outer = p.n_outer, n_inner = p.n_inner;          // A boxes per K block / taps served by one box
@@ -483,7 +502,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
     // are carried and updated only when they change, nothing is divided or re-derived per step.
     const bool comb = n_inner == 1;
     const bool w_thread = warp == 0, a_thread = comb ? warp == 0 : warp == 10;
-    if (lane == 0 && (w_thread || a_thread)) {
+    if (w_thread || a_thread) {            // warp-uniform (see umma_bf16): the elected lane's predicate gates the side effects
+      const uint32_t on = elect_one();
       const bool no_tma = (p.debug & 1) != 0;
       const uint32_t a_bytes = no_tma ? 0u : (uint32_t)a_stage, b_bytes = no_tma ? 0u : (uint32_t)b_stage;
       int sa = 0, sb = 0;                                    // ring positions (A boxes, weight tiles)
@@ -509,14 +529,14 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             uint8_t* adst = smem + (size_t)(comb ? sb : sa) * a_stage;
             if (comb) {
               mbar_wait(&bar_bfree[sb], pb);
-              mbar_expect_tx(abar, a_bytes + b_bytes);
+              mbar_expect_tx(abar, a_bytes + b_bytes, on);
             } else {
               mbar_wait(&bar_afree[sa], pa);
-              mbar_expect_tx(abar, a_bytes);
+              mbar_expect_tx(abar, a_bytes, on);
               if (++sa == SA) { sa = 0; pa ^= 1; }
             }
             // one TMA op brings all operand planes (the plane index is the box's outermost dimension)
-            if (!no_tma) tma_load_5d(adst, &maps.a[s], abar, c0, b1 + d1, b2 + d2, sample, 0);
+            if (!no_tma) tma_load_5d(adst, &maps.a[s], abar, c0, b1 + d1, b2 + d2, sample, 0, on);
           }
           if (w_thread) {
             const int kcoord = p.src_off[s] + c0;
@@ -524,9 +544,9 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
             for (int j = 0; j < n_inner; ++j, tap += tstep) {
               if (!comb) {
                 mbar_wait(&bar_bfree[sb], pb);
-                mbar_expect_tx(&bar_bfull[sb], b_bytes);
+                mbar_expect_tx(&bar_bfull[sb], b_bytes, on);
               }
-              if (!no_tma) tma_load_4d(smem_b + (size_t)sb * b_stage, &maps.w, &bar_bfull[sb], kcoord, n0, tap, 0);
+              if (!no_tma) tma_load_4d(smem_b + (size_t)sb * b_stage, &maps.w, &bar_bfull[sb], kcoord, n0, tap, 0, on);
               if (++sb == SB) { sb = 0; pb ^= 1; }
             }
           }
@@ -551,7 +571,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==============================================
-    if (lane == 0) {
+    {
       MmaCtx c;
       c.total_tiles = total_tiles; c.stride_tiles = gridDim.x; c.first_tile = blockIdx.x;
       c.nchunks = nchunks; c.n_inner = n_inner; c.SA = SA; c.SB = SB; c.BN = BN;
