@@ -1117,7 +1117,10 @@ extern "C" int accflow_tc_debug_trace(long long* host, int n) {
 }
 
 static int tc_bn_for(int cout, int nprod) {
-  const int bn_cap = nprod <= 2 ? 256 : 128;          // single-product modes (1 = bf16, 2 = fp16): one accumulator
+  int bn_cap = nprod <= 2 ? 256 : 128;                // single-product modes (1 = bf16, 2 = fp16): one accumulator
+  static int env_cap = -1;                            // perf experiments: ACCFLOW_TC_BN_CAP
+  if (env_cap < 0) { const char* e = getenv("ACCFLOW_TC_BN_CAP"); env_cap = e ? atoi(e) : 0; }
+  if (env_cap >= 32 && env_cap < bn_cap) bn_cap = env_cap;
   const int ntiles = cdiv(cout, bn_cap);
   return cdiv(cdiv(cout, ntiles), 32) * 32;
 }
@@ -1235,7 +1238,9 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
     const int slow_extent = p.mode == 1 ? p.out_h : p.out_w;
     // (narrower N tiles with two sub-tiles for the 256-channel layers were measured and are slower: the N = 64 MMA costs
     //  48 clk for 32 clk of math - GRU z|r 136 -> 158 us, profiles/r2o_narrow_tile_experiment.txt)
-    if (msub_enabled && p.mode != 0 && 2 * 2 * sub_cols <= 512 && slow_extent > 16 && m_tiles_all >= 4 * 148) {
+    static int msub_min = -1;                         // perf experiments: ACCFLOW_TC_MSUB_MIN (default 4 * 148 tiles)
+    if (msub_min < 0) { const char* e = getenv("ACCFLOW_TC_MSUB_MIN"); msub_min = e ? atoi(e) : 4 * 148; }
+    if (msub_enabled && p.mode != 0 && 2 * 2 * sub_cols <= 512 && slow_extent > 16 && m_tiles_all >= msub_min) {
       p.msub = 2;
       if (p.mode == 1) { p.tile_h = 32; p.tiles_y = cdiv(p.out_h, 32); } else { p.tile_w = 32; p.tiles_x = cdiv(p.out_w, 32); }
     }

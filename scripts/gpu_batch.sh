@@ -26,6 +26,12 @@ d=json.loads(open('gpurun_out/${TAG}_bench_gma.json').read().strip().splitlines(
     probe) PROBE_PAIRS=${PROBE_PAIRS:-18} timeout 300 python scripts/gru_probe.py > gpurun_out/${TAG}_gru_probe.jsonl 2> gpurun_out/${TAG}_gru_probe.err; echo "probe rc=$?"; cat gpurun_out/${TAG}_gru_probe.jsonl ;;
     launches) timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python scripts/one_step.py > gpurun_out/${TAG}_launches.log 2>&1; echo "launches rc=$?"; python scripts/agg_launches.py gpurun_out/${TAG}_launches.csv 24 | tee gpurun_out/${TAG}_launches_summary.txt ;;
     lookup_ab) (python scripts/lookup_ab.py; ACCFLOW_LOOKUP=fast python scripts/lookup_ab.py) > gpurun_out/${TAG}_lookup_ab.jsonl 2> gpurun_out/${TAG}_lookup_ab.err; echo "lookup_ab rc=$?"; cat gpurun_out/${TAG}_lookup_ab.jsonl ;;
+    narrow) for cfg in "128 592" "64 256" "64 592" "96 256"; do set -- $cfg; echo "== BN_CAP=$1 MSUB_MIN=$2"; ACCFLOW_TC_BN_CAP=$1 ACCFLOW_TC_MSUB_MIN=$2 PROBE_PAIRS=18 timeout 300 python scripts/gru_probe.py 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print(d['conv'][:44].ljust(44), d['us_dbg0'], d['us_dbg32'])
+"; done > gpurun_out/${TAG}_narrow.txt 2>&1; cat gpurun_out/${TAG}_narrow.txt ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
