@@ -32,6 +32,19 @@ for l in sys.stdin:
     if l.startswith('{'):
         d=json.loads(l); print(d['conv'][:44].ljust(44), d['us_dbg0'], d['us_dbg32'])
 "; done > gpurun_out/${TAG}_narrow.txt 2>&1; cat gpurun_out/${TAG}_narrow.txt ;;
+    bf16) timeout 600 python bench.py --precision bf16 --no-ref-cuda > gpurun_out/${TAG}_bench_bf16.json 2> gpurun_out/${TAG}_bench_bf16.err; echo "bf16 rc=$?"; python -c "
+import json
+d=json.loads(open('gpurun_out/${TAG}_bench_bf16.json').read().strip().splitlines()[-1]); print('bf16 value',d['value'],'e2e',d['e2e']['value'],'parity',d.get('parity'))" ;;
+    fp16full) timeout 600 python bench.py --precision fp16 --no-ref-cuda > gpurun_out/${TAG}_bench_fp16.json 2> gpurun_out/${TAG}_bench_fp16.err; echo "fp16full rc=$?"; python -c "
+import json
+d=json.loads(open('gpurun_out/${TAG}_bench_fp16.json').read().strip().splitlines()[-1]); print('fp16 value',d['value'],'e2e',d['e2e']['value'],'parity',d.get('parity'))" ;;
+    gmafull) timeout 900 python bench.py --ofe gma --clips 4 --no-ref-cuda > gpurun_out/${TAG}_bench_gma.json 2> gpurun_out/${TAG}_bench_gma.err; echo "gmafull rc=$?"; python -c "
+import json
+d=json.loads(open('gpurun_out/${TAG}_bench_gma.json').read().strip().splitlines()[-1]); print('gma value',d['value'],'e2e',d['e2e']['value'],'parity',d.get('parity'))" ;;
+    warm) timeout 600 python bench.py --warm-start --no-ref-cuda > gpurun_out/${TAG}_bench_warm_start.json 2> gpurun_out/${TAG}_bench_warm_start.err; echo "warm rc=$?"; python -c "
+import json
+d=json.loads(open('gpurun_out/${TAG}_bench_warm_start.json').read().strip().splitlines()[-1]); print('warm value',d['value'],'parity',d.get('parity'))" ;;
+    memcheck) timeout 1200 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_kernels.py -q -x -m gpu > gpurun_out/${TAG}_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/${TAG}_sanitizer_memcheck.log ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
