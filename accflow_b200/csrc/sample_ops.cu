@@ -518,6 +518,164 @@ __global__ void __launch_bounds__(256) corr_lookup_pairs_kernel(const LookupP p)
   }
 }
 
+#define ACCFLOW_LOOKUP_SEP_WARP_BYTES 6720   /* 4 patches (12 rows x 80 B) + 4 x 108 row-interpolated values + 72 axis entries */
+// Radius-4 lookup, separable and software-pipelined (round 2, third rewrite; needs w % 32 == 0 so that every level's rows
+// are whole 16-byte chunks).  corr_lookup_pairs_kernel is issue-bound (1 330 instructions per pixel, mostly the address
+// arithmetic of 24 four-byte cp.async per lane and of four texel reads per output).  Here a warp walks over pixels
+// (persistent grid) and per pixel:
+//  A. the four 12 x 16 patches arrive as 16-byte cp.async.cg of ALIGNED chunks (origin rounded down to a multiple of
+//     four texels; a chunk is wholly inside or outside the map): 6 requests per lane instead of 24;
+//  B. the axis tables are built (same arithmetic as the pairs kernel, raft/utils/utils.py:70-74);
+//  C. horizontal pass: H[y][a] = w0[a] P[y][ix[a]] + w1[a] P[y][ix[a] + 1] for the 12 rows x 9 window columns
+//     (lane = 9 * (y mod 3) + a: every address is lane base + immediate).  The patch buffer is dead after this pass:
+//     the NEXT pixel's gathers are issued here and fly during D, E and the next B (a gather-only run of this kernel
+//     takes 48 us per 18 pairs, the un-pipelined version 91 us: the two phases did not overlap);
+//  D. vertical pass: out[a][b] = wy0[b] H[iy[b]][a] + wy1[b] H[iy[b] + 1][a] (lane = 9 * (a mod 3) + b), two shared loads
+//     per output instead of four plus the table reads; results are staged in channel order over the consumed part of H;
+//  E. the 324 channels leave as 81 quads: one 8-byte store per operand plane (float4 for the fp32 copy).
+// The products and their order are the pairs kernel's, so the two kernels agree bit for bit.
+__device__ __forceinline__ void lookup_sep_gather(const LookupP& p, unsigned upix, float cx, float cy, uint32_t wb_s, int lane) {
+  constexpr int R = 4, PITCH = 80, LVB = 12 * PITCH;
+  int xa[4], y0[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const float inv = 1.f / (float)(1 << l);
+    const float fxo = floorf(fminf(fmaxf(cx * inv, -1.0e6f), 1.0e6f)), fyo = floorf(fminf(fmaxf(cy * inv, -1.0e6f), 1.0e6f));
+    xa[l] = ((int)fxo - R - 1) & ~3;                              // patch origin: one texel of slack, rounded down to a chunk
+    y0[l] = (int)fyo - R - 1;
+  }
+  const int chunk4 = (lane & 3) * 4;
+  // request (level, row, chunk) = lane + 32 k, 48 requests per level
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int lf = (32 * k) / 48, ll = (32 * k + 31) / 48;        // levels of lane 0 / lane 31 in this round (compile time)
+    const bool up = lf != ll && lane + 32 * k >= 48 * ll;
+    const int row = ((lane + 32 * k - 48 * lf) >> 2) - (up ? 12 : 0);
+    const int H = up ? p.lh[ll] : p.lh[lf], W = up ? p.lw[ll] : p.lw[lf];
+    const int gy = (up ? y0[ll] : y0[lf]) + row, gx = (up ? xa[ll] : xa[lf]) + chunk4;
+    const bool ok = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+    const float* src = (up ? p.lvl[ll] : p.lvl[lf]) + (size_t)upix * (unsigned)(H * W) + (ok ? gy * W + gx : 0);
+    const uint32_t dst = wb_s + (uint32_t)((up ? ll : lf) * LVB + row * PITCH + chunk4 * 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+  }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) corr_lookup_sep_kernel(const LookupP p) {
+  constexpr int R = 4, PITCH = 80 /* bytes per patch row: 16 texels + 4 of bank skew */, LVB = 12 * PITCH;
+  constexpr int H_OFF = 4 * LVB, HLV = 108 * 4, AXIS_OFF = H_OFF + 4 * HLV, WARP_BYTES = AXIS_OFF + 72 * 16;
+  static_assert(WARP_BYTES == ACCFLOW_LOOKUP_SEP_WARP_BYTES, "host launch size");
+  extern __shared__ __align__(16) unsigned char lk_smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned total = (unsigned)(p.batch * p.h * p.w), stride = gridDim.x * 8u;   // < 2^31 (host check)
+  unsigned upix = blockIdx.x * 8u + (unsigned)wib;
+  if (upix >= total) return;
+  unsigned char* wb = lk_smem + wib * WARP_BYTES;
+  const uint32_t wb_s = (uint32_t)__cvta_generic_to_shared(wb);
+  float4* axis = reinterpret_cast<float4*>(wb + AXIS_OFF);
+  const bool act = lane < 27;
+  const int l9 = lane / 9, m9 = lane - 9 * l9;                    // (row or column group, window column or row)
+  float2 cc = __ldg(reinterpret_cast<const float2*>(p.coords) + upix);
+  lookup_sep_gather(p, upix, cc.x, cc.y, wb_s, lane);
+  while (true) {
+    const float cx = cc.x, cy = cc.y;
+    const unsigned nxt = upix + stride;
+    const bool more = nxt < total;
+    if (more) cc = __ldg(reinterpret_cast<const float2*>(p.coords) + nxt);
+    // ---- B: axis tables: entry e = 18 level + 9 axis + k
+#pragma unroll
+    for (int rnd = 0; rnd < 3; ++rnd) {
+      const int e = lane + 32 * rnd;
+      if (e < 72) {
+        const int lvl = e / 18, rem = e - lvl * 18, ax = rem >= 9 ? 1 : 0, k = rem - 9 * ax;
+        const float inv = 1.f / (float)(1 << lvl);
+        const float b = (ax ? cy : cx) * inv;
+        const float bo = floorf(fminf(fmaxf(b, -1.0e6f), 1.0e6f));
+        const int size = (ax ? p.h : p.w) >> lvl;
+        const int org = ax ? (int)bo - R - 1 : (((int)bo - R - 1) & ~3);
+        const float c = grid_roundtrip_h(__fadd_rn(b, (float)(k - R)), size);
+        const float cf = floorf(c);
+        const bool in_range = c > -2.f && c < (float)size + 1.f;
+        const int idx = in_range ? (int)cf - org : -1;
+        // idx must address a 2-texel run inside the patch; otherwise the tap is outside the map for every finite
+        // coordinate (the patch has a texel of slack), so it contributes zero: weights 0, offset 0
+        const bool ok = in_range && idx >= 0 && idx + 1 < (ax ? 12 : 16);
+        const int off = ok ? (ax ? idx * 36 : idx * 4) : 0;       // y: rows of H (9 floats)
+        axis[e] = make_float4(__int_as_float(off), ok ? (cf + 1.f) - c : 0.f, ok ? c - cf : 0.f, 0.f);
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    if (p.radius < 0) {                                           // probe (ACCFLOW_LOOKUP_PROBE=1): gathers only
+      if (!more) return;
+      lookup_sep_gather(p, nxt, cc.x, cc.y, wb_s, lane);
+      upix = nxt;
+      continue;
+    }
+    // ---- C: horizontal pass (rows y = l9 + 3 j, window column m9) into H[level][y][a]
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float4 ex = axis[l * 18 + (act ? m9 : 0)];
+      const unsigned char* src = wb + l * LVB + (act ? l9 : 0) * PITCH + __float_as_int(ex.x);
+      float* hdst = reinterpret_cast<float*>(wb + H_OFF + l * HLV) + lane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float q0 = *reinterpret_cast<const float*>(src + j * 3 * PITCH), q1 = *reinterpret_cast<const float*>(src + j * 3 * PITCH + 4);
+        if (act) hdst[j * 27] = fmaf(q1, ex.z, q0 * ex.y);
+      }
+    }
+    __syncwarp();
+    if (more) lookup_sep_gather(p, nxt, cc.x, cc.y, wb_s, lane);  // the patch buffer is free: next pixel's gathers fly from here
+    // ---- D: vertical pass, staged in channel order 81 l + 9 a + b (a = l9 + 3 i, b = m9) over the consumed part of H
+    float* stage = reinterpret_cast<float*>(wb + H_OFF);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      float v[3];
+      if (act) {
+        const float4 ey = axis[l * 18 + 9 + m9];
+        const unsigned char* src = wb + H_OFF + l * HLV + __float_as_int(ey.x) + l9 * 4;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float top = *reinterpret_cast<const float*>(src + i * 12), bot = *reinterpret_cast<const float*>(src + i * 12 + 36);
+          v[i] = fmaf(bot, ey.z, top * ey.y);
+        }
+      }
+      __syncwarp();                                               // level l of H is consumed: the stage may overwrite H[<= l]
+      if (act) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) stage[l * 81 + i * 27 + lane] = v[i];
+      }
+    }
+    __syncwarp();
+    // ---- E: 81 quads out
+    {
+      const long long pix = upix;
+      const float4* stage4 = reinterpret_cast<const float4*>(stage);
+      float* o32 = p.out ? p.out + pix * p.out_ld : nullptr;
+      __nv_bfloat16* opl = FMT ? p.out_pl + pix * p.pl_pitch : nullptr;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int q = lane + 32 * t;
+        if (t < 2 || q < 81) {
+          const float4 v = stage4[q];
+          if (o32) *reinterpret_cast<float4*>(o32 + 4 * q) = v;
+          if constexpr (FMT != 0) store_planes4_t<FMT, true>(opl + 4 * q, p.pl_stride, &v.x);
+        }
+      }
+      if (lane == 0) {
+        const unsigned hw = (unsigned)(p.h * p.w), pl = upix % hw, py = pl / (unsigned)p.w;
+        const float fx = cx - (float)(pl - py * (unsigned)p.w), fy = cy - (float)py;
+        if (p.flow_out) *reinterpret_cast<float2*>(p.flow_out + pix * 2) = make_float2(fx, fy);
+        if (p.mf_tail)
+          lookup_store_pair<FMT>(p.mf_tail + pix * p.mf_ld, FMT && p.tail_pl ? p.tail_pl + pix * p.tail_pitch : nullptr, p.tail_stride, fx, fy);
+      }
+    }
+    if (!more) return;
+    upix = nxt;
+    __syncwarp();                                                 // stage and axis tables are rewritten by the next pixel
+  }
+}
+
 __global__ void coords_init_kernel(const float* __restrict__ finit, int batch, int h, int w, float* __restrict__ coords) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   const int hw = h * w;
@@ -907,9 +1065,35 @@ extern "C" int accflow_corr_lookup_f32(const float* lvl0, const float* lvl1, con
                         (!out_planes || (pl_pitch % 2 == 0 && pl_stride % 2 == 0 && al(out_planes, 3))) &&
                         (!mf_tail || (mf_ld % 2 == 0 && al(mf_tail, 7))) &&
                         (!tail_planes || (out_planes && tail_pitch % 2 == 0 && tail_stride % 2 == 0 && al(tail_planes, 3)));
-  static int variant = -1;            // ACCFLOW_LOOKUP=fast: the single-channel kernel (kept for A/B measurements)
-  if (variant < 0) { const char* e = getenv("ACCFLOW_LOOKUP"); variant = (e && !strcmp(e, "fast")) ? 1 : 0; }
-  if (pairs_ok && variant == 0) {     // RAFT / GMA
+  // ACCFLOW_LOOKUP=pairs / fast: the earlier kernels (kept for A/B measurements and for shapes the separable one excludes)
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("ACCFLOW_LOOKUP"); variant = !e ? 0 : !strcmp(e, "fast") ? 2 : !strcmp(e, "pairs") ? 1 : 0; }
+  const bool sep_ok = pairs_ok && w % 32 == 0 && al(lvl0, 15) && al(lvl1, 15) && al(lvl2, 15) && al(lvl3, 15) &&
+                      (!out || (out_ld % 4 == 0 && al(out, 15))) &&
+                      (!out_planes || (pl_pitch % 4 == 0 && pl_stride % 4 == 0 && al(out_planes, 7)));
+  if (sep_ok && variant == 0) {       // RAFT / GMA at widths that are multiples of 256 pixels
+    typedef void (*LookupFn)(const LookupP);
+    static const LookupFn fns[5] = {corr_lookup_sep_kernel<0>, corr_lookup_sep_kernel<1>, corr_lookup_sep_kernel<2>,
+                                    corr_lookup_sep_kernel<3>, corr_lookup_sep_kernel<4>};
+    const int smem = 8 * ACCFLOW_LOOKUP_SEP_WARP_BYTES;
+    static thread_local int cfg_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cfg_dev != dev) {
+      for (int f = 0; f < 5; ++f) {
+        cudaError_t e = cudaFuncSetAttribute(fns[f], cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail((int)e, "corr_lookup: smem attribute: %s", cudaGetErrorString(e));
+      }
+      cfg_dev = dev;
+    }
+    static int probe = -1;
+    if (probe < 0) { const char* e = getenv("ACCFLOW_LOOKUP_PROBE"); probe = e ? atoi(e) : 0; }
+    if (probe) p.radius = -4;
+    static thread_local int sm_count = 0;
+    if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
+    const int resident = 4 * sm_count;                          // 4 blocks of 52.5 KB per SM
+    fns[out_planes ? nplanes : 0]<<<nblk < resident ? nblk : resident, 256, smem, ST>>>(p);
+  } else if (pairs_ok && variant <= 1) {
     switch (out_planes ? nplanes : 0) {
       case 0: corr_lookup_pairs_kernel<0><<<nblk, 256, 0, ST>>>(p); break;
       case 1: corr_lookup_pairs_kernel<1><<<nblk, 256, 0, ST>>>(p); break;

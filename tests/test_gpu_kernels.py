@@ -310,6 +310,50 @@ def test_corr_lookup_bench_shaped_maps(hw):
     assert maxdiff(out.permute(0, 3, 1, 2), ref) < 2e-5
 
 
+@pytest.mark.parametrize("fmt", [2, 4, 1, 3])
+def test_corr_lookup_operand_planes(fmt):
+    """The lookup's operand planes (what convc1 reads, raft/update.py:89-90) are the split of the very fp32 values the
+    same launch writes: fp16x2 hi = fp16(v), lo = fp16((v - hi) * 2^11); fp16; bf16; bf16x3.  Also the flow tail of the
+    motion features (cat([out, flow]), raft/update.py:96-97) in both forms."""
+    from accflow_b200 import _lib as L
+    h, w, B = 32, 64, 2
+    P = h * w
+    g = torch.Generator().manual_seed(67)
+    lv = [torch.randn(B * P, (h >> l) * (w >> l), generator=g).cuda() for l in range(4)]
+    grid = torch.stack(torch.meshgrid(torch.arange(w), torch.arange(h), indexing="xy"), -1).reshape(1, P, 2).float()
+    c = (grid + torch.randn(B, P, 2, generator=g) * 6.0).cuda().contiguous()
+    npl = 1 if fmt == 4 else fmt
+    out = torch.empty(B, P, 324, device="cuda")
+    pitch = 328
+    pl = torch.zeros(npl, B, P, pitch, device="cuda", dtype=torch.bfloat16)
+    mf = torch.zeros(B, P, 128, device="cuda")
+    tpl = torch.zeros(npl, B, P, 128, device="cuda", dtype=torch.bfloat16)
+    flow = torch.empty(B, P, 2, device="cuda")
+    L.call("accflow_corr_lookup_f32", lv[0].data_ptr(), lv[1].data_ptr(), lv[2].data_ptr(), lv[3].data_ptr(), B, h, w, 4,
+           c.data_ptr(), out.data_ptr(), 324, flow.data_ptr(), mf.data_ptr() + 4 * 126, 128, pl.data_ptr(), pitch,
+           B * P * pitch, tpl.data_ptr() + 2 * 126, 128, B * P * 128, fmt, None)
+    torch.cuda.synchronize()
+
+    def split(v):
+        if fmt in (2, 4):
+            v = v.clamp(-65504.0, 65504.0)
+            hi = v.half()
+            return [hi] if fmt == 4 else [hi, ((v - hi.float()) * 2048.0).half()]
+        p0 = v.bfloat16()
+        if fmt == 1:
+            return [p0]
+        r1 = v - p0.float()
+        p1 = r1.bfloat16()
+        return [p0, p1, (r1 - p1.float()).bfloat16()]
+
+    view = (lambda t: t.view(torch.float16)) if fmt in (2, 4) else (lambda t: t)
+    for i, ref in enumerate(split(out)):
+        assert torch.equal(view(pl[i])[..., :324], ref), (fmt, i)
+    assert torch.equal(mf[..., 126:], flow)
+    for i, ref in enumerate(split(flow)):
+        assert torch.equal(view(tpl[i])[..., 126:], ref), (fmt, i)
+
+
 @pytest.mark.parametrize("hw", [(32, 32), (16, 64), (64, 64)])
 def test_corr_volume_with_fused_first_level(hw):
     """CorrBlock.__init__ (raft/corr.py:8-22, 47-55) through the engine path whose GEMM epilogue emits level 1:
