@@ -76,6 +76,7 @@ SIGNATURES = {
     "accflow_tapsum3x3_f32": [fp, i, i, i, i, i, fp, fp, i, fp, i, fp, i, fp],
     "accflow_convex_upsample_f32": [fp, i, i, fp, i, i, i, i, fp, fp],
     "accflow_downflow8_f32": [fp, i, i, i, fp, fp],
+    "accflow_upflow8_f32": [fp, i, i, i, i, fp, fp],
     "accflow_warp_occ_f32": [fp, i, fp, i, fp, i, i, i, i, fp, i, fp, i, fp],
     "accflow_backwarp_nchw_f32": [fp, fp, i, i, i, i, fp, fp],
     "accflow_epe_metrics_f32": [fp, fp, fp, i, i, i, fp, fp, fp],

@@ -693,22 +693,32 @@ __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, 
 }
 
 // =============================== convex upsample ===========================================
+// 16 threads per source pixel, four sub-pixels (one 16-byte run of every mask plane) each: 9 x LDG.128 of the mask per
+// thread, float4 stores; a block covers 16 pixels of a row, so the eight output rows leave as 512-byte runs.
 __global__ void __launch_bounds__(256) convex_upsample_kernel(const float* __restrict__ flow, int flow_ld,
                                                               int coords_mode, const float* __restrict__ mask,
                                                               int mask_ld, int h, int w, float* __restrict__ out) {
   const int b = blockIdx.z, y = blockIdx.y;
-  const int x = blockIdx.x * 4 + (threadIdx.x >> 6);
-  const int sub = threadIdx.x & 63;
+  const int x = blockIdx.x * 16 + (threadIdx.x >> 4);
+  const int t = threadIdx.x & 15;                       // sub-pixels 4t .. 4t + 3: output row t >> 1, columns 4 (t & 1) ..
   if (x >= w) return;
   const long long pix = ((long long)b * h + y) * w + x;
-  const float* mp = mask + pix * mask_ld + sub;
-  float m[9], mx = -INFINITY;
+  const float4* mp = reinterpret_cast<const float4*>(mask + pix * mask_ld) + t;
+  float4 m[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) { m[k] = __ldg(mp + k * 64); mx = fmaxf(mx, m[k]); }
-  float sum = 0.f;
+  for (int k = 0; k < 9; ++k) m[k] = __ldg(mp + k * 16);
+  float4 mx = m[0];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) { m[k] = expf(m[k] - mx); sum += m[k]; }
-  float ox = 0.f, oy = 0.f;
+  for (int k = 1; k < 9; ++k) { mx.x = fmaxf(mx.x, m[k].x); mx.y = fmaxf(mx.y, m[k].y); mx.z = fmaxf(mx.z, m[k].z); mx.w = fmaxf(mx.w, m[k].w); }
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    m[k].x = __expf(m[k].x - mx.x); m[k].y = __expf(m[k].y - mx.y); m[k].z = __expf(m[k].z - mx.z); m[k].w = __expf(m[k].w - mx.w);
+    sum.x += m[k].x; sum.y += m[k].y; sum.z += m[k].z; sum.w += m[k].w;
+  }
+  // softmax weights as m * (1 / sum) with ex2.approx exponentials: <= 3 ulp from exp() / sum, i.e. 4e-7 of a weight
+  const float4 inv = make_float4(1.f / sum.x, 1.f / sum.y, 1.f / sum.z, 1.f / sum.w);
+  float4 ox = make_float4(0.f, 0.f, 0.f, 0.f), oy = ox;
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
     const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
@@ -718,15 +728,16 @@ __global__ void __launch_bounds__(256) convex_upsample_kernel(const float* __res
       fx = __ldg(fp); fy = __ldg(fp + 1);
       if (coords_mode) { fx -= (float)xx; fy -= (float)yy; }
     }
-    const float pk = m[k] / sum;
-    ox += pk * (8.f * fx);
-    oy += pk * (8.f * fy);
+    fx *= 8.f; fy *= 8.f;
+    const float4 pk = make_float4(m[k].x * inv.x, m[k].y * inv.y, m[k].z * inv.z, m[k].w * inv.w);
+    ox.x += pk.x * fx; ox.y += pk.y * fx; ox.z += pk.z * fx; ox.w += pk.w * fx;
+    oy.x += pk.x * fy; oy.y += pk.y * fy; oy.z += pk.z * fy; oy.w += pk.w * fy;
   }
-  const int i = sub >> 3, j = sub & 7;
+  const int i = t >> 1, j = (t & 1) * 4;
   const long long H8 = 8LL * h, W8 = 8LL * w;
   float* o = out + ((long long)b * 2 * H8 + (8 * y + i)) * W8 + 8 * x + j;
-  o[0] = ox;
-  o[H8 * W8] = oy;
+  *reinterpret_cast<float4*>(o) = ox;
+  *reinterpret_cast<float4*>(o + H8 * W8) = oy;
 }
 
 // =============================== downflow8 ==================================================
@@ -750,6 +761,26 @@ __global__ void downflow8_kernel(const float* __restrict__ in, int batch, int H,
               ly * (hx * __ldg(pl + (long long)y1 * W + x0) + lx * __ldg(pl + (long long)y1 * W + x1));
     out[(long long)i * 2 + c] = v / 8.f;
   }
+}
+
+// =============================== upflow8 ====================================================
+// 8 * F.interpolate(flow, 8x, bilinear, align_corners=True) (networks/utils.py:91-93): ATen upsample_bilinear2d:
+// scale = (in - 1) / (out - 1), src = scale * dst, the upper neighbour clamps at the border.  NCHW in and out.
+__global__ void __launch_bounds__(256) upflow8_kernel(const float* __restrict__ in, int planes, int h, int w, float* __restrict__ out) {
+  const int W8 = 8 * w, H8 = 8 * h;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (long long)planes * H8 * W8) return;
+  const int ox = (int)(i % W8), oy = (int)((i / W8) % H8);
+  const long long pl = i / ((long long)W8 * H8);
+  const float sy = H8 > 1 ? (float)(h - 1) / (float)(H8 - 1) : 0.f, sx = W8 > 1 ? (float)(w - 1) / (float)(W8 - 1) : 0.f;
+  const float fy = __fmul_rn(sy, (float)oy), fx = __fmul_rn(sx, (float)ox);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+  const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+  const float* p = in + pl * h * w;
+  const float v = hy * (hx * __ldg(p + y0 * w + x0) + lx * __ldg(p + y0 * w + x1)) +
+                  ly * (hx * __ldg(p + y1 * w + x0) + lx * __ldg(p + y1 * w + x1));
+  out[i] = 8.f * v;
 }
 
 // =============================== warp + occlusion ==========================================
@@ -1122,7 +1153,9 @@ extern "C" int accflow_convex_upsample_f32(const float* flow, int flow_ld, int c
                                            int mask_ld, int batch, int h, int w, float* out_nchw, void* stream) {
   ACCFLOW_REQUIRE(flow && mask && out_nchw, "convex_upsample: null pointer");
   ACCFLOW_REQUIRE(batch > 0 && h > 0 && w > 0 && flow_ld >= 2 && mask_ld >= 576, "convex_upsample: bad shape");
-  convex_upsample_kernel<<<dim3(cdiv(w, 4), h, batch), 256, 0, ST>>>(flow, flow_ld, coords_mode, mask, mask_ld, h, w, out_nchw);
+  ACCFLOW_REQUIRE(mask_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_nchw) & 15) == 0,
+                  "convex_upsample: mask and out must be 16B aligned, mask_ld %% 4 == 0");
+  convex_upsample_kernel<<<dim3(cdiv(w, 16), h, batch), 256, 0, ST>>>(flow, flow_ld, coords_mode, mask, mask_ld, h, w, out_nchw);
   return launched("convex_upsample");
 }
 
@@ -1131,6 +1164,13 @@ extern "C" int accflow_downflow8_f32(const float* flow_nchw, int batch, int H, i
   ACCFLOW_REQUIRE(H % 8 == 0 && W % 8 == 0 && H >= 8 && W >= 8, "downflow8: H,W must be multiples of 8 (AccFlow_.py:140)");
   downflow8_kernel<<<cdiv((long long)batch * (H / 8) * (W / 8), 256), 256, 0, ST>>>(flow_nchw, batch, H, W, out_nhwc);
   return launched("downflow8");
+}
+
+extern "C" int accflow_upflow8_f32(const float* flow_nchw, int batch, int c, int h, int w, float* out_nchw, void* stream) {
+  ACCFLOW_REQUIRE(flow_nchw && out_nchw && batch > 0 && c > 0 && h > 0 && w > 0, "upflow8: bad arguments");
+  ACCFLOW_REQUIRE((long long)batch * c * h * w * 64 < (1ll << 40), "upflow8: tensor too large");
+  upflow8_kernel<<<cdiv((long long)batch * c * h * w * 64, 256), 256, 0, ST>>>(flow_nchw, batch * c, h, w, out_nchw);
+  return launched("upflow8");
 }
 
 extern "C" int accflow_warp_occ_f32(const float* c1, int c1_ld, const float* c2, int c2_ld, const float* flow,

@@ -66,6 +66,18 @@ def downflow8(flow: torch.Tensor) -> torch.Tensor:
     return nchw(out)
 
 
+def upflow8(flow: torch.Tensor, mode: str = "bilinear") -> torch.Tensor:
+    """8 * F.interpolate(flow, 8x, bilinear, align_corners=True) (networks/utils.py:91-93)."""
+    if mode != "bilinear":
+        raise ValueError("upflow8: only the reference's default mode 'bilinear' exists here")
+    flow = _cuda(flow)
+    n, c, h, w = flow.shape
+    out = torch.empty(n, c, 8 * h, 8 * w, device=flow.device, dtype=F32)
+    with torch.cuda.device(flow.device):
+        L.call("accflow_upflow8_f32", flow.data_ptr(), n, c, h, w, out.data_ptr(), _s())
+    return out
+
+
 def get_occ(flow12, i1, i2, binary=True):
     c1, c2 = nhwc(i1), nhwc(i2)
     fl = nhwc(flow12)

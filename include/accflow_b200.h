@@ -272,6 +272,10 @@ ACCFLOW_API int accflow_convex_upsample_f32(const float* flow, int flow_ld, int 
  * divided by 8, written NHWC [B,h,w,2]. */
 ACCFLOW_API int accflow_downflow8_f32(const float* flow_nchw, int batch, int H, int W, float* out_nhwc, void* stream);
 
+/* upflow8 (networks/utils.py:91-93, raft/utils/utils.py:90-92): 8 * align_corners bilinear resize of NCHW (B,C,h,w)
+ * to (B,C,8h,8w). */
+ACCFLOW_API int accflow_upflow8_f32(const float* flow_nchw, int batch, int c, int h, int w, float* out_nchw, void* stream);
+
 /* getOcc (AccFlow_.py:127-135) with backwarp (networks/utils.py:96-124), NHWC.
  * occ_out (binary branch, [B,h*w] 0/1) and/or emap_out (|c1 - warp(c2)| NHWC) may be NULL. */
 ACCFLOW_API int accflow_warp_occ_f32(const float* c1, int c1_ld, const float* c2, int c2_ld, const float* flow,

@@ -436,6 +436,16 @@ def test_convex_upsample(golden):
     assert maxdiff(P.convex_upsample(dev(flow), dev(mask)), g["upsample.out"]) < 1e-5
 
 
+def test_upflow8_vs_torch():
+    """networks/utils.py:91-93: 8 * F.interpolate(flow, 8x, 'bilinear', align_corners=True)."""
+    from accflow_b200.networks.utils import upflow8
+    g = torch.Generator().manual_seed(5)
+    for shape in ((2, 2, 16, 24), (1, 2, 64, 64), (1, 3, 1, 5)):
+        fl = torch.randn(*shape, generator=g) * 3
+        ref = 8 * F.interpolate(fl, size=(8 * shape[2], 8 * shape[3]), mode="bilinear", align_corners=True)
+        assert maxdiff(upflow8(dev(fl)), ref) < 2e-5, shape
+
+
 def test_backwarp_downflow_occ(golden):
     from accflow_b200 import ops as P
     g, _ = golden
