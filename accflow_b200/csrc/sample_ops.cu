@@ -158,6 +158,49 @@ __global__ void __launch_bounds__(256) corr_pool_kernel(const float* __restrict_
   }
 }
 
+// Two successive 2x2 means of an h x w map per volume row, one WARP per row (the fused correlation path: level 1 comes
+// out of the GEMM epilogue, levels 2 and 3 from here).  A lane owns 4 x 4 blocks of the map: four 16-byte loads, the
+// 2 x 2 level-a values and the level-b value all stay in registers - no shared memory, no block barrier (the block-per-row
+// kernel above was issue-bound: 75 % SM busy at 32 % of DRAM).  Summation order as raft/corr.py:20-22 / avg_pool2d.
+__global__ void __launch_bounds__(256) corr_pool2_kernel(const float* __restrict__ src, long long n_rows, int h, int w,
+                                                         float* __restrict__ la, float* __restrict__ lb) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int bw = w >> 2, nblk = (h >> 2) * bw, wa = w >> 1;
+  const float* s = src + row * h * w;
+  float* oa = la + row * (h >> 1) * wa;
+  float* ob = lb + row * nblk;
+  for (int b0 = 0; b0 < nblk; b0 += 64) {
+    float4 r[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int b = b0 + lane + 32 * u;
+      if (b < nblk) {
+        const int by = b / bw, bx = b - by * bw;
+        const float4* q = reinterpret_cast<const float4*>(s + (4 * by) * w + 4 * bx);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[u][k] = __ldg(q + k * (w >> 2));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int b = b0 + lane + 32 * u;
+      if (b < nblk) {
+        const int by = b / bw, bx = b - by * bw;
+        const float a00 = (((r[u][0].x + r[u][0].y) + r[u][1].x) + r[u][1].y) * 0.25f;
+        const float a01 = (((r[u][0].z + r[u][0].w) + r[u][1].z) + r[u][1].w) * 0.25f;
+        const float a10 = (((r[u][2].x + r[u][2].y) + r[u][3].x) + r[u][3].y) * 0.25f;
+        const float a11 = (((r[u][2].z + r[u][2].w) + r[u][3].z) + r[u][3].w) * 0.25f;
+        float* pa = oa + (2 * by) * wa + 2 * bx;
+        *reinterpret_cast<float2*>(pa) = make_float2(a00, a01);
+        *reinterpret_cast<float2*>(pa + wa) = make_float2(a10, a11);
+        ob[b] = (((a00 + a01) + a10) + a11) * 0.25f;
+      }
+    }
+  }
+}
+
 // =============================== correlation lookup ========================================
 struct LookupP {
   const float* lvl[4];
@@ -784,7 +827,8 @@ __global__ void __launch_bounds__(256) upflow8_kernel(const float* __restrict__ 
 }
 
 // =============================== warp + occlusion ==========================================
-// One warp per pixel; lanes stride over 4-channel groups.
+// One warp per pixel; lanes stride over 4-channel groups.  (8 x 4 pixel tiles per 1024-thread block - more tap rows
+// served from L1 - were measured slower: 58 -> 77 us per 27 pairs.)
 __global__ void __launch_bounds__(256) warp_occ_kernel(const float* __restrict__ c1, int c1_ld,
                                                        const float* __restrict__ c2, int c2_ld,
                                                        const float* __restrict__ flow, int batch, int h, int w,
@@ -1053,7 +1097,13 @@ extern "C" int accflow_nhwc_transpose_f32(const float* in, int batch, int hw, in
 
 extern "C" int accflow_corr_pool_f32(const float* lvl0, long long n_rows, int h, int w, float* lvl1, float* lvl2,
                                      float* lvl3, void* stream) {
-  ACCFLOW_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && n_rows > 0, "corr_pool: null pointer");
+  ACCFLOW_REQUIRE(lvl0 && lvl1 && lvl2 && n_rows > 0, "corr_pool: null pointer");
+  if (!lvl3) {      // two levels only, one warp per row
+    ACCFLOW_REQUIRE(h >= 4 && w >= 4 && h % 4 == 0 && w % 4 == 0 && (reinterpret_cast<uintptr_t>(lvl0) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(lvl1) & 7) == 0, "corr_pool: two-level form needs h, w %% 4 == 0 and aligned maps");
+    corr_pool2_kernel<<<cdiv(n_rows, 8), 256, 0, ST>>>(lvl0, n_rows, h, w, lvl1, lvl2);
+    return launched("corr_pool");
+  }
   ACCFLOW_REQUIRE(h >= 8 && w >= 8, "corr_pool: map %dx%d too small for 4 levels", h, w);
   const size_t smem = (size_t)(h * w + (h / 2) * (w / 2) + (h / 4) * (w / 4)) * sizeof(float);
   ACCFLOW_REQUIRE(smem <= 200 * 1024, "corr_pool: map %dx%d exceeds shared memory", h, w);

@@ -797,9 +797,8 @@ class FlowEstimatorEngine:
             # from level 1 (a quarter of the bytes of level 0)
             k.gemm_nt(tag + ".corr", f1, f2, View(lv[0].view(B, h, w, P)), alpha=1.0 / math.sqrt(D),
                       pool_out=lv[1], pool_w=w)
-            spare = k.buf(tag + ".pyr4", B * P, (h // 16) * (w // 16))
             L.call("accflow_corr_pool_f32", lv[1].data_ptr(), B * P, h // 2, w // 2, lv[2].data_ptr(), lv[3].data_ptr(),
-                   spare.data_ptr(), _stream())
+                   None, _stream())
             return lv
         k.gemm_nt(tag + ".corr", f1, f2, View(lv[0].view(B, h, w, P)), alpha=1.0 / math.sqrt(D))
         L.call("accflow_corr_pool_f32", lv[0].data_ptr(), B * P, h, w, lv[1].data_ptr(), lv[2].data_ptr(),

@@ -231,7 +231,9 @@ ACCFLOW_API int accflow_nhwc_transpose_f32(const float* in, int batch, int hw, i
                                            int out_ld, void* stream); /* out row (per channel) stride >= hw */
 
 /* 3x avg_pool2d(2,2) over the target dims of the level-0 correlation volume
- * (raft/corr.py:20-22).  lvl0: [n_rows][h*w]; lvl1..3 written densely with floor sizes. */
+ * (raft/corr.py:20-22).  lvl0: [n_rows][h*w]; lvl1..3 written densely with floor sizes.
+ * lvl3 == NULL: two levels only (h, w multiples of 4) - the form used when the first level already left the
+ * correlation GEMM's epilogue. */
 ACCFLOW_API int accflow_corr_pool_f32(const float* lvl0, long long n_rows, int h, int w, float* lvl1, float* lvl2,
                           float* lvl3, void* stream);
 

@@ -55,6 +55,7 @@ timeit("instnorm 12x256x256x64 (3 kernels)", lambda: K.instnorm(t, True, None, F
 # corr pool
 l1, l2, l3 = (torch.empty(B * P, (h >> l) * (w >> l), device=dev) for l in (1, 2, 3))
 timeit("corr_pool", lambda: L.call("accflow_corr_pool_f32", lv[0].data_ptr(), B * P, h, w, l1.data_ptr(), l2.data_ptr(), l3.data_ptr(), None), B * P * P * 4 * 1.33)
+timeit("corr_pool levels 2-3 from level 1 (fused path)", lambda: L.call("accflow_corr_pool_f32", l1.data_ptr(), B * P, h // 2, w // 2, l2.data_ptr(), l3.data_ptr(), None, None), B * P * (P // 4) * 4 * 1.3125)
 
 # convex upsample (flow + 576-channel mask -> 8x flow), once per pair
 cflow = torch.randn(B, P, 2, device=dev); mask = torch.randn(B, h, w, 576, device=dev); up = torch.empty(B, 2, 8 * h, 8 * w, device=dev)
