@@ -1331,11 +1331,13 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   ACCFLOW_REQUIRE(enc != nullptr, "conv2d_tc: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   tc::TmapPack maps;
   memset(&maps, 0, sizeof(maps));
-  CUtensorMapL2promotion l2p = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  // 128 B = one swizzle-atom row of a box; 256 B promotion over-fetches around ragged boxes (same-box A/B: -1.3 % flows/s,
+  // profiles/r4e_ab_l2_promotion.jsonl; none / 64 / 128 are equivalent)
+  CUtensorMapL2promotion l2p = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   if (const char* e = getenv("ACCFLOW_TC_L2P")) {
     int v = atoi(e);
     l2p = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-          : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+          : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   }
   {
     const cuuint64_t gdim[4] = {(cuuint64_t)w.k, (cuuint64_t)w.rows, (cuuint64_t)w.t, (cuuint64_t)w.nplanes};
