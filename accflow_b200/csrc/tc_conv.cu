@@ -1253,8 +1253,16 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
                    p.out_h % 2 == 0 && d.out_ld == d.cout && d.cout % 128 == 0;
   if (const char* e = getenv("ACCFLOW_TC_TMA_STORE")) tma_store = tma_store && atoi(e) != 0;
   p.tma_store = tma_store;
-  p.m_major = per_sample && p.n_tiles >= 8;                  // wide per-sample outputs (correlation volume, attention passes)
-  if (const char* e = getenv("ACCFLOW_TC_M_MAJOR")) p.m_major = p.m_major && atoi(e) != 0;
+  // Tile order.  M-major (tile = m * n_tiles + n): the CTAs that run concurrently cover all N tiles of the same pixels, so
+  // an activation box is fetched from HBM once and re-read from L2 (and a CTA keeps its weight N tile: grid and n_tiles are
+  // even); N-major re-reads the whole activation tensor once per N tile after ~150 MB of other traffic (ncu on the GRU z|r
+  // conv: 264 MB of DRAM reads for ~190 MB of unique inputs).  Same-box A/B: +1.0 % flows/s
+  // (profiles/r4f_ab_tile_order.jsonl).  ACCFLOW_TC_M_MAJOR=0: never; 1: only the wide per-sample GEMMs (the rule until r4f).
+  p.m_major = p.n_tiles >= 2;
+  if (const char* e = getenv("ACCFLOW_TC_M_MAJOR")) {
+    const int v = atoi(e);
+    p.m_major = v == 0 ? false : v == 1 ? (per_sample && p.n_tiles >= 8) : p.m_major;
+  }
   const int epi_bytes = tma_store ? 8 * 8192 : 2 * tc::BM * 20 * 4;   // 8 warps x two 4 KB boxes | two 128 x (16+4)-float panels
   const int ring_bytes = 222 * 1024 - 1024 - epi_bytes;
   int stages = ring_bytes / stage_bytes, stages_b;
