@@ -132,7 +132,7 @@ class PackedConv:
             self._tc = {}
         if fp16x2 not in self._tc:
             taps = self.kh * self.kw
-            pitch = (self.cin + 7) // 8 * 8
+            pitch = Kernels.plane_pitch(self.cin)          # 128-byte aligned rows, like the activation planes
             wt = torch.zeros(taps, self.cout, pitch, device=self.w_oihw.device, dtype=F32)
             wt[:, :, : self.cin] = self.w_oihw.permute(2, 3, 0, 1).reshape(taps, self.cout, self.cin)
             planes = split_planes_torch(wt, fp16x2)
@@ -217,8 +217,17 @@ class Kernels:
             if rng not in st:
                 st.append(rng)
 
+    # Plane pitch: a pixel's channels start on a 128-byte line (64 elements), so every 64-channel K block a TMA box
+    # fetches is one whole L2 line per pixel instead of two partial ones (324 -> 384, 104 -> 128, 96 -> 128, 48 -> 64).
+    PLANE_ALIGN = int(os.environ.get("ACCFLOW_PLANE_ALIGN", "64"))
+
+    @classmethod
+    def plane_pitch(cls, ld: int) -> int:
+        a = cls.PLANE_ALIGN if ld >= 32 else 8
+        return (ld + a - 1) // a * a
+
     def _plane_geom(self, v: View):
-        cp = (v.ld + 7) // 8 * 8
+        cp = self.plane_pitch(v.ld)
         return cp, v.t.shape[0] * v.h * v.w * cp
 
     def planes_ptr(self, v: View, create: bool):
@@ -607,7 +616,7 @@ class EncoderPlan:
         n = sum(int(im.shape[0]) for im in images)
         H, W = int(images[0].shape[-2]), int(images[0].shape[-1])
         h2, w2 = H // 2, W // 2
-        pitch = 48
+        pitch = Kernels.plane_pitch(48)
         patches = k.buf16("stem.rows", k.nplanes, n, h2, w2, pitch)
         stride_pl = n * h2 * w2 * pitch
         b0 = 0
