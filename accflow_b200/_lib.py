@@ -12,7 +12,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ACCFLOW_LIB") or os.path.join(HERE, "libaccflow_b200.so")   # env override: A/B builds
 MAX_SRC = 4
-ABI_VERSION = 4
+ABI_VERSION = 5
+TILES_AUTO, TILES_FORWARD, TILES_REVERSE = 0, 1, 2      # accflow_conv_desc.tile_order
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
 EPI_STORE, EPI_GRU_ZR, EPI_GRU_Q, EPI_STORE_POOL, EPI_ROWSTATS, EPI_STORE_T = 0, 1, 2, 3, 4, 5
 
@@ -32,6 +33,7 @@ class ConvDesc(C.Structure):
         ("out", fp), ("out_ld", C.c_int), ("out2", fp), ("out2_ld", C.c_int),
         ("h", fp), ("h_ld", C.c_int), ("z", fp), ("z_ld", C.c_int), ("pool_w", C.c_int),
         ("pre_add", fp), ("pre_ld", C.c_int), ("pre_mod", C.c_int), ("row_stats", fp), ("out_h", C.c_int), ("out_w", C.c_int),
+        ("tile_order", C.c_int),
     ]
 
 

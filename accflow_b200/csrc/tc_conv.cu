@@ -64,6 +64,7 @@ struct Params {
   int m_major;    // tile walk: 0 = N-major (CTAs that run together share a weight tile), 1 = M-major (per-sample GEMMs with a
                   // P x P output: the CTAs that run together write adjacent column ranges of the same rows)
   int tma_store;  // ACCFLOW_EPI_STORE_POOL: level 0 leaves through 32 x 32 fp32 TMA store boxes (maps.out)
+  int reverse; // walk the tiles last-to-first (the host alternates launches: see accflow_conv2d_tc)
   int debug;   // perf experiments only (ACCFLOW_TC_DEBUG): bit 0 = no TMA loads, bit 1 = no MMAs, bit 5 = no main loop (results are garbage)
   float alpha;
   const float* scale;
@@ -509,7 +510,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       int sa = 0, sb = 0;                                    // ring positions (A boxes, weight tiles)
       uint32_t pa = 1, pb = 1;                               // parity of the "free" phase to wait for (first lap passes)
       const int tstep = p.mode == 1 ? p.kw : 1;              // weight tap index = tbase + j * tstep
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x) {
+        const int tile = p.reverse ? total_tiles - 1 - tile_i : tile_i;
         const int n_tile = p.m_major ? tile % p.n_tiles : tile / m_tiles;
         int t = p.m_major ? tile / p.n_tiles : tile - n_tile * m_tiles;
         const int tile_x = t % p.tiles_x; t /= p.tiles_x;
@@ -602,7 +604,8 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
     const float* const srow = stg + (32 * (warp & 3) + (lane >> 2)) * PITCH + pc4 * 4;              // rows it reads back
     const long long map_px = (long long)p.out_h * p.out_w;
     int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x, ++lt) {
+      const int tile = p.reverse ? total_tiles - 1 - tile_i : tile_i;
       const int n_tile = p.m_major ? tile % p.n_tiles : tile / m_tiles;
       int t = p.m_major ? tile / p.n_tiles : tile - n_tile * m_tiles;
       const int tile_x = t % p.tiles_x; t /= p.tiles_x;
@@ -1224,6 +1227,15 @@ extern "C" int accflow_conv2d_tc(const accflow_conv_desc* dp, const accflow_tc_i
   }
   p.msub = 1;
   if (const char* e = getenv("ACCFLOW_TC_DEBUG")) p.debug = atoi(e);
+  {
+    // Serpentine across launches: consecutive convolutions walk their tiles in opposite directions, so a layer starts on
+    // the pixels its producer wrote last - the part of a 75-150 MB activation tensor that is still in the 126 MB L2 -
+    // instead of streaming both tensors through the L2 in the same order (every line evicted before it is re-read).
+    static thread_local unsigned launch_parity = 0;
+    static int serp = -1;
+    if (serp < 0) { const char* e = getenv("ACCFLOW_TC_SERPENTINE"); serp = e ? atoi(e) : 1; }
+    p.reverse = !serp ? 0 : d.tile_order == ACCFLOW_TILES_FORWARD ? 0 : d.tile_order == ACCFLOW_TILES_REVERSE ? 1 : (int)(launch_parity++ & 1u);
+  }
   // N tile: multiple of 32; the split modes keep two accumulators (MAIN | CORR) x two TMEM slots (BN <= 128).
   const int bn = tc_bn_for(d.cout, nprod);
   p.bn = bn;

@@ -280,14 +280,16 @@ class Kernels:
              weight_ptr: Optional[int] = None, weight_batch_stride=0, cout=None, cout_pad=None,
              use_affine=True, tc_b: Optional["L.TcWeights"] = None, tc_src_planes=None, planes_only=False,
              emit_planes=True, pool_w=0, pre_add: Optional[View] = None, row_stats: Optional[torch.Tensor] = None,
-             tc_out_planes=None, out_h: int = 0, pre_mod: int = 0):
+             tc_out_planes=None, out_h: int = 0, pre_mod: int = 0, tile_order: int = 0):
         """``planes_only``: the output (``out``; ``out2`` for the GRU z|r epilogue) is read by tensor-core
         convolutions only, so in the tensor-core modes its fp32 copy is not written (half the store bytes).
         ``emit_planes=False``: the next reader is not a tensor-core conv (InstanceNorm), so no planes are written.
         ``pre_add``: fp32 slice added before the activation / gate math (the hoisted GRU ``inp`` term); with
         ``pre_mod`` > 0 it holds ``pre_mod`` samples and sample s reads sample s % pre_mod (pairs that share their
-        first frame share the term)."""
+        first frame share the term).  ``tile_order``: L.TILES_FORWARD / L.TILES_REVERSE - walk the output tiles
+        opposite to the producer of the input (it then starts on what is still in L2); 0 = alternate per launch."""
         d = L.ConvDesc()
+        d.tile_order = tile_order
         cin = 0
         for k, s in enumerate(srcs):
             d.src[k], d.src_c[k], d.src_ld[k] = s.ptr, s.c, s.ld
@@ -395,7 +397,7 @@ class Kernels:
         self._done(out, pl[0] is not None)
 
     def flow_conv7(self, tag: str, flow: torch.Tensor, batch: int, h: int, w: int, pc: PackedConv, out: View,
-                   planes_only=False):
+                   planes_only=False, tile_order: int = 0):
         """relu(conv7x7(flow)) for a 2-channel flow field [batch, h*w, 2] (raft/update.py:92, AccFlow_.py:62)."""
         if not self.tc:
             self.conv_smallc(flow.data_ptr(), False, batch, 2, h, w, pc, L.ACT_RELU, out)
@@ -405,10 +407,10 @@ class Kernels:
         L.call("accflow_flow_patch_f32", flow.data_ptr(), batch, h, w, None, patch.ld, pl[0], pl[1], pl[2],
                self.plane_fmt, _stream())          # planes only: nothing reads the fp32 patch
         self._stale[patch.t.data_ptr()] = []
-        self.conv(pc.as_1x1(), [patch.ch(0, 98)], out, act=L.ACT_RELU, planes_only=planes_only)
+        self.conv(pc.as_1x1(), [patch.ch(0, 98)], out, act=L.ACT_RELU, planes_only=planes_only, tile_order=tile_order)
 
     def conv_smallcout(self, pc: PackedConv, x: View, out: View, act=L.ACT_NONE, accum: Optional[torch.Tensor] = None,
-                       accum_ld: int = 0):
+                       accum_ld: int = 0, tile_order: int = 0):
         """3x3 conv with <= 4 output channels; ``accum`` (optional, [pixels, accum_ld]) += result.
         Tensor-core modes: a 1x1 conv with 9*cout outputs (each activation read once) + a 9-tap sum;
         fp32 mode: the FFMA bandwidth kernel."""
@@ -417,7 +419,7 @@ class Kernels:
         if self.tc:
             n9 = 9 * pc.cout
             t = self.view(f"tapsum{n9}", x.b, x.h, x.w, (n9 + 3) // 4 * 4)
-            self.conv(pc.as_taps1x1(), [x], t)           # (rows 9*cout.. of the padded filter are zero)
+            self.conv(pc.as_taps1x1(), [x], t, tile_order=tile_order)   # (rows 9*cout.. of the padded filter are zero)
             L.call("accflow_tapsum3x3_f32", t.ptr, t.ld, x.b, x.h, x.w, pc.cout, scale, pc.shift.data_ptr(), act,
                    out.ptr, out.ld, None if accum is None else accum.data_ptr(), accum_ld, _stream())
         else:
@@ -900,21 +902,25 @@ class FlowEstimatorEngine:
             assert tuple(flow_init.shape) == (B, 2, h, w)
         L.call("accflow_coords_init_f32", None if flow_init is None else flow_init.data_ptr(), B, h, w,
                coords.data_ptr(), s())
+        # Tile directions (results do not depend on them): every conv walks opposite to the producer of its input - the
+        # lookup and the patch / tap-sum kernels run first-to-last - so it starts on the part still in L2.
+        FWD, REV = L.TILES_FORWARD, L.TILES_REVERSE
         for _ in range(iters):
             k.corr_lookup(lv, self.RADIUS, coords, corr, flow, mf.ch(126, 128), planes_only=True)
-            k.conv(self.convc1, [corr], cor1, act=L.ACT_RELU, planes_only=True)
-            k.conv(self.convc2, [cor1], cf.ch(0, 192), act=L.ACT_RELU, planes_only=True)
-            k.flow_conv7(tag, flow, B, h, w, self.convf1, flo1, planes_only=True)
-            k.conv(self.convf2, [flo1], cf.ch(192, 256), act=L.ACT_RELU, planes_only=True)
-            k.conv(self.convm, [cf], mf.ch(0, 126), act=L.ACT_RELU, planes_only=not self.gma)
+            k.conv(self.convc1, [corr], cor1, act=L.ACT_RELU, planes_only=True, tile_order=REV)
+            k.conv(self.convc2, [cor1], cf.ch(0, 192), act=L.ACT_RELU, planes_only=True, tile_order=FWD)
+            k.flow_conv7(tag, flow, B, h, w, self.convf1, flo1, planes_only=True, tile_order=REV)
+            k.conv(self.convf2, [flo1], cf.ch(192, 256), act=L.ACT_RELU, planes_only=True, tile_order=FWD)
+            k.conv(self.convm, [cf], mf.ch(0, 126), act=L.ACT_RELU, planes_only=not self.gma, tile_order=REV)
             if self.gma:
                 self.aggregate(st["attn"], mf, mfg, tag)
             for (zr, q), (pre_zr, pre_q) in zip(self.gru, st["gru_pre"]):
                 k.conv(zr, [hid] + x_srcs, epilogue=L.EPI_GRU_ZR, h=hid, z=z, out2=rh, planes_only=True, pre_add=pre_zr,
-                       pre_mod=st["pre_mod"])
-                k.conv(q, [rh] + x_srcs, epilogue=L.EPI_GRU_Q, h=hid, z=z, pre_add=pre_q, pre_mod=st["pre_mod"])
-            k.conv(self.fh1, [hid], fh, act=L.ACT_RELU, planes_only=True)
-            k.conv_smallcout(self.fh2, fh, delta, accum=coords, accum_ld=2)     # coords1 += delta_flow
+                       pre_mod=st["pre_mod"], tile_order=FWD)
+                k.conv(q, [rh] + x_srcs, epilogue=L.EPI_GRU_Q, h=hid, z=z, pre_add=pre_q, pre_mod=st["pre_mod"],
+                       tile_order=REV)
+            k.conv(self.fh1, [hid], fh, act=L.ACT_RELU, planes_only=True, tile_order=FWD)
+            k.conv_smallcout(self.fh2, fh, delta, accum=coords, accum_ld=2, tile_order=REV)     # coords1 += delta_flow
         # mask head + convex upsample: only the last iteration's is observable (raft.py:139-146)
         k.conv(self.mk1, [hid], fh, act=L.ACT_RELU, planes_only=True)
         mask = k.view(tag + ".mask", B, h, w, 576)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ACCFLOW_ABI_VERSION 4
+#define ACCFLOW_ABI_VERSION 5
 #if defined(__GNUC__)
 #define ACCFLOW_API __attribute__((visibility("default")))
 #else
@@ -59,6 +59,9 @@ enum {
 };
 
 #define ACCFLOW_MAX_SRC 4
+#define ACCFLOW_TILES_AUTO 0
+#define ACCFLOW_TILES_FORWARD 1
+#define ACCFLOW_TILES_REVERSE 2
 
 /* One convolution / GEMM launch.  Replaces every nn.Conv2d (+ following elementwise ops) on
  * the path: raft/update.py:6-14,33-60,79-136; raft/extractor.py:54-63,201-225;
@@ -105,6 +108,10 @@ typedef struct accflow_conv_desc {
   /* tensor-core kernel: evaluate only the first out_h rows / out_w columns of the output map (0 = all, i.e.
    * (in + 2*pad - k)/stride + 1).  Expresses asymmetric padding: the stem's 4-tap form pads 2 above and 1 below. */
   int out_h, out_w;
+  /* tensor-core kernel: direction in which the launch walks its output tiles - ACCFLOW_TILES_AUTO (0: consecutive launches
+   * alternate), ACCFLOW_TILES_FORWARD, ACCFLOW_TILES_REVERSE.  Results do not depend on it; a consumer that walks opposite
+   * to its producer starts on the part of the activation tensor that is still in L2. */
+  int tile_order;
 } accflow_conv_desc;
 
 ACCFLOW_API int accflow_abi_version(void);

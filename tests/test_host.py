@@ -20,7 +20,7 @@ def test_cabi_exports_every_declared_symbol():
     assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.accflow_abi_version() == 4
+    assert lib.accflow_abi_version() == L.ABI_VERSION == 5
     assert lib.accflow_instnorm_chunks(4096) == 4
 
 
