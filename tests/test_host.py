@@ -145,3 +145,9 @@ def test_packed_conv_1x1_rewrites_are_the_same_filter():
     cols = F.unfold(f, 7, padding=3).view(1, 2, 49, 10 * 12).permute(0, 2, 1, 3).reshape(1, 98, 10, 12)   # (tap, cin) order
     pc7 = PackedConv([w7], [None], 1, (3, 3))
     assert float((F.conv2d(cols, pc7.as_1x1().w_oihw) - ref7).abs().max()) < 5e-5
+
+
+def test_graft_entry_build_runs():
+    """The driver's build check: compiles (or finds up to date) the library, loads it and imports the package."""
+    import __graft_entry__ as g
+    g.build()
