@@ -53,6 +53,7 @@ i, ll, f = C.c_int, C.c_longlong, C.c_float
 # name -> argtypes (restype is int unless listed in _RESTYPE); mirrors include/accflow_b200.h
 SIGNATURES = {
     "accflow_abi_version": [],
+    "accflow_sizeof": [i],
     "accflow_last_error": [C.c_char_p, C.c_size_t],
     "accflow_launch_count": [i],
     "accflow_launch_count_add": [ll],
@@ -87,7 +88,7 @@ SIGNATURES = {
     "accflow_softmax_rows_f32": [fp, ll, i, fp],
 }
 _RESTYPE = {"accflow_launch_count": ll, "accflow_launch_count_add": ll}
-_NO_CHECK = {"accflow_abi_version", "accflow_last_error", "accflow_launch_count", "accflow_launch_count_add",
+_NO_CHECK = {"accflow_abi_version", "accflow_sizeof", "accflow_last_error", "accflow_launch_count", "accflow_launch_count_add",
              "accflow_instnorm_chunks", "accflow_tc_rowstat_parts"}
 
 _lib = None
@@ -111,6 +112,10 @@ def load() -> C.CDLL:
         fn.restype = _RESTYPE.get(name, C.c_int)
     if lib.accflow_abi_version() != ABI_VERSION:
         raise AccflowError("ABI version mismatch between _lib.py and libaccflow_b200.so")
+    for which, mirror in enumerate((ConvDesc, TcWeights, TcIO)):
+        if lib.accflow_sizeof(which) != C.sizeof(mirror):
+            raise AccflowError(f"{mirror.__name__}: ctypes mirror is {C.sizeof(mirror)} bytes, the library's struct "
+                               f"{lib.accflow_sizeof(which)} (include/accflow_b200.h and _lib.py disagree)")
     _lib = lib
     return lib
 

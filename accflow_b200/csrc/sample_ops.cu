@@ -1040,6 +1040,9 @@ using namespace accflow;
 #define ST ((cudaStream_t)stream)
 
 extern "C" int accflow_abi_version(void) { return ACCFLOW_ABI_VERSION; }
+extern "C" int accflow_sizeof(int which) {
+  return which == 0 ? (int)sizeof(accflow_conv_desc) : which == 1 ? (int)sizeof(accflow_tc_weights) : which == 2 ? (int)sizeof(accflow_tc_io) : -1;
+}
 
 extern "C" int accflow_last_error(char* buf, size_t len) {
   if (!buf || len == 0) return -1;

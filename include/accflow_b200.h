@@ -115,6 +115,9 @@ typedef struct accflow_conv_desc {
 } accflow_conv_desc;
 
 ACCFLOW_API int accflow_abi_version(void);
+/* sizeof() of the structs that cross the ABI, so a binding can check its mirror: which = 0 accflow_conv_desc,
+ * 1 accflow_tc_weights, 2 accflow_tc_io; -1 for anything else. */
+ACCFLOW_API int accflow_sizeof(int which);
 /* Copies the calling thread's last error message (NUL-terminated) into buf. */
 ACCFLOW_API int accflow_last_error(char* buf, size_t len);
 /* Number of kernels this library has launched since load / last reset (bench "gpu_launches"). */
