@@ -404,7 +404,7 @@ def run_b200(args):
              "bf16": "conv_tc_kernel (tcgen05 implicit-GEMM conv, bf16 products)"}[args.precision]
     issued = achieved * {"bf16x3": 6, "fp16x2": 3}.get(args.precision, 1)
     traffic, traffic_note = None, None
-    for name in (f"r4h_conv_tc_zr_{args.precision}_ncu_full.jsonl",
+    for name in (f"r4p_conv_tc_zr_{args.precision}_ncu_full.jsonl", f"r4h_conv_tc_zr_{args.precision}_ncu_full.jsonl",
                  f"r3w_conv_tc_zr_{args.precision}_ncu_full.jsonl", f"r3c_conv_tc_zr_{args.precision}_ncu_full.jsonl",
                  f"r2_conv_tc_zr_{args.precision}_ncu_full.jsonl",
                  f"r1c_conv_tc_zr_{args.precision}_ncu_full.jsonl",
@@ -414,7 +414,7 @@ def run_b200(args):
             t = json.loads(open(tfile).readline())
             traffic = (t["dram_read_MB"] + t["dram_write_MB"]) * 1e6
             traffic_note = (f"STATIC, not measured in this run: dram__bytes_read+write of one GRU z|r conv launch (1x5, "
-                            f"{'18' if name.startswith(('r2_', 'r3c_', 'r3w_', 'r4h_')) else '8'} pairs x 64x64; `ncu --set full`) from profiles/{name}")
+                            f"{'18' if name.startswith(('r2_', 'r3c_', 'r3w_', 'r4h_', 'r4p_')) else '8'} pairs x 64x64; `ncu --set full`) from profiles/{name}")
             break
     roofline = {"bound": "tensor", "kernel": kname, "issued_mma_tflops": issued, "issued_frac": issued / pk["bf16_tflops_sustained"],
                 "traffic_note": traffic_note,
