@@ -603,6 +603,7 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
     float4* const stg_own = reinterpret_cast<float4*>(stg + trow * PITCH);                          // row this thread stages
     const float* const srow = stg + (32 * (warp & 3) + (lane >> 2)) * PITCH + pc4 * 4;              // rows it reads back
     const long long map_px = (long long)p.out_h * p.out_w;
+    int staged_n0[2] = {-1, -1};
     int lt = 0;
     for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x, ++lt) {
       const int tile = p.reverse ? total_tiles - 1 - tile_i : tile_i;
@@ -613,7 +614,10 @@ conv_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ TmapPac
       const int sample = t / p.tiles_y;
       const int ox0 = tile_x * p.tile_w, oy0 = tile_y * p.tile_h, n0 = n_tile * BN;
       const int slot = lt & 1, use = lt >> 1;
-      {  // stage this tile's scale / shift (global-load latency off the per-panel critical path)
+      if (n0 != staged_n0[lt & 1]) {   // stage this tile's scale / shift (global-load latency off the per-panel critical path);
+        // a CTA usually keeps its N tile (M-major order, one or two N tiles): the copy staged two tiles ago is still valid,
+        // and short tiles (stem, patch convs) do not expose the load latency once per tile
+        staged_n0[lt & 1] = n0;
         const int et = tid - 64;                                  // 0..255
         if (et < BN) {
           const int n = n0 + et;
