@@ -94,6 +94,29 @@ def test_conv2d_matches_torch(KP, case):
     assert maxdiff(out.permute(0, 3, 1, 2), ref) < tol
 
 
+def test_conv2d_tile_order_does_not_change_results():
+    """accflow_conv_desc.tile_order only changes the order in which a launch walks its output tiles (L2 locality):
+    forward, reverse and the alternating default give bit-identical outputs (two N tiles, ragged map, several waves)."""
+    from accflow_b200 import _lib as L
+    from accflow_b200.engine import Kernels, PackedConv, View
+    K = Kernels(torch.device("cuda:0"), "fp16x2")
+    g = torch.Generator().manual_seed(77)
+    x = View(torch.randn(3, 70, 90, 128, generator=g).cuda())
+    w = torch.randn(256, 128, 3, 3, generator=g) / math.sqrt(128 * 9)
+    b = torch.randn(256, generator=g)
+    pc = PackedConv([dev(w)], [dev(b)], 1, (1, 1))
+    outs = []
+    for order in (L.TILES_FORWARD, L.TILES_REVERSE, L.TILES_AUTO, L.TILES_AUTO):
+        out = torch.zeros(3, 70, 90, 256, device="cuda")
+        K.conv(pc, [x], View(out), act=L.ACT_RELU, tile_order=order)
+        torch.cuda.synchronize()
+        outs.append(out)
+    ref = torch.relu(F.conv2d(x.t.permute(0, 3, 1, 2).cpu(), w, b, padding=1))
+    assert maxdiff(outs[0].permute(0, 3, 1, 2), ref) < 2e-5
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
 def test_conv2d_channel_slices_and_residual(KP):
     K, tol = KP
     """Sources / destinations that are channel slices of wider buffers (the cat-free layout)."""
